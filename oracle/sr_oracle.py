@@ -453,6 +453,21 @@ def swinir_flops(cfg: SwinIRCfg, h: int, w: int) -> float:
     return 2.0 * mac
 
 
+def swinir_gemm_flops(cfg: SwinIRCfg, h: int, w: int) -> float:
+    """Part of swinir_flops executed by the tensor-core GEMM kernel family of the CUDA path
+    (everything except the window attention products and the 1-channel input / output convs)."""
+    T, C = h * w, cfg.embed_dim
+    mac = T * sum(cfg.depths) * 2 * 64 * C + T * 9 * cfg.in_chans * C
+    if cfg.upsampler == "pixelshuffle":
+        mac += cfg.upscale ** 2 * T * 9 * 64 * cfg.in_chans
+    return swinir_flops(cfg, h, w) - 2.0 * mac
+
+
+def edsr_gemm_flops(cfg: EDSRCfg, h: int, w: int) -> float:
+    T, Fe = h * w, cfg.n_feats
+    return edsr_flops(cfg, h, w) - 2.0 * (T * 9 * cfg.in_chans * Fe + cfg.scale ** 2 * T * 9 * Fe * cfg.in_chans)
+
+
 def edsr_flops(cfg: EDSRCfg, h: int, w: int) -> float:
     T, Fe = h * w, cfg.n_feats
     mac = T * 9 * cfg.in_chans * Fe + T * (2 * cfg.n_resblocks + 1) * 9 * Fe * Fe

@@ -1,0 +1,79 @@
+"""Build libsrk.so (all CUDA kernels + the C ABI) for sm_100a with nvcc, in tree.
+
+    python -m sr_caco_2_b200.build [--force]
+
+The shared library is written next to this file (sr_caco_2_b200/libsrk.so); it is git-ignored
+but travels to the GPU box with the repository snapshot.
+"""
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libsrk.so")
+STAMP = os.path.join(HERE, "build", "stamp.txt")
+SOURCES = ["api.cu", "metrics.cu", "elementwise.cu", "attention.cu", "gemm_mma.cu",
+           "gemm_tc5.cu", "net.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "--use_fast_math=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default",
+              "-Xptxas", "-v", "--expt-relaxed-constexpr"]
+NVCC_FLAGS = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+
+
+def _digest():
+    h = hashlib.sha256()
+    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))]
+    files.append(os.path.join(os.path.dirname(HERE), "include", "srk.h"))
+    files.append(os.path.abspath(__file__))
+    for f in files:
+        with open(f, "rb") as fh:
+            h.update(f.encode())
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def nvcc_path():
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    return "nvcc"
+
+
+def build(force=False, verbose=False):
+    dig = _digest()
+    if not force and os.path.exists(OUT) and os.path.exists(STAMP):
+        if open(STAMP).read().strip() == dig:
+            return OUT
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    objs = []
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
+        cmd = [nvcc_path(), *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    log = []
+    failed = False
+    for src, pr in procs:
+        out, _ = pr.communicate()
+        log.append(f"==== {src}\n{out}")
+        if pr.returncode != 0:
+            failed = True
+    with open(os.path.join(HERE, "build", "nvcc.log"), "w") as fh:
+        fh.write("\n".join(log))
+    if failed:
+        sys.stderr.write("\n".join(log))
+        raise RuntimeError("nvcc failed; see sr_caco_2_b200/build/nvcc.log")
+    cmd = [nvcc_path(), "-shared", "-o", OUT, *objs, "-lcudart", "-lcuda"]
+    subprocess.check_call(cmd)
+    with open(STAMP, "w") as fh:
+        fh.write(dig)
+    if verbose:
+        print("\n".join(log))
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

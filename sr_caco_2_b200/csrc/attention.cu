@@ -1,0 +1,218 @@
+// Fused 8x8-window multi-head attention:  S = q k^T * scale + rel-pos bias + shift mask,
+// softmax (fp32, warp-shuffle row reductions), O = P v.   One CTA per window, the window's
+// q|k|v rows are staged once in shared memory (cp.async, coalesced 16 B chunks); each warp owns
+// a 16-query strip of one head at a time and keeps S / P / O in registers (mma.sync m16n8k16,
+// bf16 operands, fp32 accumulate); O overwrites the strip's own q slot and the CTA writes the
+// window's output rows back coalesced.
+//
+// Restates WindowAttention.forward (dlib/models/network_swinir.py:150-176): q*scale, q@k^T,
+// + relative_position_bias_table[relative_position_index] (:116-129, :156-162), + mask
+// (calculate_mask :260-285: -100 where the 3x3 region labels of the shifted frame differ),
+// softmax(-1), @ v, head merge (:176).  The attention matrix is never materialised in HBM.
+#include "common.cuh"
+
+namespace srk {
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0,
+                                         uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
+        "{%8,%9}, {%0,%1,%2,%3};\n"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src));
+}
+
+constexpr int ATT_THREADS = 256;
+
+// DP = padded head dim (16, 32, 48 or 64)
+template <int DP>
+__global__ void __launch_bounds__(ATT_THREADS)
+window_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int ldq,
+                        __nv_bfloat16* __restrict__ out, int ldo, const float* __restrict__ rel_table, int H, int W, int nH,
+                        float scale, int shift) {
+    extern __shared__ __align__(16) unsigned char att_smem[];
+    const int nq = 3 * nH * DP;                  // valid elements per qkv row (ldq >= nq)
+    const int RS = nq * 2 + 16;                  // padded smem row stride (bytes)
+    unsigned char* rows = att_smem;              // [64][RS]
+    float* tab = reinterpret_cast<float*>(att_smem + 64 * RS);   // [nH][225]
+    int* lab = reinterpret_cast<int*>(tab + nH * 225);            // [64]
+
+    const int nW = (H >> 3) * (W >> 3);
+    const int win_g = blockIdx.x;                // global window index (b * nW + win)
+    const int win = win_g % nW;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // ---- stage q|k|v of the window -------------------------------------------------------
+    const __nv_bfloat16* src = qkv + (size_t)win_g * 64 * ldq;
+    const int chunks_per_row = nq / 8;
+    const uint32_t rows_s = (uint32_t)__cvta_generic_to_shared(rows);
+    for (int i = tid; i < 64 * chunks_per_row; i += ATT_THREADS) {
+        const int r = i / chunks_per_row, c = i - r * chunks_per_row;
+        cp_async16(rows_s + r * RS + c * 16, src + (size_t)r * ldq + c * 8);
+    }
+    asm volatile("cp.async.commit_group;\n");
+    for (int i = tid; i < nH * 225; i += ATT_THREADS) tab[i] = __ldg(rel_table + i);
+    const int wpr = W >> 3;
+    const int wi = win / wpr, wj = win - wi * wpr;
+    const bool masked = shift > 0 && (wi == (H >> 3) - 1 || wj == wpr - 1);
+    if (tid < 64) lab[tid] = masked ? win_pos_label(win, tid, H, W, shift) : 0;
+    asm volatile("cp.async.wait_group 0;\n");
+    __syncthreads();
+
+    const int g = lane >> 2, t = lane & 3;
+    const int strip = warp & 3;                  // 16-query strip
+    const int r0 = strip * 16;
+    const float LOG2E = 1.4426950408889634f;
+
+    for (int h = warp >> 2; h < nH; h += ATT_THREADS / 128) {
+        const int qc = h * DP, kc = (nH + h) * DP, vc = (2 * nH + h) * DP;   // element columns
+        float s[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+        // ---- S = Q K^T -----------------------------------------------------------------
+#pragma unroll
+        for (int ks = 0; ks < DP / 16; ++ks) {
+            uint32_t a[4];
+            ldsm_x4(a, rows_s + (r0 + (lane & 7) + ((lane >> 3) & 1) * 8) * RS +
+                           (qc + ks * 16 + (lane >> 4) * 8) * 2);
+#pragma unroll
+            for (int np = 0; np < 4; ++np) {
+                uint32_t b[4];
+                ldsm_x4(b, rows_s + (np * 16 + (lane & 7) + (lane >> 4) * 8) * RS +
+                               (kc + ks * 16 + ((lane >> 3) & 1) * 8) * 2);
+                mma_bf16(s[2 * np], a, b[0], b[1]);
+                mma_bf16(s[2 * np + 1], a, b[2], b[3]);
+            }
+        }
+        // ---- + bias + mask, softmax --------------------------------------------------------
+        const float* tb = tab + h * 225;
+        const int i0 = r0 + g, i1 = r0 + g + 8;
+        const int l0 = lab[i0], l1 = lab[i1];
+        float m0 = -3.0e38f, m1 = -3.0e38f;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int j = nt * 8 + 2 * t + e;
+                const int lj = lab[j];
+                float v0 = s[nt][e] * scale + tb[rel_pos_index(i0, j)];
+                float v1 = s[nt][2 + e] * scale + tb[rel_pos_index(i1, j)];
+                if (masked) {
+                    if (l0 != lj) v0 += -100.f;
+                    if (l1 != lj) v1 += -100.f;
+                }
+                s[nt][e] = v0; s[nt][2 + e] = v1;
+                m0 = fmaxf(m0, v0); m1 = fmaxf(m1, v1);
+            }
+        }
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+        float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const float p0 = exp2f((s[nt][e] - m0) * LOG2E);
+                const float p1 = exp2f((s[nt][2 + e] - m1) * LOG2E);
+                s[nt][e] = p0; s[nt][2 + e] = p1;
+                sum0 += p0; sum1 += p1;
+            }
+        }
+        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+        sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+        sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+        const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
+        // ---- O = P V ---------------------------------------------------------------------
+        float o[DP / 8][4];
+#pragma unroll
+        for (int i = 0; i < DP / 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            uint32_t a[4];
+            a[0] = pack2(s[2 * kk][0] * inv0, s[2 * kk][1] * inv0, SRK_BF16);
+            a[1] = pack2(s[2 * kk][2] * inv1, s[2 * kk][3] * inv1, SRK_BF16);
+            a[2] = pack2(s[2 * kk + 1][0] * inv0, s[2 * kk + 1][1] * inv0, SRK_BF16);
+            a[3] = pack2(s[2 * kk + 1][2] * inv1, s[2 * kk + 1][3] * inv1, SRK_BF16);
+#pragma unroll
+            for (int nd = 0; nd < DP / 16; ++nd) {
+                uint32_t b[4];
+                ldsm_x4_trans(b, rows_s + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * RS +
+                                     (vc + nd * 16 + (lane >> 4) * 8) * 2);
+                mma_bf16(o[2 * nd], a, b[0], b[1]);
+                mma_bf16(o[2 * nd + 1], a, b[2], b[3]);
+            }
+        }
+        // ---- O overwrites this strip's own q slot (only this warp reads it, and it is done) --
+        __syncwarp();
+#pragma unroll
+        for (int nt = 0; nt < DP / 8; ++nt) {
+            const int col = qc + nt * 8 + 2 * t;
+            *reinterpret_cast<uint32_t*>(rows + (size_t)(r0 + g) * RS + col * 2) =
+                pack2(o[nt][0], o[nt][1], SRK_BF16);
+            *reinterpret_cast<uint32_t*>(rows + (size_t)(r0 + g + 8) * RS + col * 2) =
+                pack2(o[nt][2], o[nt][3], SRK_BF16);
+        }
+    }
+    __syncthreads();
+    // ---- write the window's output rows (coalesced 16 B chunks, pad columns zeroed) -------------
+    __nv_bfloat16* dst = out + (size_t)win_g * 64 * ldo;
+    const int oc = ldo / 8, valid = nH * DP / 8;
+    for (int i = tid; i < 64 * oc; i += ATT_THREADS) {
+        const int r = i / oc, c = i - r * oc;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (c < valid) v = *reinterpret_cast<const uint4*>(rows + (size_t)r * RS + c * 16);
+        *reinterpret_cast<uint4*>(dst + (size_t)r * ldo + c * 8) = v;
+    }
+}
+
+}  // namespace srk
+
+using namespace srk;
+
+extern "C" int srk_window_attention(const void* qkv, int ldq, void* out, int ldo,
+                                    const float* rel_table, int nB, int H, int W, int nH, int dp, float scale, int shift,
+                                    void* stream) {
+    SRK_REQUIRE(qkv && out && rel_table, "window_attention: null pointer");
+    SRK_REQUIRE(nB > 0 && H > 0 && W > 0 && H % 8 == 0 && W % 8 == 0,
+                "window_attention: H, W must be positive multiples of the window size 8");
+    SRK_REQUIRE(shift == 0 || shift == 4, "window_attention: shift must be 0 or 4");
+    SRK_REQUIRE(dp == 16 || dp == 32 || dp == 48 || dp == 64,
+                "window_attention: padded head dim %d not in {16,32,48,64}", dp);
+    SRK_REQUIRE(nH >= 1 && ldo % 8 == 0 && ldo >= nH * dp, "window_attention: bad nH/ldo");
+    const int nq = 3 * nH * dp;
+    SRK_REQUIRE(ldq % 8 == 0 && ldq >= nq, "window_attention: bad ldq");
+    const size_t smem = (size_t)64 * (nq * 2 + 16) + (size_t)nH * 225 * 4 + 64 * 4;
+    SRK_REQUIRE(smem <= 227 * 1024, "window_attention: window does not fit shared memory");
+    const int grid = nB * (H / 8) * (W / 8);
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfScope ps(SRK_PROF_ATTENTION, stream);
+#define LAUNCH(D)                                                                             \
+    do {                                                                                      \
+        SRK_CUDA(cudaFuncSetAttribute(window_attention_kernel<D>,                             \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        window_attention_kernel<D><<<grid, ATT_THREADS, smem, st>>>(                          \
+            (const __nv_bfloat16*)qkv, ldq, (__nv_bfloat16*)out, ldo, rel_table, H, W, nH, scale,  \
+            shift);                                                                           \
+    } while (0)
+    if (dp == 16) LAUNCH(16);
+    else if (dp == 32) LAUNCH(32);
+    else if (dp == 48) LAUNCH(48);
+    else LAUNCH(64);
+#undef LAUNCH
+    SRK_LAUNCH_CHECK("window_attention_kernel");
+    return 0;
+}

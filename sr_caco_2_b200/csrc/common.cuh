@@ -1,0 +1,132 @@
+// Shared helpers for libsrk (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/srk.h"
+
+namespace srk {
+
+// ---- error plumbing -------------------------------------------------------------------
+extern thread_local char g_err[512];
+extern thread_local long long g_launches;
+int fail(int code, const char* fmt, ...);
+
+#define SRK_REQUIRE(cond, ...)                                        \
+    do {                                                              \
+        if (!(cond)) return ::srk::fail(SRK_ERR_INVALID, __VA_ARGS__); \
+    } while (0)
+
+#define SRK_CUDA(expr)                                                               \
+    do {                                                                             \
+        cudaError_t e__ = (expr);                                                    \
+        if (e__ != cudaSuccess)                                                      \
+            return ::srk::fail(SRK_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,        \
+                               cudaGetErrorString(e__), __FILE__, __LINE__);         \
+    } while (0)
+
+#define SRK_LAUNCH_CHECK(name)                                                       \
+    do {                                                                             \
+        ::srk::g_launches++;                                                         \
+        cudaError_t e__ = cudaGetLastError();                                        \
+        if (e__ != cudaSuccess)                                                      \
+            return ::srk::fail(SRK_ERR_CUDA, "launch of %s failed: %s", name,        \
+                               cudaGetErrorString(e__));                             \
+    } while (0)
+
+// ---- optional event timing per kernel family (see srk_profile) ---------------------------
+extern thread_local bool g_prof_on;
+void prof_begin(int family, cudaStream_t st);
+void prof_end(cudaStream_t st);
+struct ProfScope {
+    cudaStream_t st; bool on;
+    ProfScope(int family, void* stream) : st((cudaStream_t)stream), on(g_prof_on) { if (on) prof_begin(family, st); }
+    ~ProfScope() { if (on) prof_end(st); }
+};
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+// ---- 16-bit conversions ----------------------------------------------------------------
+__device__ __forceinline__ uint16_t f2h16(float v, int dtype) {
+    if (dtype == SRK_BF16) {
+        __nv_bfloat16 b = __float2bfloat16_rn(v);
+        return *reinterpret_cast<uint16_t*>(&b);
+    }
+    // saturating fp16 (finite): conv operands are the unnormalised residual stream
+    v = fminf(fmaxf(v, -65504.f), 65504.f);
+    __half h = __float2half_rn(v);
+    return *reinterpret_cast<uint16_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b, int dtype) {
+    return (uint32_t)f2h16(a, dtype) | ((uint32_t)f2h16(b, dtype) << 16);
+}
+__device__ __forceinline__ float h162f(uint16_t u, int dtype) {
+    if (dtype == SRK_BF16) return __uint_as_float(((uint32_t)u) << 16);
+    __half h = *reinterpret_cast<__half*>(&u);
+    return __half2float(h);
+}
+
+// ---- index maps (the single definition every kernel uses) -----------------------------------
+// window-major position m (within one image of H x W tokens, 8x8 windows, cyclic shift s)
+// -> token id h*W + w of the un-shifted frame.   roll(-s) + window_partition.
+__device__ __host__ __forceinline__ int win_pos_to_token(int m, int H, int W, int shift) {
+    const int wpr = W >> 3;
+    const int win = m >> 6, pos = m & 63;
+    const int wi = win / wpr, wj = win - wi * wpr;
+    int h = (wi << 3) + (pos >> 3) + shift;
+    int w = (wj << 3) + (pos & 7) + shift;
+    if (h >= H) h -= H;
+    if (w >= W) w -= W;
+    return h * W + w;
+}
+// inverse: token id -> window-major position under cyclic shift s (used when an epilogue
+// writes rows for the NEXT block's shifted windows)
+__device__ __host__ __forceinline__ int token_to_win_pos(int tok, int H, int W, int shift) {
+    int h = tok / W, w = tok - h * W;
+    h -= shift; w -= shift;
+    if (h < 0) h += H;
+    if (w < 0) w += W;
+    return (((h >> 3) * (W >> 3) + (w >> 3)) << 6) + ((h & 7) << 3) + (w & 7);
+}
+// region label of a coordinate of the shifted frame along one axis (calculate_mask)
+__device__ __host__ __forceinline__ int region_label(int c, int n, int shift) {
+    return c < n - 8 ? 0 : (c < n - shift ? 1 : 2);
+}
+// label of window-major position (win, pos) in the shifted frame
+__device__ __host__ __forceinline__ int win_pos_label(int win, int pos, int H, int W, int shift) {
+    const int wpr = W >> 3;
+    const int wi = win / wpr, wj = win - wi * wpr;
+    return region_label((wi << 3) + (pos >> 3), H, shift) * 3 +
+           region_label((wj << 3) + (pos & 7), W, shift);
+}
+// relative position index for window-local positions i (query), j (key), ws = 8
+__device__ __host__ __forceinline__ int rel_pos_index(int i, int j) {
+    return ((i >> 3) - (j >> 3) + 7) * 15 + ((i & 7) - (j & 7) + 7);
+}
+
+__device__ __forceinline__ float gelu_erf(float x) {
+    return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == SRK_ACT_GELU) return gelu_erf(v);
+    if (act == SRK_ACT_LRELU) return v > 0.f ? v : 0.01f * v;
+    if (act == SRK_ACT_RELU) return fmaxf(v, 0.f);
+    return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// engine entry points (one per translation unit)
+int gemm_mma_sync(const srk_gemm_args* g, cudaStream_t st);
+int gemm_tcgen05(const srk_gemm_args* g, cudaStream_t st);
+int validate_gemm(const srk_gemm_args* g);
+
+}  // namespace srk

@@ -1,0 +1,377 @@
+// Single-pass PSNR / MSE / NRMSE / SSIM / PSNR_Y kernel (HBM bound: reads E and H once).
+//
+// Restates, for 1-channel images, dlib/utils/utils_image.py:369-372 (uint8 quantisation),
+// :843-891 (PSNR), :894-934 (MSE), :937-1007 (NRMSE), :1010-1198 (SSIM, 11x11 sigma 1.5 valid
+// Gaussian filter, fp32) and the PSNR_Y of dlib/utils/utils_trainer.py:1005-1012, for the full
+// image and up to 8 ROI thresholds (roi = H8 >= th, utils_trainer.py:986) in the same pass.
+//
+// One CTA owns a 32x32 tile of the border-cropped image: it loads the 42x42 halo tile of E and
+// H once (coalesced rows), accumulates the squared-error / min / max terms for the pixels it
+// owns while loading, runs the separable Gaussian (horizontal then vertical) in shared memory
+// for the five SSIM moments, and reduces with warp shuffles to one fp64 atomic per quantity.
+#include "common.cuh"
+#include <math.h>
+
+namespace srk {
+
+constexpr int MT = 32;            // tile of SSIM outputs / owned pixels
+constexpr int MH = MT + 10;       // halo tile
+constexpr int MAXV = 1 + SRK_MAX_ROI_THS;
+constexpr int NTHREADS = 256;
+
+// per (image, variant) accumulator record
+struct MetAcc {
+    double sse, sse_y, ssim;
+    unsigned long long cnt, scnt;
+    int mn_key, mx_key;     // ordered-int keys of min/max of y*roi
+};
+struct MetImg {
+    int mn_all_key;         // min over the cropped target
+    int range_bad;          // any input outside [0,255] (after optional quantisation: never)
+};
+
+__device__ __forceinline__ int f2key(float f) {
+    int b = __float_as_int(f);
+    return b >= 0 ? b : b ^ 0x7fffffff;
+}
+__device__ __forceinline__ float key2f(int k) {
+    return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff);
+}
+
+__device__ __forceinline__ float quant255(float v) {
+    // (x.clamp(0,1)*255).round().clamp(0,255) ; rintf = round half to even like torch.round
+    v = fminf(fmaxf(v, 0.f), 1.f);
+    return fminf(fmaxf(rintf(__fmul_rn(v, 255.f)), 0.f), 255.f);
+}
+
+// Y of a gray value replicated to RGB, same fp32 operation order as mb_gpu_rgb2ycbcr on
+// (v/255) followed by *255 (utils_trainer.py:1005-1012); no fused multiply-adds.
+__device__ __forceinline__ float luma255(float v) {
+    float t = __fmul_rn(__fdiv_rn(v, 255.f), 255.f);
+    float s = __fadd_rn(__fadd_rn(__fmul_rn(65.481f, t), __fmul_rn(128.553f, t)),
+                        __fmul_rn(24.966f, t));
+    float y = __fadd_rn(__fdiv_rn(s, 255.f), 16.f);
+    float o = fminf(fmaxf(__fdiv_rn(y, 255.f), 0.f), 1.f);
+    return __fmul_rn(o, 255.f);
+}
+
+__constant__ float c_gauss[11];
+
+template <typename T>
+__device__ __forceinline__ T block_reduce_sum(T v, T* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    T r = 0;
+    if (wid == 0) {
+        r = lane < NTHREADS / 32 ? red[lane] : T(0);
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    }
+    return r;  // valid on thread 0
+}
+
+__device__ __forceinline__ int block_reduce_min(int v, int* red, bool is_max) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        int t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = is_max ? max(v, t) : min(v, t);
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    int r = v;
+    if (wid == 0) {
+        r = red[lane < NTHREADS / 32 ? lane : 0];
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            int t = __shfl_xor_sync(0xffffffffu, r, o);
+            r = is_max ? max(r, t) : min(r, t);
+        }
+    }
+    return r;
+}
+
+struct MetParams {
+    const float* E; const float* H; const float* roi;
+    int B, Hpx, Wpx, border, quantize, n_var;   // n_var = 1 + n_ths (or 1 with external roi)
+    float ths[SRK_MAX_ROI_THS];
+    MetAcc* acc; MetImg* img;
+};
+
+template <int NV, bool EXT_ROI>
+__global__ void __launch_bounds__(NTHREADS)
+metrics_tile_kernel(const MetParams p) {
+    extern __shared__ __align__(16) unsigned char met_smem[];
+    typedef float TileRow[MH + 1];
+    typedef float HbRow[MT + 1];
+    TileRow* sx = reinterpret_cast<TileRow*>(met_smem);            // E/255      [MH][MH+1]
+    TileRow* sy = sx + MH;                                          // H/255
+    TileRow* sq = sy + MH;                                          // H in [0,255] or external roi
+    HbRow (*hb)[MH] = reinterpret_cast<HbRow (*)[MH]>(sq + MH);     // [5][MH][MT+1] moments
+    __shared__ double red_d[NTHREADS / 32];
+    __shared__ unsigned long long red_u[NTHREADS / 32];
+    __shared__ int red_i[NTHREADS / 32];
+
+    const int b = blockIdx.z;
+    const int Hc = p.Hpx - 2 * p.border, Wc = p.Wpx - 2 * p.border;
+    const int r0 = blockIdx.y * MT, c0 = blockIdx.x * MT;
+    const float* Eb = p.E + (size_t)b * p.Hpx * p.Wpx;
+    const float* Hb = p.H + (size_t)b * p.Hpx * p.Wpx;
+    const float* Rb = EXT_ROI ? p.roi + (size_t)b * p.Hpx * p.Wpx : nullptr;
+
+    double sse[NV], ssey[NV];
+    unsigned int cnt[NV];
+    int mnk[NV], mxk[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        sse[v] = 0.0; ssey[v] = 0.0; cnt[v] = 0;
+        mnk[v] = 0x7fffffff; mxk[v] = (int)0x80000000;
+    }
+    int mn_all = 0x7fffffff;
+    int bad = 0;
+
+    // ---- load halo tile, accumulate owned-pixel terms -------------------------------------
+    for (int i = threadIdx.x; i < MH * MH; i += NTHREADS) {
+        const int lr = i / MH, lc = i - lr * MH;
+        const int r = r0 + lr, c = c0 + lc;
+        float e = 0.f, h = 0.f, w = 0.f;
+        if (r < Hc && c < Wc) {
+            const size_t off = (size_t)(r + p.border) * p.Wpx + (c + p.border);
+            e = __ldg(Eb + off);
+            h = __ldg(Hb + off);
+            if (p.quantize) { e = quant255(e); h = quant255(h); }
+            if (EXT_ROI) w = __ldg(Rb + off);
+            if (!(e >= 0.f && e <= 255.f) || !(h >= 0.f && h <= 255.f)) bad = 1;
+            if (lr < MT && lc < MT) {           // owned pixel
+                const double d = (double)e - (double)h;
+                const double dy = (double)luma255(e) - (double)luma255(h);
+                mn_all = min(mn_all, f2key(h));
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    float wv;
+                    if (EXT_ROI) wv = w;
+                    else wv = (v == 0) ? 1.f : (h >= p.ths[v - 1 < 0 ? 0 : v - 1] ? 1.f : 0.f);
+                    const double dw = d * (double)wv, dyw = dy * (double)wv;
+                    sse[v] += dw * dw;
+                    ssey[v] += dyw * dyw;
+                    cnt[v] += (wv != 0.f) ? 1u : 0u;
+                    const int k = f2key(h * wv);
+                    mnk[v] = min(mnk[v], k);
+                    mxk[v] = max(mxk[v], k);
+                }
+            }
+        }
+        sx[lr][lc] = __fdiv_rn(e, 255.f);
+        sy[lr][lc] = __fdiv_rn(h, 255.f);
+        sq[lr][lc] = EXT_ROI ? w : h;
+    }
+    __syncthreads();
+
+    // ---- horizontal Gaussian of x, y, x*x, y*y, x*y ------------------------------------------
+    for (int i = threadIdx.x; i < MH * MT; i += NTHREADS) {
+        const int lr = i / MT, lc = i - lr * MT;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+#pragma unroll
+        for (int t = 0; t < 11; ++t) {
+            const float g = c_gauss[t];
+            const float x = sx[lr][lc + t], y = sy[lr][lc + t];
+            a0 = fmaf(g, x, a0); a1 = fmaf(g, y, a1);
+            a2 = fmaf(g, x * x, a2); a3 = fmaf(g, y * y, a3); a4 = fmaf(g, x * y, a4);
+        }
+        hb[0][lr][lc] = a0; hb[1][lr][lc] = a1; hb[2][lr][lc] = a2;
+        hb[3][lr][lc] = a3; hb[4][lr][lc] = a4;
+    }
+    __syncthreads();
+
+    // ---- vertical Gaussian + SSIM map ---------------------------------------------------------
+    float ssum[NV];
+    unsigned int scnt[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) { ssum[v] = 0.f; scnt[v] = 0; }
+    const int mapH = Hc - 10, mapW = Wc - 10;
+    for (int i = threadIdx.x; i < MT * MT; i += NTHREADS) {
+        const int lr = i / MT, lc = i - lr * MT;
+        if (r0 + lr >= mapH || c0 + lc >= mapW) continue;
+        float mx = 0.f, my = 0.f, xx = 0.f, yy = 0.f, xy = 0.f;
+#pragma unroll
+        for (int t = 0; t < 11; ++t) {
+            const float g = c_gauss[t];
+            mx = fmaf(g, hb[0][lr + t][lc], mx); my = fmaf(g, hb[1][lr + t][lc], my);
+            xx = fmaf(g, hb[2][lr + t][lc], xx); yy = fmaf(g, hb[3][lr + t][lc], yy);
+            xy = fmaf(g, hb[4][lr + t][lc], xy);
+        }
+        const float c1 = 1e-4f, c2 = 9e-4f;
+        const float mxx = mx * mx, myy = my * my, mxy = mx * my;
+        const float sxx = xx - mxx, syy = yy - myy, sxy = xy - mxy;
+        const float cs = (2.f * sxy + c2) / (sxx + syy + c2);
+        const float ss = ((2.f * mxy + c1) / (mxx + myy + c1)) * cs;
+        const float q = sq[lr + 5][lc + 5];      // ROI is cropped by the filter radius
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            float wv;
+            if (EXT_ROI) wv = q;
+            else wv = (v == 0) ? 1.f : (q >= p.ths[v - 1 < 0 ? 0 : v - 1] ? 1.f : 0.f);
+            ssum[v] += ss * wv;
+            scnt[v] += (wv != 0.f) ? 1u : 0u;
+        }
+    }
+
+    // ---- block reduction, one atomic per quantity -------------------------------------------
+    MetAcc* acc = p.acc + (size_t)b * NV;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        double t0 = block_reduce_sum<double>(sse[v], red_d);
+        if (threadIdx.x == 0) atomicAdd(&acc[v].sse, t0);
+        double t1 = block_reduce_sum<double>(ssey[v], red_d);
+        if (threadIdx.x == 0) atomicAdd(&acc[v].sse_y, t1);
+        double t2 = block_reduce_sum<double>((double)ssum[v], red_d);
+        if (threadIdx.x == 0) atomicAdd(&acc[v].ssim, t2);
+        unsigned long long t3 = block_reduce_sum<unsigned long long>(cnt[v], red_u);
+        if (threadIdx.x == 0) atomicAdd(&acc[v].cnt, t3);
+        unsigned long long t4 = block_reduce_sum<unsigned long long>(scnt[v], red_u);
+        if (threadIdx.x == 0) atomicAdd(&acc[v].scnt, t4);
+        int k0 = block_reduce_min(mnk[v], red_i, false);
+        if (threadIdx.x == 0) atomicMin(&acc[v].mn_key, k0);
+        int k1 = block_reduce_min(mxk[v], red_i, true);
+        if (threadIdx.x == 0) atomicMax(&acc[v].mx_key, k1);
+    }
+    int k2 = block_reduce_min(mn_all, red_i, false);
+    if (threadIdx.x == 0) atomicMin(&p.img[b].mn_all_key, k2);
+    int k3 = block_reduce_min(bad, red_i, true);
+    if (threadIdx.x == 0 && k3) atomicOr(&p.img[b].range_bad, 1);
+}
+
+__global__ void metrics_init_kernel(MetAcc* acc, MetImg* img, int B, int NV) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B * NV) {
+        acc[i].sse = 0.0; acc[i].sse_y = 0.0; acc[i].ssim = 0.0;
+        acc[i].cnt = 0ull; acc[i].scnt = 0ull;
+        acc[i].mn_key = 0x7fffffff; acc[i].mx_key = (int)0x80000000;
+    }
+    if (i < B) { img[i].mn_all_key = 0x7fffffff; img[i].range_bad = 0; }
+}
+
+__global__ void metrics_finalize_kernel(const MetAcc* acc, const MetImg* img, int B, int NV,
+                                        int Hc, int Wc, int ext_roi, double* out,
+                                        int32_t* flags) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * NV) return;
+    const int b = i / NV, v = i - b * NV;
+    const MetAcc a = acc[i];
+    const bool full = (v == 0) && !ext_roi;
+    double n = full ? (double)Hc * (double)Wc : (double)a.cnt;
+    if (n == 0.0) n = 1.0;                                   // empty ROI
+    const double mse = a.sse / n, mse_y = a.sse_y / n;
+    const double psnr = 20.0 * log10(255.0 / sqrt(fmax(mse, 1e-45)));
+    const double psnr_y = 20.0 * log10(255.0 / sqrt(fmax(mse_y, 1e-45)));
+    double mn = (double)key2f(a.mn_key), mx = (double)key2f(a.mx_key);
+    if (!full) mn = fmax(mn, (double)key2f(img[b].mn_all_key));
+    double den = mx - mn;
+    if (den == 0.0) den = 1.0;
+    const double nrmse = sqrt(mse) / den;
+    double sn = full ? (double)(Hc - 10) * (double)(Wc - 10) : (double)a.scnt;
+    if (sn == 0.0) sn = 1.0;
+    // the reference keeps SSIM in fp32
+    const double ssim = (double)(float)(a.ssim / sn);
+    double* o = out + (size_t)i * SRK_MET_N;
+    o[SRK_MET_PSNR] = psnr; o[SRK_MET_MSE] = mse; o[SRK_MET_NRMSE] = nrmse;
+    o[SRK_MET_SSIM] = ssim; o[SRK_MET_PSNR_Y] = psnr_y;
+    int f = 0;
+    const double vals[5] = {psnr, mse, nrmse, ssim, psnr_y};
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        if (!isfinite(vals[k])) f |= 1;
+        if (vals[k] < 0.0) f |= 2;
+    }
+    if (img[b].range_bad) f |= 4;
+    if (f) atomicOr(&flags[b], f);
+}
+
+static int upload_gauss() {
+    static bool done[64] = {false};
+    int dev = 0;
+    SRK_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && done[dev]) return 0;
+    // utils_image.py:1102-1117: 2-D exp(-(x^2+y^2)/(2 sigma^2)) / sum  ==  outer(g1, g1)
+    float e[11], s = 0.f, g[11];
+    for (int i = 0; i < 11; ++i) { float c = (float)i - 5.f; e[i] = expf(-(c * c) / (2.f * 1.5f * 1.5f)); s += e[i]; }
+    for (int i = 0; i < 11; ++i) g[i] = e[i] / s;
+    SRK_CUDA(cudaMemcpyToSymbol(c_gauss, g, sizeof(g)));
+    if (dev < 64) done[dev] = true;
+    return 0;
+}
+
+constexpr size_t MET_SMEM = sizeof(float) * (3 * MH * (MH + 1) + 5 * MH * (MT + 1));
+
+template <bool EXT>
+static void launch_tile(int NV, dim3 grid, cudaStream_t st, const MetParams& p) {
+    switch (NV) {
+#define C(n) case n:                                                                          \
+        cudaFuncSetAttribute(metrics_tile_kernel<n, EXT>,                                     \
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MET_SMEM);     \
+        metrics_tile_kernel<n, EXT><<<grid, NTHREADS, MET_SMEM, st>>>(p); break;
+        C(1) C(2) C(3) C(4) C(5) C(6) C(7) C(8) C(9)
+#undef C
+    }
+}
+
+static int run_metrics(const float* E, const float* H, const float* roi, int B, int Hpx, int Wpx,
+                       int border, int quantize, const int* roi_ths, int n_ths, double* out,
+                       int32_t* flags, void* scratch, cudaStream_t st) {
+    SRK_REQUIRE(E && H && out && flags && scratch, "metrics: null pointer");
+    SRK_REQUIRE(B > 0 && Hpx > 0 && Wpx > 0 && border >= 0, "metrics: bad shape");
+    SRK_REQUIRE(n_ths >= 0 && n_ths <= SRK_MAX_ROI_THS, "metrics: n_ths must be in [0,%d]",
+                SRK_MAX_ROI_THS);
+    const int Hc = Hpx - 2 * border, Wc = Wpx - 2 * border;
+    // utils_image.py:1044-1047: the 11x11 window must fit
+    SRK_REQUIRE(Hc >= 11 && Wc >= 11,
+                "metrics: kernel size can't be greater than actual input size (%dx%d after border %d)",
+                Hc, Wc, border);
+    if (int rc = upload_gauss()) return rc;
+    const int NV = roi ? 1 : 1 + n_ths;
+    MetParams p{};
+    p.E = E; p.H = H; p.roi = roi; p.B = B; p.Hpx = Hpx; p.Wpx = Wpx; p.border = border;
+    p.quantize = quantize; p.n_var = NV;
+    for (int i = 0; i < n_ths; ++i) p.ths[i] = (float)roi_ths[i];
+    p.acc = reinterpret_cast<MetAcc*>(scratch);
+    p.img = reinterpret_cast<MetImg*>(reinterpret_cast<char*>(scratch) +
+                                      align_up(sizeof(MetAcc) * (size_t)B * NV, 16));
+    ProfScope ps(SRK_PROF_METRICS, st);
+    SRK_CUDA(cudaMemsetAsync(flags, 0, sizeof(int32_t) * B, st));
+    metrics_init_kernel<<<ceil_div((long long)B * NV, 128), 128, 0, st>>>(p.acc, p.img, B, NV);
+    SRK_LAUNCH_CHECK("metrics_init_kernel");
+    dim3 grid(ceil_div(Wc, MT), ceil_div(Hc, MT), B);
+    if (roi) launch_tile<true>(NV, grid, st, p); else launch_tile<false>(NV, grid, st, p);
+    SRK_LAUNCH_CHECK("metrics_tile_kernel");
+    metrics_finalize_kernel<<<ceil_div((long long)B * NV, 128), 128, 0, st>>>(
+        p.acc, p.img, B, NV, Hc, Wc, roi ? 1 : 0, out, flags);
+    SRK_LAUNCH_CHECK("metrics_finalize_kernel");
+    return 0;
+}
+
+}  // namespace srk
+
+extern "C" size_t srk_metrics_scratch_bytes(int B, int n_ths) {
+    const int NV = 1 + (n_ths < 0 ? 0 : n_ths);
+    return srk::align_up(sizeof(srk::MetAcc) * (size_t)B * NV, 16) + sizeof(srk::MetImg) * (size_t)B + 64;
+}
+
+extern "C" int srk_metrics(const float* E, const float* H, int B, int Hpx, int Wpx, int border,
+                           int quantize, const int* roi_ths, int n_ths, double* out,
+                           int32_t* flags, void* scratch, void* stream) {
+    return srk::run_metrics(E, H, nullptr, B, Hpx, Wpx, border, quantize, roi_ths, n_ths, out,
+                            flags, scratch, (cudaStream_t)stream);
+}
+
+extern "C" int srk_metrics_roi(const float* E, const float* H, const float* roi, int B, int Hpx,
+                               int Wpx, int border, int quantize, double* out, int32_t* flags,
+                               void* scratch, void* stream) {
+    if (!roi) return srk::fail(SRK_ERR_INVALID, "metrics_roi: null roi");
+    return srk::run_metrics(E, H, roi, B, Hpx, Wpx, border, quantize, nullptr, 0, out, flags,
+                            scratch, (cudaStream_t)stream);
+}

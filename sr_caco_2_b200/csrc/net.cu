@@ -1,0 +1,288 @@
+// Network drivers: the launch sequences of SwinIR.forward (dlib/models/network_swinir.py:930-970)
+// and of the EDSR-baseline assembled from dlib/models/network_nlsn.py:72-128,325-369, over
+// token-major (NHWC) activations with an fp32 residual stream.
+#include "common.cuh"
+#include <vector>
+
+namespace srk {
+
+struct Bump {
+    char* base; size_t off, cap;
+    void* take(size_t bytes) {
+        off = align_up(off, 256);
+        void* p = base ? base + off : nullptr;
+        off += bytes;
+        return p;
+    }
+};
+
+static inline int pad8(int v) { return (v + 7) / 8 * 8; }
+
+struct SwinBufs {
+    float *F0, *XA, *XB;
+    void *A16, *QKV, *AO, *HID, *Y1, *U[5];
+    int nq_p;
+};
+
+static size_t swin_layout(const srk_swinir_plan* p, int B, int H, int W, char* base, SwinBufs* b) {
+    Bump a{base, 0, 0};
+    const size_t M = (size_t)B * H * W;
+    int max_heads = 1;
+    int nblk = 0;
+    for (int l = 0; l < p->n_layers; ++l) nblk += p->depths[l];
+    for (int i = 0; i < nblk; ++i) max_heads = p->stbs[i].num_heads > max_heads ? p->stbs[i].num_heads : max_heads;
+    b->nq_p = (int)align_up((size_t)3 * max_heads * p->dp, 64);
+    b->F0 = (float*)a.take(M * p->Cp * 4);
+    b->XA = (float*)a.take(M * p->Cp * 4);
+    b->XB = (float*)a.take(M * p->Cp * 4);
+    b->A16 = a.take(M * p->Cp * 2);
+    b->QKV = a.take(M * b->nq_p * 2);
+    b->AO = a.take(M * p->ao_p * 2);
+    b->HID = a.take(M * p->hid_p * 2);
+    b->Y1 = a.take(M * p->Cp * 2);
+    for (int k = 0; k < 5; ++k) b->U[k] = nullptr;
+    if (p->upsampler == SRK_UPSAMPLER_PIXELSHUFFLE) {
+        size_t m = M;
+        for (int k = 0; k <= p->n_upsample; ++k) { b->U[k] = a.take(m * 64 * 2); m *= 4; }
+    }
+    return align_up(a.off, 256);
+}
+
+static int check_swin_plan(const srk_swinir_plan* p) {
+    SRK_REQUIRE(p && p->depths && p->stbs && p->rstb_convs, "swinir: null plan");
+    if (p->in_chans != 1) return fail(SRK_ERR_UNSUPPORTED, "swinir: only in_chans == 1 is built (got %d)", p->in_chans);
+    if (p->window_size != 8) return fail(SRK_ERR_UNSUPPORTED, "swinir: only window_size == 8 is built (got %d)", p->window_size);
+    if (p->upsampler == SRK_UPSAMPLER_PIXELSHUFFLE) {
+        SRK_REQUIRE(p->n_upsample >= 0 && p->n_upsample <= 4 && (1 << p->n_upsample) == p->upscale,
+                    "swinir: pixelshuffle needs upscale = 2^n (n <= 4)");
+    } else if (p->upsampler == SRK_UPSAMPLER_PIXELSHUFFLEDIRECT) {
+        SRK_REQUIRE(p->n_upsample == 1 && p->upscale * p->upscale <= 64, "swinir: direct upsampler needs scale <= 8");
+    } else {
+        return fail(SRK_ERR_UNSUPPORTED, "swinir: upsampler %d not built", p->upsampler);
+    }
+    SRK_REQUIRE(p->Cp % 64 == 0 && p->Cp >= p->embed_dim && p->hid_p % 64 == 0 && p->hid_p >= p->hidden_dim &&
+                p->dp % 16 == 0 && p->ao_p % 64 == 0 && p->embed_dim % 4 == 0, "swinir: bad padded dims");
+    return 0;
+}
+
+}  // namespace srk
+
+using namespace srk;
+
+extern "C" size_t srk_swinir_workspace_bytes(const srk_swinir_plan* p, int B, int h, int w) {
+    if (!p || B <= 0 || h <= 0 || w <= 0) return 0;
+    SwinBufs b;
+    return swin_layout(p, B, pad8(h), pad8(w), nullptr, &b);
+}
+
+#define TRY(expr) do { int rc__ = (expr); if (rc__) return rc__; } while (0)
+
+extern "C" int srk_swinir_forward(const srk_swinir_plan* p, const float* x, float* y, int B, int h,
+                                  int w, void* workspace, size_t workspace_bytes, void* stream) {
+    TRY(check_swin_plan(p));
+    SRK_REQUIRE(x && y && workspace, "swinir: null pointer");
+    SRK_REQUIRE(B > 0 && h > 0 && w > 0, "swinir: bad input shape");
+    const int H = pad8(h), W = pad8(w);
+    SRK_REQUIRE(H - h < h && W - w < w, "swinir: reflect padding needs h, w > pad");
+    SwinBufs b;
+    const size_t need = swin_layout(p, B, H, W, (char*)workspace, &b);
+    if (need > workspace_bytes) return fail(SRK_ERR_WORKSPACE, "swinir: workspace %zu < %zu bytes", workspace_bytes, need);
+    const int M = B * H * W, C = p->embed_dim, Cp = p->Cp;
+    const int ldt = p->linear_dtype, cdt = p->conv_dtype;
+    const bool fuse_ln = srk_get_engine() == SRK_ENGINE_TCGEN05 && Cp <= 256;
+    const float eps = 1e-5f;
+
+    auto conv_gemm = [&](const void* A, int lda, int Hh, int Ww, const srk_conv_params& cv) {
+        srk_gemm_args g{};
+        g.A = A; g.a_mode = SRK_A_CONV3X3; g.lda = lda; g.nB = B; g.H = Hh; g.W = Ww;
+        g.Wt = cv.w; g.M = B * Hh * Ww; g.N = cv.n_p; g.K = 9 * lda; g.dtype = cdt;
+        g.bias = cv.b; g.act = SRK_ACT_NONE; g.res_scale = 1.f; g.win_shift = -1; g.ln_win_shift = -1;
+        g.out16_dtype = cdt;
+        return g;
+    };
+    auto lin_gemm = [&](const void* A, int lda, const void* Wt, const float* bias, int N, int K) {
+        srk_gemm_args g{};
+        g.A = A; g.a_mode = SRK_A_ROWS; g.lda = lda; g.nB = B; g.H = H; g.W = W;
+        g.Wt = Wt; g.M = M; g.N = N; g.K = K; g.dtype = ldt; g.bias = bias; g.act = SRK_ACT_NONE;
+        g.res_scale = 1.f; g.win_shift = -1; g.ln_win_shift = -1; g.out16_dtype = ldt;
+        return g;
+    };
+
+    // conv_first (+ reflect pad + input scaling), patch_embed.norm
+    TRY(srk_conv_in(x, B, h, w, H, W, p->img_range, p->conv_first_w, p->conv_first_b, C, b.F0, Cp,
+                    nullptr, 0, 0, stream));
+    TRY(srk_layernorm(b.F0, Cp, M, C, p->pe_norm_g, p->pe_norm_b, eps, nullptr, 0, 0, b.XA, H, W, -1, stream));
+
+    int blk = 0;
+    bool a16_ready = false;      // A16 already holds LN1 of the next block (fused epilogue)
+    for (int l = 0; l < p->n_layers; ++l) {
+        const float* cur = b.XA;
+        for (int d = 0; d < p->depths[l]; ++d, ++blk) {
+            const srk_stb_params& s = p->stbs[blk];
+            const int nH = s.num_heads;
+            SRK_REQUIRE(nH * p->dp <= p->ao_p && 3 * nH * p->dp <= b.nq_p, "swinir: head layout overflow");
+            SRK_REQUIRE(s.shift == 0 || s.shift == 4, "swinir: shift must be 0 or window_size/2");
+            const int hd = C / nH;
+            if (!a16_ready)
+                TRY(srk_layernorm(cur, Cp, M, C, s.ln1_g, s.ln1_b, eps, b.A16, Cp, ldt, nullptr, H, W, s.shift, stream));
+            a16_ready = false;
+            // qkv
+            {
+                srk_gemm_args g = lin_gemm(b.A16, Cp, s.w_qkv, s.b_qkv, b.nq_p, Cp);
+                g.out16 = b.QKV; g.ld16 = b.nq_p;
+                TRY(srk_gemm(&g, stream));
+            }
+            TRY(srk_window_attention(b.QKV, b.nq_p, b.AO, p->ao_p, s.rel_table, B, H, W, nH, p->dp,
+                                     1.0f / sqrtf((float)hd), s.shift, stream));
+            // proj + window_reverse + roll back + residual  [+ LN2 fused]
+            {
+                srk_gemm_args g = lin_gemm(b.AO, p->ao_p, s.w_proj, s.b_proj, Cp, p->ao_p);
+                g.res = cur; g.out32 = b.XB; g.ld32 = Cp; g.win_shift = s.shift;
+                if (fuse_ln) {
+                    g.ln_g = s.ln2_g; g.ln_b = s.ln2_b; g.ln_C = C; g.ln_win_shift = -1;   // LN2 rows in token order
+                    g.out16 = b.A16; g.ld16 = Cp;
+                }
+                TRY(srk_gemm(&g, stream));
+            }
+            if (!fuse_ln)
+                TRY(srk_layernorm(b.XB, Cp, M, C, s.ln2_g, s.ln2_b, eps, b.A16, Cp, ldt, nullptr, H, W, -1, stream));
+            // fc1 + GELU
+            {
+                srk_gemm_args g = lin_gemm(b.A16, Cp, s.w_fc1, s.b_fc1, p->hid_p, Cp);
+                g.act = SRK_ACT_GELU; g.out16 = b.HID; g.ld16 = p->hid_p;
+                TRY(srk_gemm(&g, stream));
+            }
+            // fc2 + residual  [+ cast for the RSTB conv | + LN1 of the next block fused]
+            {
+                srk_gemm_args g = lin_gemm(b.HID, p->hid_p, s.w_fc2, s.b_fc2, Cp, p->hid_p);
+                g.res = b.XB; g.out32 = b.XB; g.ld32 = Cp;
+                const bool last = d == p->depths[l] - 1;
+                if (last) {
+                    g.out16 = b.A16; g.ld16 = Cp; g.out16_dtype = cdt;
+                } else if (fuse_ln) {
+                    const srk_stb_params& nx = p->stbs[blk + 1];
+                    g.ln_g = nx.ln1_g; g.ln_b = nx.ln1_b; g.ln_C = C; g.ln_win_shift = nx.shift;
+                    g.out16 = b.A16; g.ld16 = Cp;
+                    a16_ready = true;
+                }
+                TRY(srk_gemm(&g, stream));
+            }
+            cur = b.XB;
+        }
+        if (p->depths[l] == 0)  // degenerate RSTB: conv of its own input
+            TRY(srk_layernorm(b.XA, Cp, M, C, nullptr, nullptr, eps, b.A16, Cp, cdt, nullptr, H, W, -1, stream));
+        // RSTB tail conv + residual with the RSTB input
+        {
+            srk_gemm_args g = conv_gemm(b.A16, Cp, H, W, p->rstb_convs[l]);
+            g.res = b.XA; g.out32 = b.XA; g.ld32 = Cp;
+            TRY(srk_gemm(&g, stream));
+        }
+    }
+    // final norm -> conv_after_body + shallow residual
+    TRY(srk_layernorm(b.XA, Cp, M, C, p->norm_g, p->norm_b, eps, b.A16, Cp, cdt, nullptr, H, W, -1, stream));
+    const float out_scale = 1.f / p->img_range;
+    const int s_up = p->upscale;
+    {
+        srk_gemm_args g = conv_gemm(b.A16, Cp, H, W, p->conv_after_body);
+        g.res = b.F0; g.ld32 = Cp; g.out16 = b.Y1; g.ld16 = Cp;
+        TRY(srk_gemm(&g, stream));
+    }
+    if (p->upsampler == SRK_UPSAMPLER_PIXELSHUFFLE) {
+        {
+            srk_gemm_args g = conv_gemm(b.Y1, Cp, H, W, p->conv_before_upsample);
+            g.act = SRK_ACT_LRELU; g.out16 = b.U[0]; g.ld16 = 64;
+            TRY(srk_gemm(&g, stream));
+        }
+        int Hh = H, Ww = W;
+        for (int k = 0; k < p->n_upsample; ++k) {
+            srk_gemm_args g = conv_gemm(b.U[k], 64, Hh, Ww, p->upsample[k]);
+            g.out16 = b.U[k + 1]; g.ld16 = 64; g.out16_mode = SRK_O16_PIXSHUF2;
+            TRY(srk_gemm(&g, stream));
+            Hh *= 2; Ww *= 2;
+        }
+        TRY(srk_conv_out(b.U[p->n_upsample], 64, B, Hh, Ww, 64, p->conv_last_w, p->conv_last_b,
+                         out_scale, y, h * s_up, w * s_up, stream));
+    } else {
+        srk_gemm_args g = conv_gemm(b.Y1, Cp, H, W, p->upsample[0]);
+        g.img = y; g.img_s = s_up; g.img_scale = out_scale; g.img_hc = h * s_up; g.img_wc = w * s_up;
+        TRY(srk_gemm(&g, stream));
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+namespace srk {
+struct EdsrBufs { float *HF, *R; void *A16, *T16, *U[5]; };
+static size_t edsr_layout(const srk_edsr_plan* p, int B, int h, int w, char* base, EdsrBufs* b) {
+    Bump a{base, 0, 0};
+    const size_t M = (size_t)B * h * w;
+    b->HF = (float*)a.take(M * p->Fp * 4);
+    b->R = (float*)a.take(M * p->Fp * 4);
+    b->A16 = a.take(M * p->Fp * 2);
+    b->T16 = a.take(M * p->Fp * 2);
+    size_t m = M;
+    for (int k = 0; k < 5; ++k) b->U[k] = nullptr;
+    for (int k = 0; k <= p->n_tail_up; ++k) { b->U[k] = a.take(m * p->Fp * 2); m *= 4; }
+    return align_up(a.off, 256);
+}
+}  // namespace srk
+
+extern "C" size_t srk_edsr_workspace_bytes(const srk_edsr_plan* p, int B, int h, int w) {
+    if (!p || B <= 0 || h <= 0 || w <= 0) return 0;
+    EdsrBufs b;
+    return edsr_layout(p, B, h, w, nullptr, &b);
+}
+
+extern "C" int srk_edsr_forward(const srk_edsr_plan* p, const float* x, float* y, int B, int h, int w,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+    SRK_REQUIRE(p && p->body && x && y && workspace, "edsr: null pointer");
+    if (p->in_chans != 1) return fail(SRK_ERR_UNSUPPORTED, "edsr: only in_chans == 1 is built");
+    SRK_REQUIRE(p->n_tail_up >= 0 && p->n_tail_up <= 4 && (1 << p->n_tail_up) == p->scale, "edsr: scale must be 2^n, n <= 4");
+    SRK_REQUIRE(p->Fp % 64 == 0 && p->Fp >= p->n_feats && p->n_feats % 4 == 0 && p->Fp == p->n_feats,
+                "edsr: n_feats must be a multiple of 64");
+    SRK_REQUIRE(B > 0 && h > 0 && w > 0, "edsr: bad input shape");
+    EdsrBufs b;
+    const size_t need = edsr_layout(p, B, h, w, (char*)workspace, &b);
+    if (need > workspace_bytes) return fail(SRK_ERR_WORKSPACE, "edsr: workspace %zu < %zu bytes", workspace_bytes, need);
+    const int M = B * h * w, Fp = p->Fp, cdt = p->conv_dtype;
+    auto conv_gemm = [&](const void* A, int Hh, int Ww, const srk_conv_params& cv) {
+        srk_gemm_args g{};
+        g.A = A; g.a_mode = SRK_A_CONV3X3; g.lda = Fp; g.nB = B; g.H = Hh; g.W = Ww;
+        g.Wt = cv.w; g.M = B * Hh * Ww; g.N = cv.n_p; g.K = 9 * Fp; g.dtype = cdt;
+        g.bias = cv.b; g.act = SRK_ACT_NONE; g.res_scale = 1.f; g.win_shift = -1; g.ln_win_shift = -1;
+        g.out16_dtype = cdt;
+        return g;
+    };
+    (void)M;
+    TRY(srk_conv_in(x, B, h, w, h, w, 1.f, p->head_w, p->head_b, p->n_feats, b.HF, Fp, b.A16, Fp, cdt, stream));
+    const float* cur = b.HF;
+    for (int i = 0; i < p->n_resblocks; ++i) {
+        {
+            srk_gemm_args g = conv_gemm(b.A16, h, w, p->body[2 * i]);
+            g.act = SRK_ACT_RELU; g.out16 = b.T16; g.ld16 = Fp;
+            TRY(srk_gemm(&g, stream));
+        }
+        {
+            srk_gemm_args g = conv_gemm(b.T16, h, w, p->body[2 * i + 1]);
+            g.res = cur; g.res_scale = p->res_scale; g.out32 = b.R; g.ld32 = Fp;
+            g.out16 = b.A16; g.ld16 = Fp;
+            TRY(srk_gemm(&g, stream));
+        }
+        cur = b.R;
+    }
+    {
+        srk_gemm_args g = conv_gemm(b.A16, h, w, p->body[2 * p->n_resblocks]);
+        g.res = b.HF; g.ld32 = Fp; g.out16 = b.U[0]; g.ld16 = Fp;
+        TRY(srk_gemm(&g, stream));
+    }
+    int Hh = h, Ww = w;
+    for (int k = 0; k < p->n_tail_up; ++k) {
+        srk_gemm_args g = conv_gemm(b.U[k], Hh, Ww, p->tail_up[k]);
+        g.out16 = b.U[k + 1]; g.ld16 = Fp; g.out16_mode = SRK_O16_PIXSHUF2;
+        TRY(srk_gemm(&g, stream));
+        Hh *= 2; Ww *= 2;
+    }
+    TRY(srk_conv_out(b.U[p->n_tail_up], Fp, B, Hh, Ww, p->n_feats, p->tail_w, p->tail_b, 1.f, y,
+                     h * p->scale, w * p->scale, stream));
+    return 0;
+}

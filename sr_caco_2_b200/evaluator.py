@@ -1,0 +1,100 @@
+"""Host-side evaluation loop: the B200-native restatement of `fast_eval`
+(dlib/utils/utils_trainer.py:533-762) for the hot path only -- forward with the caller-side
+window padding of `_forward_with_padding` (:829-862), uint8 quantisation + PSNR / MSE / NRMSE /
+SSIM / PSNR_Y (+ ROI-marginalised variants, :874-930) and the metric-sum exchange across
+ranks (:653-674).
+
+Multi-GPU: patches are independent, so each rank evaluates an exact contiguous shard of the
+patch list (no padding by repetition, unlike DistributedSampler: the result equals the
+single-GPU mean) and ONE all-reduce(SUM) of an fp64 vector of 11 values replaces the
+reference's 11 all_gathers + barriers (dlib/utils/utils_parallel.py:13-22).
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Optional, Sequence, Tuple
+
+import torch
+
+METRICS = ("psnr", "mse", "nrmse", "ssim", "psnr_y")
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Exact contiguous split of n items over `world` ranks (sizes differ by at most one)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def pad_for_windows(lr: torch.Tensor, window_size: int = 8) -> torch.Tensor:
+    """Caller-side padding of `_forward_with_padding` (utils_trainer.py:838-852): ALWAYS adds at
+    least one window, by mirroring the last rows / columns (edge pixel repeated)."""
+    h, w = lr.shape[-2:]
+    hp = (h // window_size + 1) * window_size - h
+    wp = (w // window_size + 1) * window_size - w
+    lr = torch.cat([lr, torch.flip(lr[:, :, h - hp:, :], [2])], 2)
+    lr = torch.cat([lr, torch.flip(lr[:, :, :, w - wp:], [3])], 3)
+    return lr
+
+
+def forward_with_padding(net, lr: torch.Tensor, scale: int, swinir_padding: bool) -> torch.Tensor:
+    h, w = lr.shape[-2:]
+    if swinir_padding:
+        e = net(pad_for_windows(lr, getattr(net, "window_size", 8)))
+        return e[..., : h * scale, : w * scale]
+    return net(lr)
+
+
+def reduce_sums(vec: torch.Tensor, group=None) -> torch.Tensor:
+    """SUM all-reduce of the metric-sum vector (NCCL over NVLink on GPUs, gloo in CPU tests)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
+    return vec
+
+
+def evaluate_patches(step_fn: Callable[[torch.Tensor, torch.Tensor], torch.Tensor],
+                     lr: torch.Tensor, hr: torch.Tensor, batch_size: int,
+                     rank: int = 0, world: int = 1, group=None,
+                     device: Optional[torch.device] = None) -> Dict[str, float]:
+    """Evaluate this rank's shard of (lr, hr) with `step_fn(lr_b, hr_b) -> (b, 10) fp64`
+    (5 full-image metrics then 5 ROI-marginalised ones) and return the global means."""
+    n = lr.shape[0]
+    lo, hi = shard_range(n, rank, world)
+    dev = device if device is not None else lr.device
+    acc = torch.zeros(11, dtype=torch.float64, device=dev)
+    for s in range(lo, hi, batch_size):
+        e = min(s + batch_size, hi)
+        vals = step_fn(lr[s:e], hr[s:e])
+        acc[:10] += vals.to(dev, torch.float64).sum(0)
+        acc[10] += e - s
+    acc = reduce_sums(acc, group)
+    tot = acc.cpu()
+    cnt = float(tot[10])
+    out = {"n": cnt}
+    for i, m in enumerate(METRICS):
+        out[m] = float(tot[i]) / max(cnt, 1.0)
+        out["roi_" + m] = float(tot[5 + i]) / max(cnt, 1.0)
+    return out
+
+
+def make_cuda_step(net, scale: int, swinir_padding: bool, border: Optional[int] = None,
+                   roi_ths: Sequence[int] = (4, 5, 6, 7, 8, 9, 10), check: bool = False):
+    """The product step: SR forward + single-pass metrics on the current CUDA device."""
+    from . import utils_image as UI
+
+    b = scale if border is None else border      # fast_eval: border = args.scale (:562)
+
+    def step(lr_b: torch.Tensor, hr_b: torch.Tensor) -> torch.Tensor:
+        dev = next(net.parameters()).device
+        lr_b = lr_b.to(dev, non_blocking=True)
+        hr_b = hr_b.to(dev, non_blocking=True)
+        e = forward_with_padding(net, lr_b, scale, swinir_padding)
+        m = UI.compute_metrics(e, hr_b, b, roi_ths, check=check)
+        cols = [m[k] for k in METRICS]
+        if len(roi_ths):
+            cols += [m["roi_" + k] for k in METRICS]
+        else:
+            cols += [torch.zeros_like(cols[0])] * 5
+        return torch.stack(cols, 1)
+
+    return step

@@ -1,0 +1,283 @@
+"""SwinIR with the reference's constructor and state_dict contract, executed by libsrk.
+
+Drop-in for `dlib.models.network_swinir.SwinIR` (reference dlib/models/network_swinir.py:710-970)
+on the evaluation path: same constructor arguments (:747-769), same parameter / buffer names
+and shapes (so `load_state_dict(strict=True)` of a reference checkpoint works, SURVEY.md
+appendix B), same forward I/O (fp32 (B,1,h,w) in [0,1] -> fp32 (B,1,h*s,w*s), un-clamped).
+
+The sub-modules below only HOLD parameters under the reference's names; none of them has a
+forward of its own.  `SwinIR.forward` repacks the weights once (padded 16-bit GEMM operands)
+and issues one `srk_swinir_forward` call: hand-written sm_100a kernels, no PyTorch ops on the
+hot path, no CPU / eager fallback (a CPU tensor raises).
+
+Built: in_chans == 1, window_size == 8, upsampler in {'pixelshuffle', 'pixelshuffledirect'},
+resi_connection '1conv', eval mode.  Anything else raises NotImplementedError at construction.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import packing as P
+
+US_PIXEL_SHUFFLE = "pixelshuffle"              # dlib/utils/constants.py:91-93
+US_PIXEL_SHUFFLE_DIRECT = "pixelshuffledirect"
+R_CONNECTION_1CONV = "1conv"
+
+
+def _to_2tuple(v):
+    return tuple(v) if isinstance(v, (tuple, list)) else (v, v)
+
+
+class _Holder(nn.Module):
+    """Parameter container (no forward)."""
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("parameter holder: the network is executed by SwinIR.forward")
+
+
+def _attention_holder(dim, ws, num_heads):
+    m = _Holder()
+    m.relative_position_bias_table = nn.Parameter(torch.zeros((2 * ws - 1) ** 2, num_heads))
+    nn.init.trunc_normal_(m.relative_position_bias_table, std=.02)
+    p = torch.arange(ws * ws)
+    dy = p[:, None] // ws - p[None, :] // ws + ws - 1
+    dx = p[:, None] % ws - p[None, :] % ws + ws - 1
+    m.register_buffer("relative_position_index", (dy * (2 * ws - 1) + dx).long())
+    m.qkv = nn.Linear(dim, dim * 3, bias=True)
+    m.proj = nn.Linear(dim, dim)
+    return m
+
+
+def _shift_mask(res, ws, shift):
+    """Values of the reference's `attn_mask` buffer (network_swinir.py:260-285).  The kernels
+    derive the mask arithmetically; the buffer only exists for state_dict compatibility."""
+    def lab(n):
+        t = torch.zeros(n, dtype=torch.long)
+        t[n - ws:n - shift] = 1
+        t[n - shift:] = 2
+        return t
+    H, W = res
+    g = lab(H)[:, None] * 3 + lab(W)[None, :]
+    g = g.view(H // ws, ws, W // ws, ws).permute(0, 2, 1, 3).reshape(-1, ws * ws)
+    d = g[:, None, :] - g[:, :, None]
+    return torch.where(d != 0, torch.tensor(-100.0), torch.tensor(0.0))
+
+
+class SwinIR(nn.Module):
+    def __init__(self, img_size=64, patch_size=1, in_chans=3, embed_dim=96,
+                 depths=[6, 6, 6, 6], num_heads=[6, 6, 6, 6], window_size=7, mlp_ratio=4.,
+                 qkv_bias=True, qk_scale=None, drop_rate=0., attn_drop_rate=0.,
+                 drop_path_rate=0.1, norm_layer=nn.LayerNorm, ape=False, patch_norm=True,
+                 use_checkpoint=False, upscale=2, img_range=1., upsampler='',
+                 resi_connection=R_CONNECTION_1CONV, **kwargs):
+        super().__init__()
+        if in_chans != 1:
+            raise NotImplementedError("sr_caco_2_b200.SwinIR: only in_chans == 1 (grayscale "
+                                      "microscopy patches) is built")
+        if window_size != 8:
+            raise NotImplementedError("sr_caco_2_b200.SwinIR: only window_size == 8 is built")
+        if upsampler not in (US_PIXEL_SHUFFLE, US_PIXEL_SHUFFLE_DIRECT):
+            raise NotImplementedError(f"sr_caco_2_b200.SwinIR: upsampler {upsampler!r} not built")
+        if resi_connection != R_CONNECTION_1CONV:
+            raise NotImplementedError("sr_caco_2_b200.SwinIR: only resi_connection '1conv' is built")
+        if patch_size != 1 or ape or not patch_norm or not qkv_bias or qk_scale is not None \
+                or norm_layer is not nn.LayerNorm:
+            raise NotImplementedError("sr_caco_2_b200.SwinIR: non-default patch/ape/norm options")
+        if upsampler == US_PIXEL_SHUFFLE and (upscale & (upscale - 1)) != 0:
+            raise NotImplementedError("sr_caco_2_b200.SwinIR: pixelshuffle is built for 2^n scales")
+        if upsampler == US_PIXEL_SHUFFLE_DIRECT and upscale > 8:
+            raise NotImplementedError("sr_caco_2_b200.SwinIR: direct upsampler is built up to X8")
+        if len(depths) != len(num_heads):
+            raise ValueError("depths and num_heads must have the same length")
+        num_feat = 64
+        self.img_range = float(img_range)
+        self.mean = torch.zeros(1, 1, 1, 1)
+        self.upscale, self.upsampler, self.window_size = upscale, upsampler, window_size
+        self.in_chans, self.embed_dim, self.mlp_ratio = in_chans, embed_dim, mlp_ratio
+        self.depths, self.num_heads = list(depths), list(num_heads)
+        self.num_layers = len(depths)
+        res = _to_2tuple(img_size)
+        self.patches_resolution = list(res)
+        hidden = int(embed_dim * mlp_ratio)
+        self.hidden_dim = hidden
+
+        self.conv_first = nn.Conv2d(in_chans, embed_dim, 3, 1, 1)
+        self.patch_embed = _Holder()
+        self.patch_embed.norm = nn.LayerNorm(embed_dim)
+        self.layers = nn.ModuleList()
+        self._block_geometry = []        # (window_size, shift) per block, decided HERE from
+        for li, depth in enumerate(depths):  # img_size like network_swinir.py:232-236
+            rstb = _Holder()
+            rstb.residual_group = _Holder()
+            rstb.residual_group.blocks = nn.ModuleList()
+            for bi in range(depth):
+                ws, shift = window_size, (0 if bi % 2 == 0 else window_size // 2)
+                if min(res) <= ws:
+                    shift, ws = 0, min(res)
+                if ws != 8:
+                    raise NotImplementedError(
+                        f"sr_caco_2_b200.SwinIR: img_size {img_size} makes the reference shrink "
+                        f"its window to {ws}; only 8x8 windows are built")
+                self._block_geometry.append((ws, shift))
+                blk = _Holder()
+                blk.norm1 = nn.LayerNorm(embed_dim)
+                blk.attn = _attention_holder(embed_dim, ws, num_heads[li])
+                blk.norm2 = nn.LayerNorm(embed_dim)
+                blk.mlp = _Holder()
+                blk.mlp.fc1 = nn.Linear(embed_dim, hidden)
+                blk.mlp.fc2 = nn.Linear(hidden, embed_dim)
+                blk.register_buffer("attn_mask", _shift_mask(res, ws, shift) if shift > 0 else None)
+                rstb.residual_group.blocks.append(blk)
+            rstb.conv = nn.Conv2d(embed_dim, embed_dim, 3, 1, 1)
+            self.layers.append(rstb)
+        self.norm = nn.LayerNorm(embed_dim)
+        self.conv_after_body = nn.Conv2d(embed_dim, embed_dim, 3, 1, 1)
+        if upsampler == US_PIXEL_SHUFFLE:
+            self.conv_before_upsample = nn.Sequential(nn.Conv2d(embed_dim, num_feat, 3, 1, 1),
+                                                      nn.LeakyReLU(inplace=True))
+            ups = []
+            for _ in range(int(round(math.log2(upscale)))):
+                ups += [nn.Conv2d(num_feat, 4 * num_feat, 3, 1, 1), nn.PixelShuffle(2)]
+            self.upsample = nn.Sequential(*ups)
+            self.conv_last = nn.Conv2d(num_feat, in_chans, 3, 1, 1)
+        else:
+            self.upsample = nn.Sequential(nn.Conv2d(embed_dim, upscale ** 2 * in_chans, 3, 1, 1),
+                                          nn.PixelShuffle(upscale))
+        for m in self.modules():          # reference init, network_swinir.py:891-898
+            if isinstance(m, nn.Linear):
+                nn.init.trunc_normal_(m.weight, std=.02)
+                nn.init.constant_(m.bias, 0)
+            elif isinstance(m, nn.LayerNorm):
+                nn.init.constant_(m.bias, 0)
+                nn.init.constant_(m.weight, 1.0)
+        self._plan = None
+        self._keep = None
+        self._ws = None
+        self.register_load_state_dict_post_hook(lambda mod, keys: mod._invalidate())
+
+    # ---- packed-weight cache --------------------------------------------------------------
+    def _invalidate(self):
+        self._plan = None
+        self._keep = None
+
+    def _apply(self, fn, *a, **k):
+        self._invalidate()
+        return super()._apply(fn, *a, **k)
+
+    def flush(self):  # called by the reference's ModelPlain (model_plain.py:55) when present
+        self._invalidate()
+        self._ws = None
+
+    def _build_plan(self, linear_dtype=L.SRK_BF16, conv_dtype=L.SRK_FP16):
+        dev = self.conv_first.weight.device
+        keep: List[torch.Tensor] = []
+
+        def k(t):
+            keep.append(t)
+            return L.ptr(t)
+
+        Cdim, hid = self.embed_dim, self.hidden_dim
+        Cp, hid_p = P.up(Cdim, 64), P.up(hid, 64)
+        max_d = max(Cdim // nh for nh in self.num_heads)
+        dp = P.up(max_d, 16)
+        ao_p = P.up(max(self.num_heads) * dp, 64)
+        nq_p = P.up(3 * max(self.num_heads) * dp, 64)
+        nblk = sum(self.depths)
+        stbs = (L.StbParams * max(nblk, 1))()
+        convs = (L.ConvParams * max(self.num_layers, 1))()
+        depths = (C.c_int * max(self.num_layers, 1))(*self.depths)
+        bi_flat = 0
+        for li, rstb in enumerate(self.layers):
+            nh = self.num_heads[li]
+            if Cdim % nh != 0:
+                raise ValueError("embed_dim must be divisible by num_heads")
+            d = Cdim // nh
+            for bi, blk in enumerate(rstb.residual_group.blocks):
+                s = stbs[bi_flat]
+                s.ln1_g, s.ln1_b = k(blk.norm1.weight.detach().float().contiguous()), k(blk.norm1.bias.detach().float().contiguous())
+                s.ln2_g, s.ln2_b = k(blk.norm2.weight.detach().float().contiguous()), k(blk.norm2.bias.detach().float().contiguous())
+                wq, bq = P.pack_qkv(blk.attn.qkv.weight.detach(), blk.attn.qkv.bias.detach(), nh, d, dp, nq_p, Cp, linear_dtype)
+                s.w_qkv, s.b_qkv = k(wq), k(bq)
+                s.w_proj = k(P.pack_proj(blk.attn.proj.weight.detach(), nh, d, dp, Cp, ao_p, linear_dtype))
+                s.b_proj = k(P.pad_bias(blk.attn.proj.bias.detach(), Cp))
+                s.w_fc1 = k(P.pack_linear(blk.mlp.fc1.weight.detach(), hid_p, Cp, linear_dtype))
+                s.b_fc1 = k(P.pad_bias(blk.mlp.fc1.bias.detach(), hid_p))
+                s.w_fc2 = k(P.pack_linear(blk.mlp.fc2.weight.detach(), Cp, hid_p, linear_dtype))
+                s.b_fc2 = k(P.pad_bias(blk.mlp.fc2.bias.detach(), Cp))
+                s.rel_table = k(blk.attn.relative_position_bias_table.detach().float().t().contiguous())
+                s.shift = self._block_geometry[bi_flat][1]
+                s.num_heads = nh
+                bi_flat += 1
+            w, b = P.pack_conv3x3(rstb.conv.weight.detach(), rstb.conv.bias.detach(), Cp, Cp, conv_dtype)
+            convs[li].w, convs[li].b, convs[li].cin_p, convs[li].n_p = k(w), k(b), Cp, Cp
+        plan = L.SwinIRPlan()
+        plan.upscale, plan.in_chans, plan.window_size = self.upscale, self.in_chans, self.window_size
+        plan.embed_dim, plan.hidden_dim, plan.n_layers = Cdim, hid, self.num_layers
+        plan.upsampler = (L.UPSAMPLER_PIXELSHUFFLE if self.upsampler == US_PIXEL_SHUFFLE
+                          else L.UPSAMPLER_PIXELSHUFFLEDIRECT)
+        plan.img_range = self.img_range
+        plan.Cp, plan.hid_p, plan.dp, plan.ao_p = Cp, hid_p, dp, ao_p
+        plan.depths, plan.stbs, plan.rstb_convs = depths, stbs, convs
+        w, b = P.pack_conv_in(self.conv_first.weight.detach(), self.conv_first.bias.detach())
+        plan.conv_first_w, plan.conv_first_b = k(w), k(b)
+        plan.pe_norm_g = k(self.patch_embed.norm.weight.detach().float().contiguous())
+        plan.pe_norm_b = k(self.patch_embed.norm.bias.detach().float().contiguous())
+        plan.norm_g = k(self.norm.weight.detach().float().contiguous())
+        plan.norm_b = k(self.norm.bias.detach().float().contiguous())
+        w, b = P.pack_conv3x3(self.conv_after_body.weight.detach(), self.conv_after_body.bias.detach(), Cp, Cp, conv_dtype)
+        plan.conv_after_body = L.ConvParams(k(w), k(b), Cp, Cp)
+        if self.upsampler == US_PIXEL_SHUFFLE:
+            c0 = self.conv_before_upsample[0]
+            w, b = P.pack_conv3x3(c0.weight.detach(), c0.bias.detach(), Cp, 64, conv_dtype)
+            plan.conv_before_upsample = L.ConvParams(k(w), k(b), Cp, 64)
+            n_up = 0
+            for m in self.upsample:
+                if isinstance(m, nn.Conv2d):
+                    w, b = P.pack_conv3x3(m.weight.detach(), m.bias.detach(), 64, 256, conv_dtype, pixel_shuffle_r=2)
+                    plan.upsample[n_up] = L.ConvParams(k(w), k(b), 64, 256)
+                    n_up += 1
+            plan.n_upsample = n_up
+            plan.conv_last_w = k(P.pack_conv_out(self.conv_last.weight.detach()))
+            plan.conv_last_b = float(self.conv_last.bias.detach().float().item())
+        else:
+            m = self.upsample[0]
+            w, b = P.pack_conv3x3(m.weight.detach(), m.bias.detach(), Cp, 64, conv_dtype)
+            plan.upsample[0] = L.ConvParams(k(w), k(b), Cp, 64)
+            plan.n_upsample = 1
+        plan.linear_dtype, plan.conv_dtype = linear_dtype, conv_dtype
+        keep += [stbs, convs, depths]
+        self._plan, self._keep = plan, keep
+        assert all(t.device == dev for t in keep if isinstance(t, torch.Tensor))
+
+    # ---- forward --------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        lib = L.load()
+        if self.training:
+            raise NotImplementedError("sr_caco_2_b200.SwinIR implements the evaluation path only; "
+                                      "call .eval() (training is out of scope)")
+        L.require_device(x)
+        if x.dim() != 4 or x.shape[1] != self.in_chans:
+            raise ValueError(f"expected (B,{self.in_chans},h,w), got {tuple(x.shape)}")
+        if x.device != self.conv_first.weight.device:
+            raise L.SrkError("input and parameters are on different devices")
+        x = x.float().contiguous()
+        B, _, h, w = x.shape
+        if self._plan is None:
+            self._build_plan()
+        with torch.cuda.device(x.device):
+            need = lib.srk_swinir_workspace_bytes(C.byref(self._plan), B, h, w)
+            if self._ws is None or self._ws.numel() < need or self._ws.device != x.device:
+                self._ws = None
+                self._ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+            y = torch.empty(B, self.in_chans, h * self.upscale, w * self.upscale,
+                            dtype=torch.float32, device=x.device)
+            L.check(lib.srk_swinir_forward(C.byref(self._plan), L.ptr(x), L.ptr(y), B, h, w,
+                                           L.ptr(self._ws), self._ws.numel(), L.stream_ptr()))
+        return y

@@ -1,0 +1,485 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  Everything goes through the C ABI
+of libsrk.so; the checker is the CPU oracle (oracle/sr_oracle.py) and the golden vectors the
+unmodified reference produced (tests/golden/)."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests import common as T
+from oracle import sr_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+ENGINES = os.environ.get("SRK_TEST_ENGINES", "tcgen05,mma_sync").split(",")
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def L():
+    from sr_caco_2_b200 import _lib
+    _lib.load()
+    _lib.check(_lib.load().srk_check_device(0))
+    return _lib
+
+
+@pytest.fixture(autouse=True)
+def _sync_and_restore_engine():
+    yield
+    torch.cuda.synchronize()
+    from sr_caco_2_b200 import _lib
+    _lib.set_engine(ENGINES[0])
+
+
+def load_npz(name):
+    z = np.load(os.path.join(T.GOLDEN, name + ".npz"))
+    sd = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd::")}
+    return z, sd, json.loads(bytes(z["cfg"]).decode())
+
+
+def make_swinir(cfg, sd):
+    from sr_caco_2_b200 import SwinIR
+    net = SwinIR(upscale=cfg.upscale, in_chans=cfg.in_chans, img_size=cfg.img_size,
+                 window_size=cfg.window_size, img_range=cfg.img_range, depths=cfg.depths,
+                 embed_dim=cfg.embed_dim, num_heads=cfg.num_heads, mlp_ratio=cfg.mlp_ratio,
+                 upsampler=cfg.upsampler, resi_connection=cfg.resi_connection)
+    net.load_state_dict(sd, strict=True)
+    return net.to(DEV).eval()
+
+
+# ------------------------------------------------------------------------------------------
+# index maps: bit exact
+# ------------------------------------------------------------------------------------------
+def _index_map(L, kind, H, W, shift, a, n):
+    out = torch.empty(n, dtype=torch.int32, device=DEV)
+    L.check(L.load().srk_index_map(kind, H, W, shift, a, L.ptr(out), L.stream_ptr()))
+    return out.cpu().long()
+
+
+@pytest.mark.parametrize("HW", [(16, 16), (64, 64), (72, 72), (128, 136), (24, 40)])
+def test_index_maps_bit_exact(L, HW):
+    H, W = HW
+    for shift in (0, 4):
+        got = _index_map(L, 0, H, W, shift, 0, H * W)
+        assert torch.equal(got, O.window_gather_map(H, W, 8, shift))
+        got = _index_map(L, 1, H, W, shift, 0, H * W * 64).view(-1, 64, 64)
+        ref = (O.shift_attention_mask(H, W, 8, 4) != 0).long() if shift else torch.zeros_like(got)
+        assert torch.equal(got, ref)
+    assert torch.equal(_index_map(L, 2, 0, 0, 0, 0, 4096).view(64, 64), O.relative_position_index(8))
+    for (Cc, h, w, r) in [(1, 4, 4, 2), (2, 3, 5, 2), (1, 4, 4, 8), (64, 6, 6, 2)]:
+        got = _index_map(L, 3, h, w, r, Cc, Cc * h * r * w * r)
+        assert torch.equal(got, O.pixel_shuffle_map(Cc, h, w, r).reshape(-1))
+
+
+# ------------------------------------------------------------------------------------------
+# metrics
+# ------------------------------------------------------------------------------------------
+def _inputs_for(name):
+    from tests.test_oracle import _inputs_for as f
+    return f({"name": name})
+
+
+def test_metrics_against_reference_golden(L):
+    from sr_caco_2_b200 import utils_image as UI
+    cases = json.load(open(os.path.join(T.GOLDEN, "metrics_kat.json")))
+    by_base = {}
+    for c in cases:
+        by_base.setdefault((c["name"].split("_roi")[0], c["border"]), []).append(c)
+    for (base, border), group in by_base.items():
+        E, H = _inputs_for(base)
+        ths = sorted({c["roi_th"] for c in group if c["roi_th"] is not None})
+        m = UI.compute_metrics(E.to(DEV), H.to(DEV), border, ths, check=False)
+        raw = m["raw"].cpu()
+        for c in group:
+            v = 0 if c["roi_th"] is None else 1 + ths.index(c["roi_th"])
+            for i, k in enumerate(("psnr", "mse", "nrmse", "ssim", "psnr_y")):
+                tol = dict(psnr=1e-9, mse=1e-9, nrmse=1e-12, ssim=2e-6, psnr_y=1e-5)[k]
+                np.testing.assert_allclose(raw[:, v, i].numpy(), np.array(c[k]), rtol=tol, atol=tol,
+                                           err_msg=f"{c['name']} {k}")
+
+
+def test_metric_function_shims_match_oracle(L):
+    from sr_caco_2_b200 import utils_image as UI
+    E, H = T.synthetic_pair(3, 96, 120, 31)
+    e8, h8 = O.quantize_u8f(E), O.quantize_u8f(H)
+    roi = (h8 >= 6).float()
+    for r in (None, roi):
+        rg = None if r is None else r.to(DEV)
+        for border in (0, 3):
+            np.testing.assert_allclose(UI.mbatch_gpu_calculate_psnr(e8.to(DEV), h8.to(DEV), border, rg).cpu(),
+                                       O.psnr(e8, h8, border, r), rtol=1e-10)
+            np.testing.assert_allclose(UI.mbatch_gpu_calculate_mse(e8.to(DEV), h8.to(DEV), border, rg).cpu(),
+                                       O.mse(e8, h8, border, r), rtol=1e-10)
+            np.testing.assert_allclose(UI.mbatch_gpu_calculate_nrmse(e8.to(DEV), h8.to(DEV), border, rg).cpu(),
+                                       O.nrmse(e8, h8, border, r), rtol=1e-10)
+            got = UI.mbatch_gpu_calculate_ssim(e8.to(DEV), h8.to(DEV), border, rg)
+            assert got.dtype == torch.float32
+            np.testing.assert_allclose(got.cpu(), O.ssim(e8, h8, border, r), atol=2e-6)
+    # non-integer inputs (the PSNR_Y operands of the reference) go through the same fp64 path
+    a, b = e8 * 0.859 + 16, h8 * 0.859 + 16
+    np.testing.assert_allclose(UI.mbatch_gpu_calculate_psnr(a.to(DEV), b.to(DEV), 2).cpu(), O.psnr(a, b, 2), rtol=1e-10)
+    assert torch.equal(UI.tensor2uint82float(E.to(DEV)).cpu(), e8)
+    with pytest.raises(ValueError):       # 11x11 window does not fit (utils_image.py:1044)
+        UI.mbatch_gpu_calculate_ssim(e8[..., :12, :12].to(DEV), h8[..., :12, :12].to(DEV), border=1)
+    with pytest.raises(AssertionError):   # range assert of the reference (:1164-1172)
+        UI.mbatch_gpu_calculate_ssim((e8 + 300).to(DEV), h8.to(DEV))
+    with pytest.raises(AssertionError):
+        UI.mbatch_gpu_calculate_psnr(e8.to(DEV), h8[:2].to(DEV))
+
+
+def test_metrics_full_size_properties(L):
+    """BASELINE full size (B=32, 512x512): identities that do not need the CPU oracle."""
+    from sr_caco_2_b200 import utils_image as UI
+    g = torch.Generator(device=DEV).manual_seed(5)
+    Hh = (torch.rand(32, 1, 512, 512, device=DEV, generator=g) * 255).round() / 255
+    m = UI.compute_metrics(Hh, Hh, 8, (4, 7, 10))
+    assert torch.allclose(m["psnr"], torch.full_like(m["psnr"], 498.1308036087), atol=1e-6)
+    assert torch.allclose(m["ssim"], torch.ones_like(m["ssim"]), atol=1e-6)
+    assert float(m["mse"].abs().max()) == 0.0 and float(m["nrmse"].abs().max()) == 0.0
+    E = (Hh + 0.1 * torch.randn(Hh.shape, device=DEV, generator=g))
+    m1 = UI.compute_metrics(E, Hh, 8, (4, 7, 10))
+    m2 = UI.compute_metrics(E, Hh, 8, (4, 7, 10))
+    assert torch.equal(m1["raw"][..., :3], m2["raw"][..., :3])           # integer sums: deterministic
+    assert torch.allclose(m1["raw"], m2["raw"], rtol=1e-12, atol=1e-12)
+    # PSNR_Y - PSNR = 20 log10(255/219) for gray images
+    assert torch.allclose(m1["psnr_y"] - m1["psnr"], torch.full_like(m1["psnr"], 1.3219215), atol=1e-5)
+    # batch-permutation equivariance + per-image independence
+    perm = torch.randperm(32, device=DEV)
+    m3 = UI.compute_metrics(E[perm], Hh[perm], 8, (4, 7, 10))
+    assert torch.allclose(m3["raw"], m1["raw"][perm], rtol=1e-12, atol=1e-12)
+    sub = O.all_metrics(E[:2].cpu(), Hh[:2].cpu(), 8)
+    np.testing.assert_allclose(m1["psnr"][:2].cpu(), sub["psnr"], rtol=1e-10)
+    np.testing.assert_allclose(m1["ssim"][:2].cpu(), sub["ssim"].double(), atol=2e-6)
+
+
+# ------------------------------------------------------------------------------------------
+# building blocks
+# ------------------------------------------------------------------------------------------
+def test_layernorm_and_window_gather(L):
+    lib = L.load()
+    g = torch.Generator().manual_seed(1)
+    for (C_, ld, H, W) in [(180, 192, 16, 24), (60, 64, 8, 8)]:
+        B = 2
+        M = B * H * W
+        x = torch.zeros(M, ld)
+        x[:, :C_] = torch.randn(M, C_, generator=g) * 3 + 1
+        gam, bet = torch.randn(C_, generator=g), torch.randn(C_, generator=g)
+        ref = F.layer_norm(x[:, :C_], (C_,), gam, bet, 1e-5)
+        xd, gd, bd = x.to(DEV), gam.to(DEV), bet.to(DEV)
+        for shift in (-1, 0, 4):
+            out = torch.full((M, ld), 7.0, dtype=torch.bfloat16, device=DEV)
+            x32 = torch.full((M, ld), 7.0, device=DEV)
+            L.check(lib.srk_layernorm(L.ptr(xd), ld, M, C_, L.ptr(gd), L.ptr(bd), 1e-5, L.ptr(out), ld,
+                                      L.SRK_BF16, L.ptr(x32), H, W, shift, L.stream_ptr()))
+            exp = ref
+            if shift >= 0:
+                gm = O.window_gather_map(H, W, 8, shift)
+                idx = (torch.arange(B)[:, None] * H * W + gm[None, :]).reshape(-1)
+                exp = ref[idx]
+            assert torch.equal(out[:, :C_].float().cpu(), exp.bfloat16().float()) or \
+                float((out[:, :C_].float().cpu() - exp).abs().max()) < 0.04
+            assert float((out[:, :C_].float().cpu() - exp).abs().max()) < 0.04
+            assert float(out[:, C_:].float().abs().max()) == 0.0
+            assert float((x32[:, :C_].cpu() - ref).abs().max()) < 1e-5
+        out = torch.empty(M, ld, dtype=torch.float16, device=DEV)       # cast mode
+        L.check(lib.srk_layernorm(L.ptr(xd), ld, M, C_, None, None, 1e-5, L.ptr(out), ld, L.SRK_FP16,
+                                  None, H, W, -1, L.stream_ptr()))
+        assert torch.equal(out.cpu(), x.half())
+
+
+def test_conv_in_and_conv_out(L):
+    lib = L.load()
+    g = torch.Generator().manual_seed(2)
+    B, h, w, C_ = 2, 13, 18, 60
+    H, W, ld = 16, 24, 64
+    x = torch.rand(B, 1, h, w, generator=g)
+    wt, bs = torch.randn(C_, 1, 3, 3, generator=g), torch.randn(C_, generator=g)
+    xp = F.pad(x, (0, W - w, 0, H - h), mode="reflect") * 0.5
+    ref = F.conv2d(xp, wt, bs, padding=1).permute(0, 2, 3, 1).reshape(-1, C_)
+    o32 = torch.full((B * H * W, ld), 3.0, device=DEV)
+    o16 = torch.full((B * H * W, ld), 3.0, dtype=torch.float16, device=DEV)
+    L.check(lib.srk_conv_in(L.ptr(x.to(DEV)), B, h, w, H, W, 0.5, L.ptr(wt.reshape(C_, 9).contiguous().to(DEV)),
+                            L.ptr(bs.to(DEV)), C_, L.ptr(o32), ld, L.ptr(o16), ld, L.SRK_FP16, L.stream_ptr()))
+    assert float((o32[:, :C_].cpu() - ref).abs().max()) < 1e-5
+    assert float(o32[:, C_:].abs().max()) == 0.0
+    assert float((o16[:, :C_].float().cpu() - ref).abs().max()) < 5e-3
+    # conv_out with crop
+    Cin, lda, Hc, Wc = 64, 64, 29, 41
+    a = torch.randn(B, 32, 48, lda, generator=g).half()
+    wo, bo = torch.randn(1, Cin, 3, 3, generator=g) * 0.1, 0.3
+    refo = (F.conv2d(a.float().permute(0, 3, 1, 2), wo, torch.tensor([bo]), padding=1) * 2.0)[:, :, :Hc, :Wc]
+    y = torch.zeros(B, 1, Hc, Wc, device=DEV)
+    wk = wo[0].permute(1, 2, 0).reshape(9, Cin).contiguous().to(DEV)
+    L.check(lib.srk_conv_out(L.ptr(a.to(DEV)), lda, B, 32, 48, Cin, L.ptr(wk), bo, 2.0, L.ptr(y), Hc, Wc,
+                             L.stream_ptr()))
+    assert float((y.cpu() - refo).abs().max()) < 2e-4
+
+
+def _gemm(L, **kw):
+    g = L.GemmArgs()
+    g.res_scale, g.win_shift, g.ln_win_shift = 1.0, -1, -1
+    for k, v in kw.items():
+        setattr(g, k, L.ptr(v) if isinstance(v, torch.Tensor) else v)
+    L.check(L.load().srk_gemm(C.byref(g), L.stream_ptr()))
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+def test_gemm_rows_epilogues(L, engine, dtype):
+    L.set_engine(engine)
+    td, code = (torch.bfloat16, L.SRK_BF16) if dtype == "bf16" else (torch.float16, L.SRK_FP16)
+    g = torch.Generator().manual_seed(3)
+    H, W, B = 16, 24, 2
+    M = B * H * W
+    for (N, K) in [(192, 192), (576, 192), (384, 192), (192, 384), (64, 64), (320, 64), (128, 128)]:
+        A = (torch.randn(M, K, generator=g)).to(td)
+        Wt = (torch.randn(N, K, generator=g) * 0.05).to(td)
+        bias = torch.randn(N, generator=g)
+        ref = A.float() @ Wt.float().t() + bias
+        Ad, Wd, bd = A.to(DEV), Wt.to(DEV), bias.to(DEV)
+        # (1) bias + GELU -> 16-bit rows
+        o16 = torch.zeros(M, N, dtype=td, device=DEV)
+        _gemm(L, A=Ad, a_mode=L.A_ROWS, lda=K, nB=B, H=H, W=W, Wt=Wd, M=M, N=N, K=K, dtype=code, bias=bd,
+              act=L.ACT_GELU, out16=o16, ld16=N, out16_dtype=code, out16_mode=L.O16_ROWS)
+        exp = F.gelu(ref)
+        err = (o16.float().cpu() - exp).abs().max()
+        assert float(err) < 0.02 * max(1.0, float(exp.abs().max())), (N, K, float(err))
+        # (2) bias + residual with window reverse + roll back -> fp32, plus 16-bit cast
+        for shift in (-1, 4):
+            res = torch.randn(M, N, generator=g)
+            o32 = torch.zeros(M, N, device=DEV)
+            o16 = torch.zeros(M, N, dtype=torch.float16, device=DEV)
+            _gemm(L, A=Ad, a_mode=L.A_ROWS, lda=K, nB=B, H=H, W=W, Wt=Wd, M=M, N=N, K=K, dtype=code, bias=bd,
+                  act=L.ACT_NONE, res=res.to(DEV), res_scale=0.5, out32=o32, ld32=N, win_shift=shift,
+                  out16=o16, ld16=N, out16_dtype=L.SRK_FP16, out16_mode=L.O16_ROWS)
+            if shift >= 0:
+                gm = O.window_gather_map(H, W, 8, shift)
+                idx = (torch.arange(B)[:, None] * H * W + gm[None, :]).reshape(-1)
+                exp32 = torch.empty(M, N)
+                exp32[idx] = ref * 0.5 + res[idx]
+                exp16 = ref * 0.5 + res[idx]           # 16-bit copy stays in GEMM-row order
+            else:
+                exp32 = ref * 0.5 + res
+                exp16 = exp32
+            assert float((o32.cpu() - exp32).abs().max()) < 2e-3 * max(1.0, float(ref.abs().max()))
+            assert float((o16.float().cpu() - exp16).abs().max()) < 0.02 * max(1.0, float(ref.abs().max()))
+    # ragged M (not a multiple of the 128-row tile)
+    M2, N, K = 200, 64, 128
+    A = torch.randn(M2, K, generator=g).to(td)
+    Wt = (torch.randn(N, K, generator=g) * 0.05).to(td)
+    bias = torch.randn(N, generator=g)
+    o32 = torch.zeros(M2 + 56, N, device=DEV)
+    _gemm(L, A=A.to(DEV), a_mode=L.A_ROWS, lda=K, Wt=Wt.to(DEV), M=M2, N=N, K=K, dtype=code, bias=bias.to(DEV),
+          out32=o32, ld32=N)
+    assert float((o32[:M2].cpu() - (A.float() @ Wt.float().t() + bias)).abs().max()) < 2e-3
+    assert float(o32[M2:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_gemm_conv3x3_pixelshuffle_and_image_epilogues(L, engine):
+    L.set_engine(engine)
+    g = torch.Generator().manual_seed(4)
+    B, H, W = 2, 10, 13
+    for (Cin, Cout) in [(64, 64), (192, 192), (64, 256), (192, 64)]:
+        x = torch.randn(B, Cin, H, W, generator=g).half()
+        wt = (torch.randn(Cout, Cin, 3, 3, generator=g) * 0.05).half()
+        bias = torch.randn(Cout, generator=g)
+        ref = F.conv2d(x.float(), wt.float(), bias, padding=1)                      # (B,Cout,H,W)
+        a = x.permute(0, 2, 3, 1).contiguous().to(DEV)                               # NHWC
+        from sr_caco_2_b200 import packing as P
+        ps = 2 if Cout == 256 else 0
+        wk, bk = P.pack_conv3x3(wt.float(), bias, Cin, Cout, L.SRK_FP16, pixel_shuffle_r=ps)
+        M = B * H * W
+        if ps:
+            o16 = torch.zeros(B, 2 * H, 2 * W, 64, dtype=torch.float16, device=DEV)
+            _gemm(L, A=a, a_mode=L.A_CONV3X3, lda=Cin, nB=B, H=H, W=W, Wt=wk.to(DEV), M=M, N=Cout, K=9 * Cin,
+                  dtype=L.SRK_FP16, bias=bk.to(DEV), act=L.ACT_NONE, out16=o16, ld16=64,
+                  out16_dtype=L.SRK_FP16, out16_mode=L.O16_PIXSHUF2)
+            exp = F.pixel_shuffle(ref, 2).permute(0, 2, 3, 1)
+            assert float((o16.float().cpu() - exp).abs().max()) < 0.02 * max(1.0, float(exp.abs().max()))
+        else:
+            res = torch.randn(M, Cout, generator=g)
+            o32 = torch.zeros(M, Cout, device=DEV)
+            o16 = torch.zeros(M, Cout, dtype=torch.float16, device=DEV)
+            _gemm(L, A=a, a_mode=L.A_CONV3X3, lda=Cin, nB=B, H=H, W=W, Wt=wk.to(DEV), M=M, N=Cout, K=9 * Cin,
+                  dtype=L.SRK_FP16, bias=bk.to(DEV), act=L.ACT_LRELU, res=res.to(DEV), out32=o32, ld32=Cout,
+                  out16=o16, ld16=Cout, out16_dtype=L.SRK_FP16, out16_mode=L.O16_ROWS)
+            exp = F.leaky_relu(ref, 0.01).permute(0, 2, 3, 1).reshape(M, Cout) + res
+            assert float((o32.cpu() - exp).abs().max()) < 3e-3 * max(1.0, float(exp.abs().max()))
+            assert float((o16.float().cpu() - exp).abs().max()) < 0.02 * max(1.0, float(exp.abs().max()))
+    # pixelshuffle-direct image epilogue with crop (C -> s*s, s = 4)
+    Cin, s = 64, 4
+    x = torch.randn(B, Cin, H, W, generator=g).half()
+    wt = (torch.randn(s * s, Cin, 3, 3, generator=g) * 0.05).half()
+    bias = torch.randn(s * s, generator=g)
+    wk, bk = P.pack_conv3x3(wt.float(), bias, Cin, 64, L.SRK_FP16)
+    hc, wc = H * s - 5, W * s - 3
+    img = torch.zeros(B, 1, hc, wc, device=DEV)
+    _gemm(L, A=x.permute(0, 2, 3, 1).contiguous().to(DEV), a_mode=L.A_CONV3X3, lda=Cin, nB=B, H=H, W=W,
+          Wt=wk.to(DEV), M=B * H * W, N=64, K=9 * Cin, dtype=L.SRK_FP16, bias=bk.to(DEV), img=img, img_s=s,
+          img_scale=0.5, img_hc=hc, img_wc=wc)
+    exp = F.pixel_shuffle(F.conv2d(x.float(), wt.float(), bias, padding=1), s)[:, :, :hc, :wc] * 0.5
+    assert float((img.cpu() - exp).abs().max()) < 3e-3 * max(1.0, float(exp.abs().max()))
+
+
+@pytest.mark.parametrize("geom", [(60, 6, 16, 16, 24), (180, 6, 32, 24, 16), (64, 2, 32, 8, 8)])
+def test_window_attention(L, geom):
+    Cdim, nh, dp, H, W = geom
+    d = Cdim // nh
+    B = 2
+    g = torch.Generator().manual_seed(6)
+    M = B * H * W
+    nq = 3 * nh * dp
+    ldq, ldo = (nq + 63) // 64 * 64, (nh * dp + 63) // 64 * 64
+    table = torch.randn(225, nh, generator=g) * 0.5
+    for shift in (0, 4):
+        qkv = torch.zeros(M, 3, nh, dp)
+        qkv[..., :d] = torch.randn(M, 3, nh, d, generator=g)
+        qkv = qkv.bfloat16()
+        buf = torch.zeros(M, ldq, dtype=torch.bfloat16)
+        buf[:, :nq] = qkv.view(M, nq)
+        out = torch.full((M, ldo), 9.0, dtype=torch.bfloat16, device=DEV)
+        L.check(L.load().srk_window_attention(L.ptr(buf.to(DEV)), ldq, L.ptr(out), ldo,
+                                              L.ptr(table.t().contiguous().to(DEV)), B, H, W, nh, dp,
+                                              d ** -0.5, shift, L.stream_ptr()))
+        q, k, v = [qkv[:, i, :, :d].float().view(-1, 64, nh, d).transpose(1, 2) for i in range(3)]
+        att = (q @ k.transpose(-1, -2)) * d ** -0.5
+        att = att + table[O.relative_position_index(8).reshape(-1)].view(64, 64, nh).permute(2, 0, 1)[None]
+        if shift:
+            m = O.shift_attention_mask(H, W, 8, shift)
+            att = (att.view(B, -1, nh, 64, 64) + m[None, :, None]).view(-1, nh, 64, 64)
+        p = torch.softmax(att, -1).bfloat16().float()
+        o = (p @ v).transpose(1, 2).reshape(M, nh, d)
+        got = out.float().cpu()[:, :nh * dp].view(M, nh, dp)
+        assert float((got[..., :d] - o).abs().max()) < 0.03
+        assert float(got[..., d:].abs().max()) == 0.0
+        assert float(out.float().cpu()[:, nh * dp:].abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------
+# networks
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name", ["swinir_tiny_direct", "swinir_tiny_ps"])
+def test_swinir_tiny_against_reference_golden(L, engine, name):
+    L.set_engine(engine)
+    z, sd, cfgd = load_npz(name)
+    cfg = O.SwinIRCfg(**cfgd)
+    net = make_swinir(cfg, sd)
+    i = 0
+    while f"x{i}" in z.files:
+        x = torch.from_numpy(z[f"x{i}"])
+        y = net(x.to(DEV)).cpu()
+        ref = torch.from_numpy(z[f"y{i}"])
+        emu = O.swinir_forward(sd, cfg, x, emulate_bf16=True)
+        assert y.shape == ref.shape
+        assert float((y - emu).abs().max()) < 6e-4, "indexing / arithmetic-contract mismatch"
+        assert float((y - ref).abs().max()) < 2e-3, "SR output tolerance (north_star)"
+        i += 1
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_edsr_tiny_against_reference_golden(L, engine):
+    L.set_engine(engine)
+    from sr_caco_2_b200 import EDSR
+    z, sd, cfgd = load_npz("edsr_tiny")
+    net = EDSR(in_chans=cfgd["in_chans"], n_resblocks=cfgd["n_resblocks"], n_feats=cfgd["n_feats"],
+               scale=cfgd["scale"])
+    net.load_state_dict(sd, strict=True)
+    net = net.to(DEV).eval()
+    y = net(torch.from_numpy(z["x0"]).to(DEV)).cpu()
+    assert float((y - torch.from_numpy(z["y0"])).abs().max()) < 2e-3
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_baseline_configs_against_reference_samples(L, engine):
+    """BASELINE.json configs on tests/common.py weights: strided samples of the unmodified
+    reference's output (tests/golden/fullsize_samples.json), 2e-3 max-abs."""
+    L.set_engine(engine)
+    gold = json.load(open(os.path.join(T.GOLDEN, "fullsize_samples.json")))
+    jobs = [("cfg1_light_x2_64", T.cfg_light_x2(), (4, 64, 64), 101),
+            ("cfg1_light_x2_72", T.cfg_light_x2(), (2, 72, 72), 101),
+            ("cfg3_classical_x8_64", T.cfg_classical(8), (1, 64, 64), 103),
+            ("cfg4_classical_x4_72", T.cfg_classical(4), (1, 72, 72), 104)]
+    for name, cfg, (B, h, w), seed in jobs:
+        net = make_swinir(cfg, T.swinir_state_dict(cfg, seed=seed))
+        y = net(T.synthetic_lr(B, h, w, seed).to(DEV)).cpu()
+        gd = gold[name]
+        assert list(y.shape) == gd["shape"]
+        got = y.reshape(-1)[torch.tensor(gd["idx"])].double().numpy()
+        err = np.abs(got - np.array(gd["val"])).max()
+        assert err < 2e-3, (name, err)
+        del net
+    from sr_caco_2_b200 import EDSR
+    cfg = T.cfg_edsr_x4()
+    net = EDSR(in_chans=1, n_resblocks=16, n_feats=64, scale=4)
+    net.load_state_dict(T.edsr_state_dict(cfg, seed=102), strict=True)
+    y = net.to(DEV).eval()(T.synthetic_lr(2, 64, 64, 102).to(DEV)).cpu()
+    gd = gold["cfg2_edsr_x4_64"]
+    got = y.reshape(-1)[torch.tensor(gd["idx"])].double().numpy()
+    assert np.abs(got - np.array(gd["val"])).max() < 2e-3
+
+
+def test_cfg1_full_output_and_metrics_against_oracle(L):
+    """configs[0] end to end: whole SR output vs the CPU oracle (2e-3) and the scores the
+    evaluator reports vs the oracle's scores of the oracle's output (0.01 dB / 1e-4)."""
+    from sr_caco_2_b200 import utils_image as UI
+    cfg = T.cfg_light_x2()
+    sd = T.swinir_state_dict(cfg, seed=101)
+    net = make_swinir(cfg, sd)
+    x = T.synthetic_lr(4, 64, 64, 101)
+    ref = O.swinir_forward(sd, cfg, x)
+    y = net(x.to(DEV))
+    assert float((y.cpu() - ref).abs().max()) < 2e-3
+    Hr = (ref + 0.03 * torch.randn(ref.shape, generator=torch.Generator().manual_seed(1))).clamp(0, 1)
+    Hr = (Hr * 255).round() / 255
+    m = UI.compute_metrics(y, Hr.to(DEV), cfg.upscale, (4, 5, 6, 7, 8, 9, 10))
+    om, orm = O.all_metrics(ref, Hr, cfg.upscale), O.roi_marginal_metrics(ref, Hr, cfg.upscale)
+    assert float((m["psnr"].cpu() - om["psnr"]).abs().max()) < 0.01
+    assert float((m["ssim"].cpu() - om["ssim"].double()).abs().max()) < 1e-4
+    assert float((m["psnr_y"].cpu() - om["psnr_y"]).abs().max()) < 0.01
+    assert float((m["roi_psnr"].cpu() - orm["psnr"]).abs().max()) < 0.01
+    assert float((m["roi_ssim"].cpu() - orm["ssim"].double()).abs().max()) < 1e-4
+    assert float(((m["nrmse"].cpu() - om["nrmse"]) / om["nrmse"]).abs().max()) < 5e-3
+
+
+def test_headline_config_properties_at_full_size(L):
+    """configs[2] (classical X8, B=32, 64x64 -> 512x512) at BASELINE size: batch independence,
+    determinism, reflect-pad equivalence and finiteness -- properties that need no CPU oracle."""
+    cfg = T.cfg_classical(8)
+    net = make_swinir(cfg, T.swinir_state_dict(cfg, seed=103))
+    x = T.synthetic_lr(32, 64, 64, 103).to(DEV)
+    y = net(x)
+    assert y.shape == (32, 1, 512, 512) and bool(torch.isfinite(y).all())
+    assert torch.equal(y, net(x))                                  # deterministic
+    y1 = net(x[5:6])
+    assert float((y[5:6] - y1).abs().max()) == 0.0                  # patches are independent
+    perm = torch.randperm(32, device=DEV)
+    assert torch.equal(net(x[perm]), y[perm])
+    # a 61x59 crop is reflect-padded inside the net exactly like F.pad(..., 'reflect')
+    xc = x[:2, :, :61, :59].contiguous()
+    yc = net(xc)
+    yp = net(F.pad(xc, (0, 5, 0, 3), mode="reflect"))[:, :, :61 * 8, :59 * 8]
+    assert yc.shape == (2, 1, 488, 472) and float((yc - yp).abs().max()) == 0.0
+
+
+def test_evaluator_end_to_end_matches_oracle(L):
+    from sr_caco_2_b200.evaluator import evaluate_patches, make_cuda_step, pad_for_windows
+    cfg = O.SwinIRCfg(upscale=2, in_chans=1, img_size=32, depths=[2, 2], embed_dim=60, num_heads=[6, 6],
+                      mlp_ratio=2, upsampler="pixelshuffledirect")
+    sd = T.swinir_state_dict(cfg, seed=9)
+    net = make_swinir(cfg, sd)
+    lr = T.synthetic_lr(5, 24, 24, 9)
+    ref = O.swinir_forward(sd, cfg, pad_for_windows(lr))[..., :48, :48]
+    hr = ((ref + 0.02 * torch.randn(ref.shape, generator=torch.Generator().manual_seed(2))).clamp(0, 1) * 255).round() / 255
+    res = evaluate_patches(make_cuda_step(net, 2, True), lr, hr, batch_size=2, device=torch.device(DEV))
+    om, orm = O.all_metrics(ref, hr, 2), O.roi_marginal_metrics(ref, hr, 2)
+    assert res["n"] == 5
+    assert abs(res["psnr"] - float(om["psnr"].mean())) < 0.01
+    assert abs(res["ssim"] - float(om["ssim"].double().mean())) < 1e-4
+    assert abs(res["roi_psnr"] - float(orm["psnr"].mean())) < 0.01
+    assert abs(res["roi_ssim"] - float(orm["ssim"].double().mean())) < 1e-4
