@@ -66,7 +66,7 @@ def build(force=False, verbose=False):
     if failed:
         sys.stderr.write("\n".join(log))
         raise RuntimeError("nvcc failed; see sr_caco_2_b200/build/nvcc.log")
-    cmd = [nvcc_path(), "-shared", "-o", OUT, *objs, "-lcudart", "-lcuda"]
+    cmd = [nvcc_path(), "-shared", "-o", OUT, *objs, "-lcudart"]
     subprocess.check_call(cmd)
     with open(STAMP, "w") as fh:
         fh.write(dig)

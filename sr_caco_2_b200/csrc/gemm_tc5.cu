@@ -1,6 +1,485 @@
+// tcgen05 GEMM engine (the product path): persistent, warp-specialised, TMA-fed, TMEM
+// accumulators, fused epilogues.
+//
+//   D[128 x BN] (fp32, TMEM) += A[128 x 64] (smem, 128B swizzle, K-major) * B[BN x 64]^T (smem)
+//
+//   warp 0      : TMA producer.  A tiles come either from a 2-D tensor map over the (M, K) row
+//                 matrix, or -- implicit-GEMM 3x3 convolution -- from a 4-D tensor map over the
+//                 NHWC image: for tap (dy,dx) the box (64 ch, BW, BH, 1) is fetched at
+//                 (c0, x0+dx-1, y0+dy-1, b); TMA's out-of-bounds zero fill IS the conv padding
+//                 and the halo, no im2col buffer exists anywhere.  Weights: 2-D map over (N, K).
+//   warp 1      : allocates TMEM (2 accumulator stages), issues tcgen05.mma (one lane), commits
+//                 to the smem "empty" barriers and to the TMEM "full" barrier.
+//   warps 2..5  : epilogue.  Thread = accumulator row (TMEM lane); tcgen05.ld 32 columns at a
+//                 time; bias, activation, residual (fp32 stream, with the window_reverse + roll
+//                 row map), fp32 / 16-bit stores, PixelShuffle(2) / pixelshuffle-direct
+//                 addressing, and optionally LayerNorm of the finished row (the thread owns the
+//                 whole row, so the statistics are thread-local; the row is parked in TMEM with
+//                 tcgen05.st between the passes).
+//   The epilogue of tile i overlaps the MMAs of tile i+1 (two TMEM stages).
 #include "gemm_common.cuh"
+#include <cuda.h>
+
 namespace srk {
-int gemm_tcgen05(const srk_gemm_args* g, cudaStream_t st) {
-    return fail(SRK_ERR_UNSUPPORTED, "tcgen05 engine not built yet");
+
+constexpr int TBM = 128, TBK = 64;
+constexpr int TC_THREADS = 192;           // 6 warps
+constexpr int TC_SMEM_BUDGET = 200 * 1024;
+
+// ---- PTX wrappers ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte swizzled operand tile (rows of 64 x 16-bit = 128 B, 8-row groups of 1024 B):
+// start address >> 4 | LBO (unused for swizzled K-major, 1) | SBO = 1024 B | version 1 | SWIZZLE_128B
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::f16 instruction descriptor: D fp32, A/B both `fmt` (0 = F16, 1 = BF16), K-major A and B
+__host__ __device__ constexpr uint32_t umma_idesc(int fmt, int M, int N) {
+    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
+}
+
+struct TcParams {
+    GemmP g;
+    int n_tiles, m_tiles, nkb;
+    int conv_bw, conv_bh, conv_tx, conv_ty;     // conv-mode M tiling (box BW x BH = 128 pixels)
+};
+
+template <int BN>
+struct TcCfg {
+    static constexpr int A_BYTES = TBM * TBK * 2;
+    static constexpr int B_BYTES = BN * TBK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (TC_SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (TC_SMEM_BUDGET / STAGE_BYTES);
+    static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// row (0..127) of M tile `mt` -> GEMM row index m (or -1 when the row is outside the problem)
+__device__ __forceinline__ int tile_row_to_m(const TcParams& p, int mt, int r) {
+    const GemmP& g = p.g;
+    if (g.a_mode == SRK_A_ROWS) {
+        const int m = mt * TBM + r;
+        return m < g.M ? m : -1;
+    }
+    const int per_img = p.conv_tx * p.conv_ty;
+    const int b = mt / per_img, t = mt - b * per_img;
+    const int ty = t / p.conv_tx, tx = t - ty * p.conv_tx;
+    const int py = r / p.conv_bw, px = r - py * p.conv_bw;
+    const int y = ty * p.conv_bh + py, x = tx * p.conv_bw + px;
+    if (y >= g.H || x >= g.W) return -1;
+    return (b * g.H + y) * g.W + x;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                const TcParams p) {
+    using Cfg = TcCfg<BN>;
+    extern __shared__ unsigned char tc_smem_raw[];
+    const uint32_t raw = smem_u32(tc_smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;                     // SW128 tiles need 1024 B alignment
+    const uint32_t bars = base + Cfg::STAGES * Cfg::STAGE_BYTES;      // full[S] empty[S] tfull[2] tempty[2] tmem_ptr
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (Cfg::STAGES + s); };
+    auto tfull_bar = [&](int s) { return bars + 8u * (2 * Cfg::STAGES + s); };
+    auto tempty_bar = [&](int s) { return bars + 8u * (2 * Cfg::STAGES + 2 + s); };
+    const uint32_t tmem_slot = bars + 8u * (2 * Cfg::STAGES + 4);
+    volatile uint32_t* tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t*>(tc_smem_raw + (tmem_slot - raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const GemmP& g = p.g;
+    const int total_tiles = p.m_tiles * p.n_tiles;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                     "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            int stage = 0, phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+                int cb_, cx = 0, cy = 0;
+                if (g.a_mode == SRK_A_CONV3X3) {
+                    const int per_img = p.conv_tx * p.conv_ty;
+                    cb_ = mt / per_img;
+                    const int t = mt - cb_ * per_img;
+                    cy = (t / p.conv_tx) * p.conv_bh;
+                    cx = (t - (t / p.conv_tx) * p.conv_tx) * p.conv_bw;
+                } else {
+                    cb_ = 0;
+                }
+                for (int kb = 0; kb < p.nkb; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    const uint32_t sa = base + stage * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
+                    mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+                    if (g.a_mode == SRK_A_CONV3X3) {
+                        const int tap = kb / g.cpb, cblk = kb - tap * g.cpb;
+                        const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+                        tma_load_4d(sa, &map_a, full_bar(stage), cblk * 64, cx + dx, cy + dy, cb_);
+                    } else {
+                        tma_load_2d(sa, &map_a, full_bar(stage), kb * TBK, mt * TBM);
+                    }
+                    tma_load_2d(sb, &map_b, full_bar(stage), kb * TBK, nt * BN);
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ================================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc(g.dtype == SRK_BF16 ? 1 : 0, TBM, BN);
+            int stage = 0, phase = 0, it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int as = it & 1, aphase = (it >> 1) & 1;
+                mbar_wait(tempty_bar(as), aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+                for (int kb = 0; kb < p.nkb; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sa = base + stage * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
+                    const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sb);
+#pragma unroll
+                    for (int k = 0; k < TBK / 16; ++k)        // +32 B per UMMA_K inside the swizzle atom
+                        tc_mma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                                   (kb | k) != 0 ? 1u : 0u);
+                    tc_commit(empty_bar(stage));               // frees the smem slot when the MMAs retire
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(tfull_bar(as));                      // accumulator complete
+            }
+        }
+    } else {
+        // ================================ epilogue ================================
+        const int lg = warp & 3;                               // TMEM lane group this warp may access
+        const int r = lg * 32 + lane;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+            const int as = it & 1, aphase = (it >> 1) & 1;
+            const int n0 = nt * BN;
+            const int m = tile_row_to_m(p, mt, r);
+            const bool valid = m >= 0;
+            const int r32 = (valid && (g.res || g.out32 || g.ln_g)) ? row32_of(g, m) : 0;
+            mbar_wait(tfull_bar(as), aphase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN);
+            const float* res_row = g.res ? g.res + (size_t)r32 * g.ld32 + n0 : nullptr;
+            float* o32_row = g.out32 ? g.out32 + (size_t)r32 * g.ld32 + n0 : nullptr;
+            float lsum = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32];
+                tc_ld32(t_row + c * 32, v);
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    f[j] = apply_act(__uint_as_float(v[j]) + __ldg(g.bias + n0 + c * 32 + j), g.act);
+                }
+                if (valid) {
+                    if (res_row) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 rr = *reinterpret_cast<const float4*>(res_row + c * 32 + j);
+                            f[j] = f[j] * g.res_scale + rr.x; f[j + 1] = f[j + 1] * g.res_scale + rr.y;
+                            f[j + 2] = f[j + 2] * g.res_scale + rr.z; f[j + 3] = f[j + 3] * g.res_scale + rr.w;
+                        }
+                    }
+                    if (o32_row) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(o32_row + c * 32 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                    }
+                    if (g.out16 && !g.ln_g) {
+                        if (g.out16_mode == SRK_O16_ROWS) {
+                            uint16_t* o = g.out16 + (size_t)m * g.ld16 + n0 + c * 32;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8)
+                                *reinterpret_cast<uint4*>(o + j) =
+                                    make_uint4(pack2(f[j], f[j + 1], g.out16_dtype), pack2(f[j + 2], f[j + 3], g.out16_dtype),
+                                               pack2(f[j + 4], f[j + 5], g.out16_dtype), pack2(f[j + 6], f[j + 7], g.out16_dtype));
+                        } else {
+                            // PixelShuffle(2): a 32-column chunk never straddles a sub-pixel group (N/4 % 32 == 0)
+                            uint16_t* o = g.out16 + off16_of(g, m, n0 + c * 32);
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8)
+                                *reinterpret_cast<uint4*>(o + j) =
+                                    make_uint4(pack2(f[j], f[j + 1], g.out16_dtype), pack2(f[j + 2], f[j + 3], g.out16_dtype),
+                                               pack2(f[j + 4], f[j + 5], g.out16_dtype), pack2(f[j + 6], f[j + 7], g.out16_dtype));
+                        }
+                    }
+                    if (g.img) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            size_t off;
+                            if (offimg_of(g, m, n0 + c * 32 + j, off)) g.img[off] = f[j] * g.img_scale;
+                        }
+                    }
+                }
+                if (g.ln_g) {                                  // park the finished row in TMEM, sum for the mean
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (n0 + c * 32 + j < g.ln_C) lsum += f[j];
+                        v[j] = __float_as_uint(f[j]);
+                    }
+                    tc_st32(t_row + c * 32, v);
+                }
+            }
+            if (g.ln_g) {
+                // LayerNorm of the row this thread owns (two more passes over TMEM)
+                const float mean = lsum / (float)g.ln_C;
+                float q = 0.f;
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t v[32];
+                    tc_ld32(t_row + c * 32, v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float dlt = __uint_as_float(v[j]) - mean;
+                        if (c * 32 + j < g.ln_C) q += dlt * dlt;
+                    }
+                }
+                const float rstd = 1.f / sqrtf(q / (float)g.ln_C + 1e-5f);
+                int row16 = r32;
+                if (valid && g.ln_win_shift >= 0) {
+                    const int bi = r32 / g.T;
+                    row16 = bi * g.T + token_to_win_pos(r32 - bi * g.T, g.H, g.W, g.ln_win_shift);
+                }
+                uint16_t* o = g.out16 + (size_t)row16 * g.ld16;
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t v[32];
+                    tc_ld32(t_row + c * 32, v);
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int n = c * 32 + j;
+                        f[j] = n < g.ln_C ? (__uint_as_float(v[j]) - mean) * rstd * __ldg(g.ln_g + n) + __ldg(g.ln_b + n) : 0.f;
+                    }
+                    if (valid) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8)
+                            *reinterpret_cast<uint4*>(o + c * 32 + j) =
+                                make_uint4(pack2(f[j], f[j + 1], g.out16_dtype), pack2(f[j + 2], f[j + 3], g.out16_dtype),
+                                           pack2(f[j + 4], f[j + 5], g.out16_dtype), pack2(f[j + 6], f[j + 7], g.out16_dtype));
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(as));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                     "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+static int encode_map(CUtensorMap* map, int dtype, int rank, const void* ptr, const cuuint64_t* dims,
+                      const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return fail(SRK_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult rc = enc(map, dtype == SRK_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                      (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) return fail(SRK_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)rc);
+    return 0;
+}
+
+static int num_sms() {
+    static int n[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && n[dev]) return n[dev];
+    int v = 148;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (dev < 64) n[dev] = v;
+    return v;
+}
+
+template <int BN>
+static int launch_tc5(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st) {
+    using Cfg = TcCfg<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SRK_CUDA(cudaFuncSetAttribute(gemm_tc5_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        attr_set = true;
+    }
+    const int total = p.m_tiles * p.n_tiles;
+    const int grid = total < num_sms() ? total : num_sms();
+    gemm_tc5_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM, st>>>(ma, mb, p);
+    SRK_LAUNCH_CHECK("gemm_tc5_kernel");
+    return 0;
+}
+
+int gemm_tcgen05(const srk_gemm_args* a, cudaStream_t st) {
+    SRK_REQUIRE(a->N % 64 == 0, "gemm(tcgen05): N=%d must be a multiple of 64", a->N);
+    SRK_REQUIRE(((uintptr_t)a->A & 15) == 0 && ((uintptr_t)a->Wt & 15) == 0, "gemm(tcgen05): operands must be 16 B aligned");
+    TcParams p{};
+    p.g = make_gemm_params(a);
+    const int BN = a->N % 256 == 0 ? 256 : (a->N % 192 == 0 ? 192 : (a->N % 128 == 0 ? 128 : 64));
+    if (a->ln_g) {
+        SRK_REQUIRE(a->N == BN, "gemm(tcgen05): fused LayerNorm needs the whole row in one tile (N=%d)", a->N);
+        SRK_REQUIRE(a->out16 && a->out16_mode == SRK_O16_ROWS && a->ln_b && a->ln_C > 0 && a->ln_C <= a->N,
+                    "gemm(tcgen05): bad fused LayerNorm arguments");
+    }
+    if (a->out16 && a->out16_mode == SRK_O16_PIXSHUF2)
+        SRK_REQUIRE((a->N / 4) % 32 == 0, "gemm(tcgen05): pixel-shuffle output needs N/4 %% 32 == 0");
+    if (a->res || a->out32) SRK_REQUIRE(a->ld32 % 4 == 0, "gemm(tcgen05): ld32 %% 4");
+    p.n_tiles = a->N / BN;
+    p.nkb = a->K / TBK;
+    CUtensorMap ma, mb;
+    if (a->a_mode == SRK_A_CONV3X3) {
+        // pick the 128-pixel box (BW x BH) that wastes the fewest out-of-image pixels
+        long best = -1;
+        for (int bw = 8; bw <= 128; bw *= 2) {
+            const int bh = 128 / bw;
+            const long cover = (long)((a->W + bw - 1) / bw) * bw * (long)((a->H + bh - 1) / bh) * bh;
+            if (best < 0 || cover < best) { best = cover; p.conv_bw = bw; p.conv_bh = bh; }
+        }
+        p.conv_tx = (a->W + p.conv_bw - 1) / p.conv_bw;
+        p.conv_ty = (a->H + p.conv_bh - 1) / p.conv_bh;
+        p.m_tiles = a->nB * p.conv_tx * p.conv_ty;
+        cuuint64_t dims[4] = {(cuuint64_t)a->lda, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->nB};
+        cuuint64_t strides[3] = {(cuuint64_t)a->lda * 2, (cuuint64_t)a->W * a->lda * 2, (cuuint64_t)a->H * a->W * a->lda * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)p.conv_bw, (cuuint32_t)p.conv_bh, 1};
+        if (int rc = encode_map(&ma, a->dtype, 4, a->A, dims, strides, box)) return rc;
+    } else {
+        p.m_tiles = ceil_div(a->M, TBM);
+        cuuint64_t dims[2] = {(cuuint64_t)a->K, (cuuint64_t)a->M};
+        cuuint64_t strides[1] = {(cuuint64_t)a->lda * 2};
+        cuuint32_t box[2] = {64, 128};
+        if (int rc = encode_map(&ma, a->dtype, 2, a->A, dims, strides, box)) return rc;
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)a->K, (cuuint64_t)a->N};
+        cuuint64_t strides[1] = {(cuuint64_t)a->K * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)BN};
+        if (int rc = encode_map(&mb, a->dtype, 2, a->Wt, dims, strides, box)) return rc;
+    }
+    switch (BN) {
+        case 256: return launch_tc5<256>(ma, mb, p, st);
+        case 192: return launch_tc5<192>(ma, mb, p, st);
+        case 128: return launch_tc5<128>(ma, mb, p, st);
+        default: return launch_tc5<64>(ma, mb, p, st);
+    }
+}
+
+}  // namespace srk
