@@ -1,0 +1,71 @@
+"""Per-shape timing of the GEMM calls of cfg3 (B=32, 64x64): us, TFLOP/s, GB/s of algorithmic bytes."""
+import ctypes as C, sys, os, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from sr_caco_2_b200 import _lib as L
+L.load()
+dev = "cuda:0"
+eng = sys.argv[1] if len(sys.argv) > 1 else "tcgen05"
+L.set_engine(eng)
+B, H, W = 32, 64, 64
+M = B * H * W
+
+def run(name, **kw):
+    g = L.GemmArgs(); g.res_scale, g.win_shift, g.ln_win_shift = 1.0, -1, -1
+    keep = []
+    for k, v in kw.items():
+        if isinstance(v, torch.Tensor): keep.append(v); v = L.ptr(v)
+        setattr(g, k, v)
+    lib = L.load()
+    if os.environ.get("SRK_PROFILE_ONCE"):
+        L.check(lib.srk_gemm(C.byref(g), L.stream_ptr())); torch.cuda.synchronize(); return 1.0
+    for _ in range(3): L.check(lib.srk_gemm(C.byref(g), L.stream_ptr()))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 10
+    e0.record()
+    for _ in range(n): L.check(lib.srk_gemm(C.byref(g), L.stream_ptr()))
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n * 1e3  # us
+
+def t16(*shape, dt=torch.bfloat16): return (torch.randn(*shape, device=dev) * 0.1).to(dt)
+rows = []
+def report(name, us, flops, bytes_):
+    rows.append(dict(name=name, us=round(us, 1), tflops=round(flops / us / 1e6, 1), gbs=round(bytes_ / us / 1e3, 1)))
+    print(f"{name:28s} {us:9.1f} us  {flops/us/1e6:8.1f} TFLOP/s  {bytes_/us/1e3:8.1f} GB/s", flush=True)
+
+Cp = 192
+A = t16(M, Cp); bias = torch.zeros(576, device=dev)
+X = torch.randn(M, Cp, device=dev); X2 = torch.empty_like(X)
+lng = torch.ones(180, device=dev); lnb = torch.zeros(180, device=dev)
+# qkv
+Wq = t16(576, Cp); QKV = torch.empty(M, 576, device=dev, dtype=torch.bfloat16)
+us = run("qkv", A=A, a_mode=0, lda=Cp, nB=B, H=H, W=W, Wt=Wq, M=M, N=576, K=Cp, dtype=0, bias=bias, out16=QKV, ld16=576, out16_dtype=0)
+report("qkv N576 K192 ->bf16", us, 2*M*576*192, M*(384+1152))
+Wp = t16(192, 192); A16 = torch.empty(M, Cp, device=dev, dtype=torch.bfloat16)
+us = run("proj", A=A, a_mode=0, lda=Cp, nB=B, H=H, W=W, Wt=Wp, M=M, N=192, K=192, dtype=0, bias=bias, res=X, out32=X2, ld32=Cp, win_shift=4,
+         ln_g=lng, ln_b=lnb, ln_C=180, out16=A16, ld16=Cp, out16_dtype=0)
+report("proj N192 K192 +res+LN", us, 2*M*192*192, M*(384+768+768+384))
+us = run("proj_nores", A=A, a_mode=0, lda=Cp, nB=B, H=H, W=W, Wt=Wp, M=M, N=192, K=192, dtype=0, bias=bias, out16=A16, ld16=Cp, out16_dtype=0)
+report("  (N192 K192 ->bf16 only)", us, 2*M*192*192, M*(384+384))
+W1 = t16(384, 192); HID = torch.empty(M, 384, device=dev, dtype=torch.bfloat16)
+us = run("fc1", A=A, a_mode=0, lda=Cp, nB=B, H=H, W=W, Wt=W1, M=M, N=384, K=192, dtype=0, bias=bias, act=1, out16=HID, ld16=384, out16_dtype=0)
+report("fc1 N384 K192 GELU->bf16", us, 2*M*384*192, M*(384+768))
+W2 = t16(192, 384)
+us = run("fc2", A=HID, a_mode=0, lda=384, nB=B, H=H, W=W, Wt=W2, M=M, N=192, K=384, dtype=0, bias=bias, res=X, out32=X2, ld32=Cp,
+         ln_g=lng, ln_b=lnb, ln_C=180, ln_win_shift=4, out16=A16, ld16=Cp, out16_dtype=0)
+report("fc2 N192 K384 +res+LN", us, 2*M*192*384, M*(768+768+768+384))
+Ah = t16(M, Cp, dt=torch.float16); Wc = t16(192, 9*192, dt=torch.float16)
+us = run("convCC", A=Ah, a_mode=1, lda=Cp, nB=B, H=H, W=W, Wt=Wc, M=M, N=192, K=9*192, dtype=1, bias=bias, res=X, out32=X2, ld32=Cp)
+report("conv 192->192 +res", us, 2*M*192*1728, M*(384+768+768))
+Wb = t16(64, 9*192, dt=torch.float16); U0 = torch.empty(M, 64, device=dev, dtype=torch.float16)
+us = run("before_up", A=Ah, a_mode=1, lda=Cp, nB=B, H=H, W=W, Wt=Wb, M=M, N=64, K=9*192, dtype=1, bias=bias, act=2, out16=U0, ld16=64, out16_dtype=1)
+report("conv 192->64 lrelu", us, 2*M*64*1728, M*(384+128))
+Wu = t16(256, 9*64, dt=torch.float16)
+for k, (hh, ww) in enumerate([(64, 64), (128, 128), (256, 256)]):
+    Mi = B*hh*ww
+    Ui = t16(Mi, 64, dt=torch.float16); Uo = torch.empty(Mi*4, 64, device=dev, dtype=torch.float16)
+    us = run("up", A=Ui, a_mode=1, lda=64, nB=B, H=hh, W=ww, Wt=Wu, M=Mi, N=256, K=576, dtype=1, bias=bias, out16=Uo, ld16=64, out16_dtype=1, out16_mode=1)
+    report(f"up{k} 64->256 ps @{hh}", us, 2*Mi*256*576, Mi*(128+512))
+    del Ui, Uo
+json.dump(rows, open(f"gpurun_out/gemm_bench_{eng}.json", "w"), indent=1)

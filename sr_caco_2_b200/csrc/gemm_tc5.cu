@@ -10,12 +10,13 @@
 //                 and the halo, no im2col buffer exists anywhere.  Weights: 2-D map over (N, K).
 //   warp 1      : allocates TMEM (2 accumulator stages), issues tcgen05.mma (one lane), commits
 //                 to the smem "empty" barriers and to the TMEM "full" barrier.
-//   warps 2..5  : epilogue.  Thread = accumulator row (TMEM lane); tcgen05.ld 32 columns at a
-//                 time; bias, activation, residual (fp32 stream, with the window_reverse + roll
-//                 row map), fp32 / 16-bit stores, PixelShuffle(2) / pixelshuffle-direct
-//                 addressing, and optionally LayerNorm of the finished row (the thread owns the
-//                 whole row, so the statistics are thread-local; the row is parked in TMEM with
-//                 tcgen05.st between the passes).
+//   warps 2..9  : epilogue (two warps per TMEM lane group).  Phase T: tcgen05.ld drains the
+//                 accumulator (thread = row) into a padded fp32 staging tile in shared memory
+//                 and releases the TMEM stage.  Phase R: the same warps walk the staged rows
+//                 with lane = column pair, so every global access is a coalesced 128/256 B row
+//                 segment: bias, activation, residual (fp32 stream, window_reverse + roll row
+//                 map), fp32 / 16-bit stores, PixelShuffle(2) / pixelshuffle-direct addressing
+//                 and, optionally, LayerNorm of the finished row (warp-shuffle statistics).
 //   The epilogue of tile i overlaps the MMAs of tile i+1 (two TMEM stages).
 #include "gemm_common.cuh"
 #include <cuda.h>
@@ -23,8 +24,8 @@
 namespace srk {
 
 constexpr int TBM = 128, TBK = 64;
-constexpr int TC_THREADS = 192;           // 6 warps
-constexpr int TC_SMEM_BUDGET = 200 * 1024;
+constexpr int TC_THREADS = 320;           // 10 warps: TMA, MMA, 8 epilogue
+constexpr int TC_SMEM_TOTAL = 227 * 1024;
 
 // ---- PTX wrappers ----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -43,11 +44,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "{\n"
         ".reg .pred P1;\n"
         "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
         "@P1 bra DONE;\n"
         "bra WAIT_LOOP;\n"
         "DONE:\n"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
+        "}\n" ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     asm volatile(
@@ -116,6 +117,28 @@ __host__ __device__ constexpr uint32_t umma_idesc(int fmt, int M, int N) {
            ((uint32_t)(M >> 4) << 24);
 }
 
+// epilogue specialisations (E_GENERIC keeps every option as a run-time flag)
+enum { E_GENERIC = 0, E_O16 = 1, E_RES_LN = 2, E_RES = 3, E_PIXSHUF = 4 };
+
+template <int DT>
+__device__ __forceinline__ uint32_t packf(float a, float b) {
+    if (DT == SRK_BF16) {
+        __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&t);
+    }
+    a = fminf(fmaxf(a, -65504.f), 65504.f);
+    b = fminf(fmaxf(b, -65504.f), 65504.f);
+    __half2 t = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+template <int ACT>
+__device__ __forceinline__ float actf(float v) {
+    if (ACT == SRK_ACT_GELU) return gelu_erf(v);
+    if (ACT == SRK_ACT_LRELU) return v > 0.f ? v : 0.01f * v;
+    if (ACT == SRK_ACT_RELU) return fmaxf(v, 0.f);
+    return v;
+}
+
 struct TcParams {
     GemmP g;
     int n_tiles, m_tiles, nkb;
@@ -127,9 +150,14 @@ struct TcCfg {
     static constexpr int A_BYTES = TBM * TBK * 2;
     static constexpr int B_BYTES = BN * TBK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (TC_SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (TC_SMEM_BUDGET / STAGE_BYTES);
+    static constexpr int SROW = BN + 4;                       // staging row stride (floats): conflict-free float4 / float2
+    static constexpr int STAGING_BYTES = TBM * SROW * 4;
+    static constexpr int AVAIL = TC_SMEM_TOTAL - STAGING_BYTES - 1024 - 256;
+    static constexpr int STAGES = (AVAIL / STAGE_BYTES) > 6 ? 6 : (AVAIL / STAGE_BYTES);
     static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
-    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static_assert(STAGES >= 3, "not enough shared memory for the operand pipeline");
+    static_assert(BN % 64 == 0 && BN <= 192, "BN must be 64, 128 or 192");
 };
 
 // row (0..127) of M tile `mt` -> GEMM row index m (or -1 when the row is outside the problem)
@@ -148,7 +176,7 @@ __device__ __forceinline__ int tile_row_to_m(const TcParams& p, int mt, int r) {
     return (b * g.H + y) * g.W + x;
 }
 
-template <int BN>
+template <int BN, int EPI, int ACT, int DT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 const TcParams p) {
@@ -156,7 +184,8 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     extern __shared__ unsigned char tc_smem_raw[];
     const uint32_t raw = smem_u32(tc_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                     // SW128 tiles need 1024 B alignment
-    const uint32_t bars = base + Cfg::STAGES * Cfg::STAGE_BYTES;      // full[S] empty[S] tfull[2] tempty[2] tmem_ptr
+    const uint32_t stg_base = base + Cfg::STAGES * Cfg::STAGE_BYTES;  // fp32 staging tile [128][SROW]
+    const uint32_t bars = stg_base + Cfg::STAGING_BYTES;              // full[S] empty[S] tfull[2] tempty[2] tmem_ptr
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (Cfg::STAGES + s); };
     auto tfull_bar = [&](int s) { return bars + 8u * (2 * Cfg::STAGES + s); };
@@ -171,7 +200,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
@@ -245,123 +274,200 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         }
     } else {
         // ================================ epilogue ================================
+        const int ew = warp - 2;                               // 0..7
         const int lg = warp & 3;                               // TMEM lane group this warp may access
-        const int r = lg * 32 + lane;
+        const int half = ew >> 2;                              // column half in phase T, row half in phase R
+        float* stg = reinterpret_cast<float*>(tc_smem_raw + (stg_base - raw)) + (size_t)(lg * 32) * Cfg::SROW;
+        constexpr int NP = BN / 64;                            // column pairs per lane
+        constexpr bool kRes = EPI == E_RES_LN || EPI == E_RES;
+        constexpr bool kPrefetch = kRes && NP <= 3;            // residual rows held in registers (<= 96)
+        const bool has_res = EPI == E_GENERIC ? (g.res != nullptr) : kRes;
+        const bool has_ln = EPI == E_GENERIC ? (g.ln_g != nullptr) : (EPI == E_RES_LN);
+        const int act = g.act;
+        const float inv_c = 1.f / (float)(g.ln_C > 0 ? g.ln_C : 1);
         int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
-            const int as = it & 1, aphase = (it >> 1) & 1;
-            const int n0 = nt * BN;
-            const int m = tile_row_to_m(p, mt, r);
-            const bool valid = m >= 0;
-            const int r32 = (valid && (g.res || g.out32 || g.ln_g)) ? row32_of(g, m) : 0;
-            mbar_wait(tfull_bar(as), aphase);
-            tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN);
-            const float* res_row = g.res ? g.res + (size_t)r32 * g.ld32 + n0 : nullptr;
-            float* o32_row = g.out32 ? g.out32 + (size_t)r32 * g.ld32 + n0 : nullptr;
-            float lsum = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t v[32];
-                tc_ld32(t_row + c * 32, v);
-                float f[32];
+        float2 lng[NP], lnb[NP];
+        if (has_ln) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    f[j] = apply_act(__uint_as_float(v[j]) + __ldg(g.bias + n0 + c * 32 + j), g.act);
-                }
-                if (valid) {
-                    if (res_row) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 rr = *reinterpret_cast<const float4*>(res_row + c * 32 + j);
-                            f[j] = f[j] * g.res_scale + rr.x; f[j + 1] = f[j + 1] * g.res_scale + rr.y;
-                            f[j + 2] = f[j + 2] * g.res_scale + rr.z; f[j + 3] = f[j + 3] * g.res_scale + rr.w;
-                        }
+            for (int k = 0; k < NP; ++k) {
+                const int n = 64 * k + 2 * lane;
+                lng[k] = n < g.ln_C ? __ldg(reinterpret_cast<const float2*>(g.ln_g + n)) : make_float2(0.f, 0.f);
+                lnb[k] = n < g.ln_C ? __ldg(reinterpret_cast<const float2*>(g.ln_b + n)) : make_float2(0.f, 0.f);
+            }
+        }
+        // row bookkeeping of one tile: lane i (< 16) describes row i of this warp's phase-R rows
+        auto rows_of = [&](int tile_, int& m_, int& r32_, int& r16_) {
+            m_ = -1; r32_ = 0; r16_ = 0;
+            if (tile_ >= total_tiles) return;
+            const int mt_ = tile_ / p.n_tiles;
+            m_ = lane < 16 ? tile_row_to_m(p, mt_, lg * 32 + half * 16 + lane) : -1;
+            if (m_ >= 0) {
+                r32_ = (has_res || g.out32 || has_ln) ? row32_of(g, m_) : m_;
+                r16_ = m_;
+                if (has_ln) {
+                    r16_ = r32_;
+                    if (g.ln_win_shift >= 0) {
+                        const int bi = r32_ / g.T;
+                        r16_ = bi * g.T + token_to_win_pos(r32_ - bi * g.T, g.H, g.W, g.ln_win_shift);
                     }
-                    if (o32_row) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<float4*>(o32_row + c * 32 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                    }
-                    if (g.out16 && !g.ln_g) {
-                        if (g.out16_mode == SRK_O16_ROWS) {
-                            uint16_t* o = g.out16 + (size_t)m * g.ld16 + n0 + c * 32;
-#pragma unroll
-                            for (int j = 0; j < 32; j += 8)
-                                *reinterpret_cast<uint4*>(o + j) =
-                                    make_uint4(pack2(f[j], f[j + 1], g.out16_dtype), pack2(f[j + 2], f[j + 3], g.out16_dtype),
-                                               pack2(f[j + 4], f[j + 5], g.out16_dtype), pack2(f[j + 6], f[j + 7], g.out16_dtype));
-                        } else {
-                            // PixelShuffle(2): a 32-column chunk never straddles a sub-pixel group (N/4 % 32 == 0)
-                            uint16_t* o = g.out16 + off16_of(g, m, n0 + c * 32);
-#pragma unroll
-                            for (int j = 0; j < 32; j += 8)
-                                *reinterpret_cast<uint4*>(o + j) =
-                                    make_uint4(pack2(f[j], f[j + 1], g.out16_dtype), pack2(f[j + 2], f[j + 3], g.out16_dtype),
-                                               pack2(f[j + 4], f[j + 5], g.out16_dtype), pack2(f[j + 6], f[j + 7], g.out16_dtype));
-                        }
-                    }
-                    if (g.img) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            size_t off;
-                            if (offimg_of(g, m, n0 + c * 32 + j, off)) g.img[off] = f[j] * g.img_scale;
-                        }
-                    }
-                }
-                if (g.ln_g) {                                  // park the finished row in TMEM, sum for the mean
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (n0 + c * 32 + j < g.ln_C) lsum += f[j];
-                        v[j] = __float_as_uint(f[j]);
-                    }
-                    tc_st32(t_row + c * 32, v);
                 }
             }
-            if (g.ln_g) {
-                // LayerNorm of the row this thread owns (two more passes over TMEM)
-                const float mean = lsum / (float)g.ln_C;
-                float q = 0.f;
+        };
+        // residual rows live in registers and are software-pipelined one tile ahead: as soon as
+        // row i of the current tile is finished, row i of the NEXT tile is requested into the
+        // same registers, so the HBM latency hides behind the rest of phase R + the next phase T
+        float2 resv[kPrefetch ? 16 : 1][NP];
+        int my_m, my_r32, my_r16;
+        rows_of(blockIdx.x, my_m, my_r32, my_r16);
+        if (kPrefetch) {
+            const int n0f = (blockIdx.x % p.n_tiles) * BN;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int m = __shfl_sync(0xffffffffu, my_m, i);
+                const int r32 = __shfl_sync(0xffffffffu, my_r32, i);
+                const float* rr = g.res + (size_t)r32 * g.ld32 + n0f + 2 * lane;
+#pragma unroll
+                for (int k = 0; k < NP; ++k)
+                    resv[kPrefetch ? i : 0][k] = m >= 0 ? __ldg(reinterpret_cast<const float2*>(rr + 64 * k)) : make_float2(0.f, 0.f);
+            }
+        }
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int nt = tile % p.n_tiles;
+            const int as = it & 1, aphase = (it >> 1) & 1;
+            const int n0 = nt * BN;
+            int nx_m, nx_r32, nx_r16;
+            rows_of(tile + gridDim.x, nx_m, nx_r32, nx_r16);
+            const int n0x = ((tile + (int)gridDim.x) % p.n_tiles) * BN;
+            float2 bia[NP];
+#pragma unroll
+            for (int k = 0; k < NP; ++k) bia[k] = __ldg(reinterpret_cast<const float2*>(g.bias + n0 + 64 * k + 2 * lane));
+
+            // ---- phase T: TMEM -> staging (thread = row, this warp's column chunks) ----
+            mbar_wait(tfull_bar(as), aphase);
+            tc_fence_after();
+            {
+                const uint32_t t_row = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN);
+                float* srow = stg + (size_t)lane * Cfg::SROW;
+                constexpr int CH = BN / 32;                    // 32-column chunks in the tile
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
+                for (int c = half; c < CH; c += 2) {           // chunks interleaved between the two warps
                     uint32_t v[32];
                     tc_ld32(t_row + c * 32, v);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float dlt = __uint_as_float(v[j]) - mean;
-                        if (c * 32 + j < g.ln_C) q += dlt * dlt;
-                    }
-                }
-                const float rstd = 1.f / sqrtf(q / (float)g.ln_C + 1e-5f);
-                int row16 = r32;
-                if (valid && g.ln_win_shift >= 0) {
-                    const int bi = r32 / g.T;
-                    row16 = bi * g.T + token_to_win_pos(r32 - bi * g.T, g.H, g.W, g.ln_win_shift);
-                }
-                uint16_t* o = g.out16 + (size_t)row16 * g.ld16;
-#pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
-                    uint32_t v[32];
-                    tc_ld32(t_row + c * 32, v);
-                    float f[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int n = c * 32 + j;
-                        f[j] = n < g.ln_C ? (__uint_as_float(v[j]) - mean) * rstd * __ldg(g.ln_g + n) + __ldg(g.ln_b + n) : 0.f;
-                    }
-                    if (valid) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8)
-                            *reinterpret_cast<uint4*>(o + c * 32 + j) =
-                                make_uint4(pack2(f[j], f[j + 1], g.out16_dtype), pack2(f[j + 2], f[j + 3], g.out16_dtype),
-                                           pack2(f[j + 4], f[j + 5], g.out16_dtype), pack2(f[j + 6], f[j + 7], g.out16_dtype));
-                    }
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<uint4*>(srow + c * 32 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(as));
+            if (lane == 0) mbar_arrive(tempty_bar(as));        // accumulator stage drained
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + lg) : "memory");   // both halves staged
+
+            // ---- phase R: staged rows -> global (lane = column pair) ----
+            auto process_row = [&](const int i, float2 (&rslot)[NP]) {
+                const int m = __shfl_sync(0xffffffffu, my_m, i);
+                const int r32 = __shfl_sync(0xffffffffu, my_r32, i);
+                const int r16 = __shfl_sync(0xffffffffu, my_r16, i);
+                if (m < 0) {
+                    if (kPrefetch) {
+                        const int mx = __shfl_sync(0xffffffffu, nx_m, i);
+                        const int rx = __shfl_sync(0xffffffffu, nx_r32, i);
+                        const float* rn = g.res + (size_t)rx * g.ld32 + n0x + 2 * lane;
+#pragma unroll
+                        for (int k = 0; k < NP; ++k)
+                            rslot[k] = mx >= 0 ? __ldg(reinterpret_cast<const float2*>(rn + 64 * k)) : make_float2(0.f, 0.f);
+                    }
+                    return;
+                }
+                const float* srow = stg + (size_t)(half * 16 + i) * Cfg::SROW;
+                float2 v[NP];
+#pragma unroll
+                for (int k = 0; k < NP; ++k) {
+                    v[k] = *reinterpret_cast<const float2*>(srow + 64 * k + 2 * lane);
+                    if (EPI == E_GENERIC) {
+                        v[k].x = apply_act(v[k].x + bia[k].x, act);
+                        v[k].y = apply_act(v[k].y + bia[k].y, act);
+                    } else {
+                        v[k].x = actf<ACT>(v[k].x + bia[k].x);
+                        v[k].y = actf<ACT>(v[k].y + bia[k].y);
+                    }
+                }
+                if (has_res) {
+                    const float* rr = g.res + (size_t)r32 * g.ld32 + n0 + 2 * lane;
+#pragma unroll
+                    for (int k = 0; k < NP; ++k) {
+                        const float2 t = kPrefetch ? rslot[k] : __ldg(reinterpret_cast<const float2*>(rr + 64 * k));
+                        v[k].x = v[k].x * g.res_scale + t.x;
+                        v[k].y = v[k].y * g.res_scale + t.y;
+                    }
+                    if (kPrefetch) {                           // request row i of the next tile
+                        const int mx = __shfl_sync(0xffffffffu, nx_m, i);
+                        const int rx = __shfl_sync(0xffffffffu, nx_r32, i);
+                        const float* rn = g.res + (size_t)rx * g.ld32 + n0x + 2 * lane;
+#pragma unroll
+                        for (int k = 0; k < NP; ++k)
+                            rslot[k] = mx >= 0 ? __ldg(reinterpret_cast<const float2*>(rn + 64 * k)) : make_float2(0.f, 0.f);
+                    }
+                }
+                if ((EPI == E_GENERIC || kRes) && g.out32) {
+                    float* oo = g.out32 + (size_t)r32 * g.ld32 + n0 + 2 * lane;
+#pragma unroll
+                    for (int k = 0; k < NP; ++k) *reinterpret_cast<float2*>(oo + 64 * k) = v[k];
+                }
+                if (has_ln) {
+                    float sm = 0.f;
+#pragma unroll
+                    for (int k = 0; k < NP; ++k) sm += v[k].x + v[k].y;     // pad columns are exactly 0
+                    const float mean = warp_sum(sm) * inv_c;
+                    float q = 0.f;
+#pragma unroll
+                    for (int k = 0; k < NP; ++k) {
+                        if (64 * k + 2 * lane < g.ln_C) {
+                            const float a0 = v[k].x - mean, a1 = v[k].y - mean;
+                            q += a0 * a0 + a1 * a1;
+                        }
+                    }
+                    const float rstd = rsqrtf(warp_sum(q) * inv_c + 1e-5f);
+                    uint16_t* oo = g.out16 + (size_t)r16 * g.ld16 + 2 * lane;
+#pragma unroll
+                    for (int k = 0; k < NP; ++k) {
+                        const bool in = 64 * k + 2 * lane < g.ln_C;
+                        const float y0 = in ? (v[k].x - mean) * rstd * lng[k].x + lnb[k].x : 0.f;
+                        const float y1 = in ? (v[k].y - mean) * rstd * lng[k].y + lnb[k].y : 0.f;
+                        *reinterpret_cast<uint32_t*>(oo + 64 * k) =
+                            EPI == E_GENERIC ? pack2(y0, y1, g.out16_dtype) : packf<DT>(y0, y1);
+                    }
+                } else if (EPI == E_PIXSHUF || (EPI == E_GENERIC && g.out16 && g.out16_mode == SRK_O16_PIXSHUF2)) {
+                    // PixelShuffle(2): a 64-column group never straddles a sub-pixel (N/4 % 64 == 0)
+#pragma unroll
+                    for (int k = 0; k < NP; ++k)
+                        *reinterpret_cast<uint32_t*>(g.out16 + off16_of(g, m, n0 + 64 * k) + 2 * lane) =
+                            EPI == E_GENERIC ? pack2(v[k].x, v[k].y, g.out16_dtype) : packf<DT>(v[k].x, v[k].y);
+                } else if (EPI == E_O16 || g.out16) {
+                    uint16_t* oo = g.out16 + (size_t)m * g.ld16 + n0 + 2 * lane;
+#pragma unroll
+                    for (int k = 0; k < NP; ++k)
+                        *reinterpret_cast<uint32_t*>(oo + 64 * k) =
+                            EPI == E_GENERIC ? pack2(v[k].x, v[k].y, g.out16_dtype) : packf<DT>(v[k].x, v[k].y);
+                }
+                if (EPI == E_GENERIC && g.img) {
+#pragma unroll
+                    for (int k = 0; k < NP; ++k) {
+                        size_t off;
+                        if (offimg_of(g, m, n0 + 64 * k + 2 * lane, off)) g.img[off] = v[k].x * g.img_scale;
+                        if (offimg_of(g, m, n0 + 64 * k + 2 * lane + 1, off)) g.img[off] = v[k].y * g.img_scale;
+                    }
+                }
+            };
+            if constexpr (kPrefetch) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) process_row(i, resv[i]);
+            } else {
+#pragma unroll 2
+                for (int i = 0; i < 16; ++i) process_row(i, resv[0]);
+            }
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + lg) : "memory");   // staging free for the next tile
+            my_m = nx_m; my_r32 = nx_r32; my_r16 = nx_r16;
         }
     }
     tc_fence_before();
@@ -414,19 +520,44 @@ static int num_sms() {
     return v;
 }
 
-template <int BN>
+template <int BN, int EPI, int ACT, int DT>
 static int launch_tc5(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st) {
     using Cfg = TcCfg<BN>;
     static bool attr_set = false;
     if (!attr_set) {
-        SRK_CUDA(cudaFuncSetAttribute(gemm_tc5_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        SRK_CUDA(cudaFuncSetAttribute(gemm_tc5_kernel<BN, EPI, ACT, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)Cfg::SMEM));
         attr_set = true;
     }
     const int total = p.m_tiles * p.n_tiles;
     const int grid = total < num_sms() ? total : num_sms();
-    gemm_tc5_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM, st>>>(ma, mb, p);
+    gemm_tc5_kernel<BN, EPI, ACT, DT><<<grid, TC_THREADS, Cfg::SMEM, st>>>(ma, mb, p);
     SRK_LAUNCH_CHECK("gemm_tc5_kernel");
     return 0;
+}
+
+// picks the specialised epilogue when the call matches one, else the generic kernel
+template <int BN>
+static int dispatch_tc5(const srk_gemm_args* a, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p,
+                        cudaStream_t st) {
+    const bool res = a->res != nullptr, o32 = a->out32 != nullptr, o16 = a->out16 != nullptr;
+    const bool ln = a->ln_g != nullptr, img = a->img != nullptr;
+    const bool ps = o16 && a->out16_mode == SRK_O16_PIXSHUF2;
+    const int dt = a->out16_dtype, act = a->act;
+    if (!img && !res && !o32 && o16 && !ln && !ps) {
+        if (act == SRK_ACT_NONE && dt == SRK_BF16) return launch_tc5<BN, E_O16, SRK_ACT_NONE, SRK_BF16>(ma, mb, p, st);
+        if (act == SRK_ACT_NONE && dt == SRK_FP16) return launch_tc5<BN, E_O16, SRK_ACT_NONE, SRK_FP16>(ma, mb, p, st);
+        if (act == SRK_ACT_GELU && dt == SRK_BF16) return launch_tc5<BN, E_O16, SRK_ACT_GELU, SRK_BF16>(ma, mb, p, st);
+        if (act == SRK_ACT_LRELU && dt == SRK_FP16) return launch_tc5<BN, E_O16, SRK_ACT_LRELU, SRK_FP16>(ma, mb, p, st);
+        if (act == SRK_ACT_RELU && dt == SRK_FP16) return launch_tc5<BN, E_O16, SRK_ACT_RELU, SRK_FP16>(ma, mb, p, st);
+    }
+    if (!img && res && ln && act == SRK_ACT_NONE && dt == SRK_BF16)
+        return launch_tc5<BN, E_RES_LN, SRK_ACT_NONE, SRK_BF16>(ma, mb, p, st);
+    if (!img && res && !ln && !ps && act == SRK_ACT_NONE && (!o16 || dt == SRK_FP16))
+        return launch_tc5<BN, E_RES, SRK_ACT_NONE, SRK_FP16>(ma, mb, p, st);
+    if (!img && !res && !o32 && ps && act == SRK_ACT_NONE && dt == SRK_FP16)
+        return launch_tc5<BN, E_PIXSHUF, SRK_ACT_NONE, SRK_FP16>(ma, mb, p, st);
+    return launch_tc5<BN, E_GENERIC, 0, 0>(ma, mb, p, st);
 }
 
 int gemm_tcgen05(const srk_gemm_args* a, cudaStream_t st) {
@@ -434,14 +565,14 @@ int gemm_tcgen05(const srk_gemm_args* a, cudaStream_t st) {
     SRK_REQUIRE(((uintptr_t)a->A & 15) == 0 && ((uintptr_t)a->Wt & 15) == 0, "gemm(tcgen05): operands must be 16 B aligned");
     TcParams p{};
     p.g = make_gemm_params(a);
-    const int BN = a->N % 256 == 0 ? 256 : (a->N % 192 == 0 ? 192 : (a->N % 128 == 0 ? 128 : 64));
+    const int BN = a->N % 192 == 0 ? 192 : (a->N % 128 == 0 ? 128 : 64);
     if (a->ln_g) {
         SRK_REQUIRE(a->N == BN, "gemm(tcgen05): fused LayerNorm needs the whole row in one tile (N=%d)", a->N);
         SRK_REQUIRE(a->out16 && a->out16_mode == SRK_O16_ROWS && a->ln_b && a->ln_C > 0 && a->ln_C <= a->N,
                     "gemm(tcgen05): bad fused LayerNorm arguments");
     }
     if (a->out16 && a->out16_mode == SRK_O16_PIXSHUF2)
-        SRK_REQUIRE((a->N / 4) % 32 == 0, "gemm(tcgen05): pixel-shuffle output needs N/4 %% 32 == 0");
+        SRK_REQUIRE((a->N / 4) % 64 == 0, "gemm(tcgen05): pixel-shuffle output needs N/4 %% 64 == 0");
     if (a->res || a->out32) SRK_REQUIRE(a->ld32 % 4 == 0, "gemm(tcgen05): ld32 %% 4");
     p.n_tiles = a->N / BN;
     p.nkb = a->K / TBK;
@@ -475,10 +606,9 @@ int gemm_tcgen05(const srk_gemm_args* a, cudaStream_t st) {
         if (int rc = encode_map(&mb, a->dtype, 2, a->Wt, dims, strides, box)) return rc;
     }
     switch (BN) {
-        case 256: return launch_tc5<256>(ma, mb, p, st);
-        case 192: return launch_tc5<192>(ma, mb, p, st);
-        case 128: return launch_tc5<128>(ma, mb, p, st);
-        default: return launch_tc5<64>(ma, mb, p, st);
+        case 192: return dispatch_tc5<192>(a, ma, mb, p, st);
+        case 128: return dispatch_tc5<128>(a, ma, mb, p, st);
+        default: return dispatch_tc5<64>(a, ma, mb, p, st);
     }
 }
 
