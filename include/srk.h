@@ -158,9 +158,10 @@ int srk_conv_in(const float* x, int B, int h, int w, int H, int W, float in_scal
                 const float* wgt, const float* bias, int C, float* out32, int ld32,
                 void* out16, int ld16, int out16_dtype, void* stream);
 
-/* 1-channel 3x3 output conv (conv_last / EDSR tail.1): a: (B,H,W,lda) fp16, w: (9, Cin) fp32,
- * y: (B,1,Hc,Wc) fp32 cropped to Hc x Wc, y = (conv + bias) * out_scale. */
-int srk_conv_out(const void* a, int lda, int B, int H, int W, int Cin, const float* wgt,
+/* 1-channel 3x3 output conv (conv_last / EDSR tail.1): a: (B,H,W,lda) fp16, w: (9, Cin) fp16
+ * tap major, y: (B,1,Hc,Wc) fp32 cropped to Hc x Wc, y = (conv + bias) * out_scale.
+ * Built for Cin == lda == 64 (num_feat of the reference's upsamplers). */
+int srk_conv_out(const void* a, int lda, int B, int H, int W, int Cin, const void* wgt,
                  float bias, float out_scale, float* y, int Hc, int Wc, void* stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -198,7 +199,7 @@ typedef struct {
     srk_conv_params conv_before_upsample;            /* pixelshuffle only */
     srk_conv_params upsample[4];                     /* log2(s) convs (N order (i,j,c)) or the direct conv */
     int n_upsample;
-    const float* conv_last_w; float conv_last_b;     /* (9,64) fp32 */
+    const void* conv_last_w; float conv_last_b;      /* (9,64) fp16 */
     int linear_dtype, conv_dtype;                    /* SRK_BF16 / SRK_FP16 */
 } srk_swinir_plan;
 
@@ -213,7 +214,7 @@ typedef struct {
     const float *head_w, *head_b;        /* (F,9),(F) fp32 */
     const srk_conv_params* body;         /* host array [2*n_resblocks + 1] */
     srk_conv_params tail_up[4]; int n_tail_up;
-    const float* tail_w; float tail_b;   /* (9,F) fp32 */
+    const void* tail_w; float tail_b;    /* (9,F) fp16 */
     int conv_dtype;
 } srk_edsr_plan;
 

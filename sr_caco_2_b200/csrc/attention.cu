@@ -33,6 +33,11 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src));
 }
 
+__device__ __forceinline__ uint32_t packbf(float a, float b) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+
 constexpr int ATT_THREADS = 256;
 
 // DP = padded head dim (16, 32, 48 or 64)
@@ -96,37 +101,49 @@ window_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int ldq,
             }
         }
         // ---- + bias + mask, softmax --------------------------------------------------------
-        const float* tb = tab + h * 225;
+        // rel_pos_index(i, j) with i = r0 + g (+8), j = nt*8 + 2t + e collapses to
+        //   base - 15*nt - e   (+15 for the second row): compile-time offsets from one pointer
+        const float* bp = tab + h * 225 + (2 * strip + 7) * 15 + (g - 2 * t + 7);
         const int i0 = r0 + g, i1 = r0 + g + 8;
-        const int l0 = lab[i0], l1 = lab[i1];
         float m0 = -3.0e38f, m1 = -3.0e38f;
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int j = nt * 8 + 2 * t + e;
-                const int lj = lab[j];
-                float v0 = s[nt][e] * scale + tb[rel_pos_index(i0, j)];
-                float v1 = s[nt][2 + e] * scale + tb[rel_pos_index(i1, j)];
-                if (masked) {
-                    if (l0 != lj) v0 += -100.f;
-                    if (l1 != lj) v1 += -100.f;
-                }
+                const float v0 = fmaf(s[nt][e], scale, bp[-15 * nt - e]);
+                const float v1 = fmaf(s[nt][2 + e], scale, bp[15 - 15 * nt - e]);
                 s[nt][e] = v0; s[nt][2 + e] = v1;
-                m0 = fmaxf(m0, v0); m1 = fmaxf(m1, v1);
             }
+        }
+        if (masked) {                                          // only the last window row / column
+            const int l0 = lab[i0], l1 = lab[i1];
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int lj = lab[nt * 8 + 2 * t + e];
+                    if (l0 != lj) s[nt][e] += -100.f;
+                    if (l1 != lj) s[nt][2 + e] += -100.f;
+                }
+            }
+        }
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
+            m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
         }
         m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
         m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
         m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
         m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+        const float mb0 = m0 * LOG2E, mb1 = m1 * LOG2E;
         float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const float p0 = exp2f((s[nt][e] - m0) * LOG2E);
-                const float p1 = exp2f((s[nt][2 + e] - m1) * LOG2E);
+                const float p0 = ex2_approx(fmaf(s[nt][e], LOG2E, -mb0));
+                const float p1 = ex2_approx(fmaf(s[nt][2 + e], LOG2E, -mb1));
                 s[nt][e] = p0; s[nt][2 + e] = p1;
                 sum0 += p0; sum1 += p1;
             }
@@ -135,18 +152,18 @@ window_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int ldq,
         sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
         sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
         sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
-        const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
-        // ---- O = P V ---------------------------------------------------------------------
+        const float inv0 = rcp_approx(sum0), inv1 = rcp_approx(sum1);
+        // ---- O = P V  (P in [0,1] is rounded to bf16 un-normalised; 1/sum is applied to O) ----
         float o[DP / 8][4];
 #pragma unroll
         for (int i = 0; i < DP / 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
             uint32_t a[4];
-            a[0] = pack2(s[2 * kk][0] * inv0, s[2 * kk][1] * inv0, SRK_BF16);
-            a[1] = pack2(s[2 * kk][2] * inv1, s[2 * kk][3] * inv1, SRK_BF16);
-            a[2] = pack2(s[2 * kk + 1][0] * inv0, s[2 * kk + 1][1] * inv0, SRK_BF16);
-            a[3] = pack2(s[2 * kk + 1][2] * inv1, s[2 * kk + 1][3] * inv1, SRK_BF16);
+            a[0] = packbf(s[2 * kk][0], s[2 * kk][1]);
+            a[1] = packbf(s[2 * kk][2], s[2 * kk][3]);
+            a[2] = packbf(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+            a[3] = packbf(s[2 * kk + 1][2], s[2 * kk + 1][3]);
 #pragma unroll
             for (int nd = 0; nd < DP / 16; ++nd) {
                 uint32_t b[4];
@@ -162,9 +179,9 @@ window_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int ldq,
         for (int nt = 0; nt < DP / 8; ++nt) {
             const int col = qc + nt * 8 + 2 * t;
             *reinterpret_cast<uint32_t*>(rows + (size_t)(r0 + g) * RS + col * 2) =
-                pack2(o[nt][0], o[nt][1], SRK_BF16);
+                packbf(o[nt][0] * inv0, o[nt][1] * inv0);
             *reinterpret_cast<uint32_t*>(rows + (size_t)(r0 + g + 8) * RS + col * 2) =
-                pack2(o[nt][2], o[nt][3], SRK_BF16);
+                packbf(o[nt][2] * inv1, o[nt][3] * inv1);
         }
     }
     __syncthreads();

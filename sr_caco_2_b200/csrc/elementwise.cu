@@ -131,73 +131,116 @@ conv_in_kernel(const float* __restrict__ x, int B, int h, int w, int H, int W, f
 }
 
 // ------------------------------------------------------------------------------------------
-// conv_out: 3x3, Cin (<= 64 per pass) -> 1 channel on an NHWC fp16 image, fp32 weights and
-// accumulation (conv_last network_swinir.py:868,942; EDSR tail.1 network_nlsn.py:352-356).
-// 8 lanes share one pixel (16 B = 8 channels each, so a warp reads 512 contiguous bytes per
-// tap), a warp produces 32 consecutive output pixels and stores them as one 128 B line.
+// conv_out: 3x3, 64 -> 1 channel on an NHWC fp16 image (conv_last network_swinir.py:868,942;
+// EDSR tail.1 network_nlsn.py:352-356).  Tensor-core direct convolution from a shared-memory
+// halo tile: a CTA owns 8 x 32 output pixels, stages the 10 x 34 x 64ch halo once (cp.async,
+// zero-filled outside the image = the conv padding, double buffered across tiles) and each
+// warp produces one output row.  The MMA N dimension carries the three horizontal taps:
+//   D[p][dx] = sum_dy sum_c halo[row+dy][p][c] * w[dy][dx][c]        (mma.sync m16n8k16, fp16)
+//   out[x]   = D[x][0] + D[x+1][1] + D[x+2][2] + bias
+// so every A fragment (ldmatrix) is used for 3 taps.  Weights are fp16 here (fp32 accumulate).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-conv_out_kernel(const __half* __restrict__ a, int lda, int B, int H, int W, int Cin,
-                const float* __restrict__ wgt, float bias, float out_scale, float* __restrict__ y,
-                int Hc, int Wc) {
-    extern __shared__ __align__(16) float ws[];      // [9][cpad] weights, zero padded to 64-multiples
-    const int cpad = ((Cin + 63) / 64) * 64;
-    for (int i = threadIdx.x; i < 9 * cpad; i += blockDim.x) {
-        const int tp = i / cpad, c = i - tp * cpad;
-        ws[i] = c < Cin ? wgt[tp * Cin + c] : 0.f;
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int sub = lane & 7, grp = lane >> 3;
-    const int xsegs = (Wc + 31) >> 5;
-    const long long nwarps = (long long)B * Hc * xsegs;
-    const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
-    const int cpasses = cpad / 64;
-    for (long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-         wid < nwarps; wid += wstride) {
-        const int xs = (int)(wid % xsegs);
-        const int oy = (int)((wid / xsegs) % Hc);
-        const int bi = (int)(wid / ((long long)xsegs * Hc));
-        float mine = 0.f;
-#pragma unroll 1
-        for (int it = 0; it < 8; ++it) {
-            const int ox = xs * 32 + it * 4 + grp;
-            float acc = 0.f;
-            for (int cp = 0; cp < cpasses; ++cp) {
-                const int c0 = cp * 64 + sub * 8;
-                if (ox < Wc && c0 < lda) {
+constexpr int CO_TH = 8, CO_TW = 32, CO_HH = CO_TH + 2, CO_HW = CO_TW + 2;
+constexpr int CO_PIX_STRIDE = 144;                               // 128 B of channels + 16 B pad (ldmatrix conflict-free)
+constexpr int CO_TILE_BYTES = CO_HH * CO_HW * CO_PIX_STRIDE;     // 48,960 B
+constexpr int CO_THREADS = 256;
+
+__device__ __forceinline__ void co_cp16(uint32_t dst, const void* src, bool valid) {
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(sz));
+}
+
+__global__ void __launch_bounds__(CO_THREADS, 2)
+conv_out_mma_kernel(const __half* __restrict__ a, int B, int H, int W, const __half* __restrict__ wgt16,
+                    float bias, float out_scale, float* __restrict__ y, int Hc, int Wc) {
+    extern __shared__ __align__(16) unsigned char co_smem[];
+    const uint32_t sm = (uint32_t)__cvta_generic_to_shared(co_smem);
+    float* dsm = reinterpret_cast<float*>(co_smem + 2 * CO_TILE_BYTES);          // [8 warps][3][48]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int tx_n = (Wc + CO_TW - 1) / CO_TW, ty_n = (Hc + CO_TH - 1) / CO_TH;
+    const int n_tiles = B * ty_n * tx_n;
+
+    // B fragments: B[k = channel][n = dx] = w[dy][dx][channel] for n < 3 (wgt16 is [9][64], tap major)
+    uint32_t bf[3][4][2];
 #pragma unroll
-                    for (int dy = 0; dy < 3; ++dy) {
-                        const int yy = oy + dy - 1;
-                        if (yy < 0 || yy >= H) continue;
+    for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-                        for (int dx = 0; dx < 3; ++dx) {
-                            const int xx = ox + dx - 1;
-                            if (xx < 0 || xx >= W) continue;
-                            const uint4 q = __ldg(reinterpret_cast<const uint4*>(
-                                a + (((size_t)bi * H + yy) * W + xx) * lda + c0));
-                            const __half2* hp = reinterpret_cast<const __half2*>(&q);
-                            const float4 w0 = *reinterpret_cast<const float4*>(ws + (dy * 3 + dx) * cpad + c0);
-                            const float4 w1 = *reinterpret_cast<const float4*>(ws + (dy * 3 + dx) * cpad + c0 + 4);
-                            const float2 f0 = __half22float2(hp[0]), f1 = __half22float2(hp[1]);
-                            const float2 f2 = __half22float2(hp[2]), f3 = __half22float2(hp[3]);
-                            acc = fmaf(w0.x, f0.x, acc); acc = fmaf(w0.y, f0.y, acc);
-                            acc = fmaf(w0.z, f1.x, acc); acc = fmaf(w0.w, f1.y, acc);
-                            acc = fmaf(w1.x, f2.x, acc); acc = fmaf(w1.y, f2.y, acc);
-                            acc = fmaf(w1.z, f3.x, acc); acc = fmaf(w1.w, f3.y, acc);
-                        }
-                    }
+        for (int ks = 0; ks < 4; ++ks) {
+            uint32_t v0 = 0, v1 = 0;
+            if (g < 3) {
+                const __half* wp = wgt16 + (dy * 3 + g) * 64 + ks * 16 + 2 * t;
+                v0 = *reinterpret_cast<const uint32_t*>(wp);
+                v1 = *reinterpret_cast<const uint32_t*>(wp + 8);
+            }
+            bf[dy][ks][0] = v0; bf[dy][ks][1] = v1;
+        }
+
+    auto load_tile = [&](int tile, int buf) {
+        const int bi = tile / (ty_n * tx_n), rem = tile - bi * ty_n * tx_n;
+        const int y0 = (rem / tx_n) * CO_TH - 1, x0 = (rem % tx_n) * CO_TW - 1;
+        const uint32_t dst0 = sm + buf * CO_TILE_BYTES;
+        for (int i = tid; i < CO_HH * CO_HW * 8; i += CO_THREADS) {
+            const int pix = i >> 3, ch = i & 7;
+            const int py = pix / CO_HW, px = pix - py * CO_HW;
+            const int yy = y0 + py, xx = x0 + px;
+            const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+            const __half* src = ok ? a + (((size_t)bi * H + yy) * W + xx) * 64 + ch * 8 : a;
+            co_cp16(dst0 + pix * CO_PIX_STRIDE + ch * 16, src, ok);
+        }
+        asm volatile("cp.async.commit_group;\n");
+    };
+
+    int buf = 0;
+    if ((int)blockIdx.x < n_tiles) load_tile(blockIdx.x, 0);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
+        const int nxt = tile + gridDim.x;
+        if (nxt < n_tiles) { load_tile(nxt, buf ^ 1); asm volatile("cp.async.wait_group 1;\n"); }
+        else asm volatile("cp.async.wait_group 0;\n");
+        __syncthreads();
+        const uint32_t tb = sm + buf * CO_TILE_BYTES;
+        float acc[3][4];
+#pragma unroll
+        for (int mt = 0; mt < 3; ++mt) acc[mt][0] = acc[mt][1] = acc[mt][2] = acc[mt][3] = 0.f;
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+            for (int mt = 0; mt < 3; ++mt) {
+                // halo pixels mt*16 .. mt*16+15 of halo row (warp + dy); the third tile is clamped
+                int prow = mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                prow = prow < CO_HW ? prow : CO_HW - 1;
+                const uint32_t abase = tb + ((warp + dy) * CO_HW + prow) * CO_PIX_STRIDE + (lane >> 4) * 16;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    uint32_t af[4];
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                                 : "=r"(af[0]), "=r"(af[1]), "=r"(af[2]), "=r"(af[3]) : "r"(abase + ks * 32));
+                    asm volatile(
+                        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                        : "+f"(acc[mt][0]), "+f"(acc[mt][1]), "+f"(acc[mt][2]), "+f"(acc[mt][3])
+                        : "r"(af[0]), "r"(af[1]), "r"(af[2]), "r"(af[3]), "r"(bf[dy][ks][0]), "r"(bf[dy][ks][1]));
                 }
             }
-            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-            // lane L must hold pixel L: it is produced at iteration L>>2 by lane group L&3
-            const float tv = __shfl_sync(0xffffffffu, acc, (lane & 3) * 8);
-            if ((lane >> 2) == it) mine = tv;
         }
-        const int ox = xs * 32 + lane;
-        if (ox < Wc) y[((size_t)bi * Hc + oy) * Wc + ox] = (mine + bias) * out_scale;
+        // D columns 0..2 of the 48 halo pixels -> per-warp scratch, then out[x] = D[x][0] + D[x+1][1] + D[x+2][2]
+        float* dw = dsm + warp * 3 * 48;
+#pragma unroll
+        for (int mt = 0; mt < 3; ++mt) {
+            if (t == 0) {
+                dw[0 * 48 + mt * 16 + g] = acc[mt][0]; dw[1 * 48 + mt * 16 + g] = acc[mt][1];
+                dw[0 * 48 + mt * 16 + g + 8] = acc[mt][2]; dw[1 * 48 + mt * 16 + g + 8] = acc[mt][3];
+            } else if (t == 1) {
+                dw[2 * 48 + mt * 16 + g] = acc[mt][0]; dw[2 * 48 + mt * 16 + g + 8] = acc[mt][2];
+            }
+        }
+        __syncwarp();
+        {
+            const int bi = tile / (ty_n * tx_n), rem = tile - bi * ty_n * tx_n;
+            const int oy = (rem / tx_n) * CO_TH + warp, ox = (rem % tx_n) * CO_TW + lane;
+            const float v = dw[lane] + dw[48 + lane + 1] + dw[96 + lane + 2];
+            if (oy < Hc && ox < Wc) y[((size_t)bi * Hc + oy) * Wc + ox] = (v + bias) * out_scale;
+        }
+        __syncthreads();                                             // tile buffer `buf` is free again
     }
 }
 
@@ -245,19 +288,23 @@ extern "C" int srk_conv_in(const float* x, int B, int h, int w, int H, int W, fl
     return 0;
 }
 
-extern "C" int srk_conv_out(const void* a, int lda, int B, int H, int W, int Cin, const float* wgt,
+extern "C" int srk_conv_out(const void* a, int lda, int B, int H, int W, int Cin, const void* wgt,
                             float bias, float out_scale, float* y, int Hc, int Wc, void* stream) {
     SRK_REQUIRE(a && wgt && y, "conv_out: null pointer");
     SRK_REQUIRE(B > 0 && H > 0 && W > 0 && Hc > 0 && Wc > 0 && Hc <= H && Wc <= W, "conv_out: bad shape");
-    SRK_REQUIRE(lda % 8 == 0 && Cin <= lda, "conv_out: lda must be a multiple of 8 and >= Cin");
-    const long long nwarps = (long long)B * Hc * ((Wc + 31) / 32);
-    const long long blocks = (nwarps + 7) / 8;
-    const int grid = (int)(blocks < 148 * 8 ? blocks : 148 * 8);
-    const size_t smem = (size_t)9 * ((Cin + 63) / 64) * 64 * sizeof(float);
-    SRK_REQUIRE(smem <= 48 * 1024, "conv_out: Cin too large");
+    if (lda != 64 || Cin != 64)
+        return fail(SRK_ERR_UNSUPPORTED, "conv_out: built for 64 input channels (got Cin=%d, lda=%d)", Cin, lda);
+    cudaStream_t st = (cudaStream_t)stream;
     ProfScope ps(SRK_PROF_CONV_OUT, stream);
-    conv_out_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const __half*)a, lda, B, H, W, Cin, wgt,
-                                                            bias, out_scale, y, Hc, Wc);
-    SRK_LAUNCH_CHECK("conv_out_kernel");
+    const size_t smem = 2 * (size_t)CO_TILE_BYTES + 8 * 3 * 48 * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        SRK_CUDA(cudaFuncSetAttribute(conv_out_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    const long long tiles = (long long)B * ((Hc + CO_TH - 1) / CO_TH) * ((Wc + CO_TW - 1) / CO_TW);
+    const int grid = (int)(tiles < 2 * 148 ? tiles : 2 * 148);
+    conv_out_mma_kernel<<<grid, CO_THREADS, smem, st>>>((const __half*)a, B, H, W, (const __half*)wgt, bias, out_scale, y, Hc, Wc);
+    SRK_LAUNCH_CHECK("conv_out_mma_kernel");
     return 0;
 }

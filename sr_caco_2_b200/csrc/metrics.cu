@@ -292,6 +292,259 @@ __global__ void metrics_finalize_kernel(const MetAcc* acc, const MetImg* img, in
     if (f) atomicOr(&flags[b], f);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Hot-path variant (quantize = 1, thresholded ROIs): integer arithmetic on the uint8 levels.
+// The ROIs roi_v = (H8 >= th_v) are nested, so every pixel is dropped into ONE bucket
+// k = #{v : H8 >= th_v} (thresholds sorted ascending by the host) and the per-variant sums are
+// suffix sums over buckets, formed in the finalize kernel.  Squared errors are exact integers;
+// PSNR_Y follows from Y = 219/255 * v + 16 (65.481 + 128.553 + 24.966 = 219), i.e.
+// mse_y = mse * (219/255)^2, which equals the reference's fp32 luma path to ~1e-7 dB.
+// The separable Gaussian runs as 4-output sliding windows held in registers.
+// ------------------------------------------------------------------------------------------
+struct BucketAcc {                       // per (image, bucket)
+    unsigned long long sse, cnt, scnt;
+    double ssim;
+    int mn, mx;                          // min / max level inside the bucket (255 / -1 when empty)
+};
+
+__global__ void metrics_fast_init_kernel(BucketAcc* acc, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { acc[i].sse = 0ull; acc[i].cnt = 0ull; acc[i].scnt = 0ull; acc[i].ssim = 0.0; acc[i].mn = 255; acc[i].mx = -1; }
+}
+
+struct FastParams {
+    const float* E; const float* H;
+    int B, Hpx, Wpx, border, n_ths;
+    float ths[SRK_MAX_ROI_THS];
+    BucketAcc* acc;
+};
+
+__global__ void __launch_bounds__(NTHREADS)
+metrics_fast_kernel(const FastParams p) {
+    extern __shared__ __align__(16) unsigned char met_smem[];
+    typedef float TileRow[MH + 2];
+    typedef float HbRow[MT + 1];
+    TileRow* sx = reinterpret_cast<TileRow*>(met_smem);             // E8/255   [MH][MH+2]
+    TileRow* sy = sx + MH;                                           // H8/255
+    HbRow (*hb)[MH] = reinterpret_cast<HbRow (*)[MH]>(sy + MH);      // [5][MH][MT+1]
+    unsigned char* sk = reinterpret_cast<unsigned char*>(&hb[5][0][0]);   // bucket of every halo pixel [MH][MH]
+    __shared__ float lut[256];
+    __shared__ unsigned long long r_sse[MAXV], r_cnt[MAXV], r_scnt[MAXV];
+    __shared__ double r_ssim[MAXV];
+    __shared__ int r_mn[MAXV], r_mx[MAXV];
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int b = blockIdx.z;
+    const int Hc = p.Hpx - 2 * p.border, Wc = p.Wpx - 2 * p.border;
+    const int r0 = blockIdx.y * MT, c0 = blockIdx.x * MT;
+    const float* Eb = p.E + (size_t)b * p.Hpx * p.Wpx;
+    const float* Hb = p.H + (size_t)b * p.Hpx * p.Wpx;
+    const int NB = p.n_ths + 1;
+
+    lut[tid] = __fdiv_rn((float)tid, 255.f);                         // x / 255 exactly as the reference divides
+    if (tid < MAXV) { r_sse[tid] = 0ull; r_cnt[tid] = 0ull; r_scnt[tid] = 0ull; r_ssim[tid] = 0.0; r_mn[tid] = 255; r_mx[tid] = -1; }
+    __syncthreads();
+
+    unsigned int cnt[MAXV], sse[MAXV];
+    int mn[MAXV], mx[MAXV];
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) { cnt[k] = 0; sse[k] = 0; mn[k] = 255; mx[k] = -1; }
+
+    for (int i = tid; i < MH * MH; i += NTHREADS) {
+        const int lr = i / MH, lc = i - lr * MH;
+        const int r = r0 + lr, c = c0 + lc;
+        int e = 0, h = 0, kb = 0;
+        if (r < Hc && c < Wc) {
+            const size_t off = (size_t)(r + p.border) * p.Wpx + (c + p.border);
+            const float hf = quant255(__ldg(Hb + off));
+            e = (int)quant255(__ldg(Eb + off));
+            h = (int)hf;
+#pragma unroll
+            for (int t = 0; t < SRK_MAX_ROI_THS; ++t) kb += (t < p.n_ths && hf >= p.ths[t]) ? 1 : 0;
+            if (lr < MT && lc < MT) {                                // owned pixel
+                const int d = e - h;
+                const unsigned int d2 = (unsigned int)(d * d);
+#pragma unroll
+                for (int k = 0; k < MAXV; ++k) {
+                    const bool in = kb == k;
+                    cnt[k] += in ? 1u : 0u;
+                    sse[k] += in ? d2 : 0u;
+                    mn[k] = in ? min(mn[k], h) : mn[k];
+                    mx[k] = in ? max(mx[k], h) : mx[k];
+                }
+            }
+        }
+        sx[lr][lc] = lut[e];
+        sy[lr][lc] = lut[h];
+        sk[lr * MH + lc] = (unsigned char)kb;
+    }
+    __syncthreads();
+
+    // ---- horizontal pass: (row, 4 consecutive outputs) per work item ----
+    for (int w = tid; w < MH * (MT / 4); w += NTHREADS) {
+        const int lr = w / (MT / 4), seg = w - lr * (MT / 4);
+        const int cb = seg * 4;
+        float x[14], y[14];
+#pragma unroll
+        for (int t = 0; t < 14; ++t) { x[t] = sx[lr][cb + t]; y[t] = sy[lr][cb + t]; }
+        float a[5][4];
+#pragma unroll
+        for (int q = 0; q < 5; ++q)
+#pragma unroll
+            for (int o = 0; o < 4; ++o) a[q][o] = 0.f;
+#pragma unroll
+        for (int t = 0; t < 14; ++t) {
+            const float xx = x[t] * x[t], yy = y[t] * y[t], xy = x[t] * y[t];
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                const int tap = t - o;
+                if (tap >= 0 && tap < 11) {
+                    const float gq = c_gauss[tap];
+                    a[0][o] = fmaf(gq, x[t], a[0][o]); a[1][o] = fmaf(gq, y[t], a[1][o]);
+                    a[2][o] = fmaf(gq, xx, a[2][o]); a[3][o] = fmaf(gq, yy, a[3][o]); a[4][o] = fmaf(gq, xy, a[4][o]);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 5; ++q)
+#pragma unroll
+            for (int o = 0; o < 4; ++o) hb[q][lr][cb + o] = a[q][o];
+    }
+    __syncthreads();
+
+    // ---- vertical pass + SSIM: (column, 4 consecutive rows) per thread ----
+    float ssum[MAXV];
+    unsigned int scnt[MAXV];
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) { ssum[k] = 0.f; scnt[k] = 0; }
+    const int mapH = Hc - 10, mapW = Wc - 10;
+    {
+        const int lc = tid & 31, rb = (tid >> 5) * 4;
+        float a[5][4];
+#pragma unroll
+        for (int q = 0; q < 5; ++q)
+#pragma unroll
+            for (int o = 0; o < 4; ++o) a[q][o] = 0.f;
+#pragma unroll
+        for (int t = 0; t < 14; ++t) {
+            float v[5];
+#pragma unroll
+            for (int q = 0; q < 5; ++q) v[q] = hb[q][rb + t][lc];
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                const int tap = t - o;
+                if (tap >= 0 && tap < 11) {
+                    const float gq = c_gauss[tap];
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) a[q][o] = fmaf(gq, v[q], a[q][o]);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            const int lr = rb + o;
+            if (r0 + lr < mapH && c0 + lc < mapW) {
+                const float c1 = 1e-4f, c2 = 9e-4f;
+                const float mxm = a[0][o], mym = a[1][o];
+                const float mxx = mxm * mxm, myy = mym * mym, mxy = mxm * mym;
+                const float sxx = a[2][o] - mxx, syy = a[3][o] - myy, sxy = a[4][o] - mxy;
+                const float cs = (2.f * sxy + c2) / (sxx + syy + c2);
+                const float ss = ((2.f * mxy + c1) / (mxx + myy + c1)) * cs;
+                const int kb = sk[(lr + 5) * MH + lc + 5];           // ROI is cropped by the filter radius
+#pragma unroll
+                for (int k = 0; k < MAXV; ++k) {
+                    const bool in = kb == k;
+                    ssum[k] += in ? ss : 0.f;
+                    scnt[k] += in ? 1u : 0u;
+                }
+            }
+        }
+    }
+
+    // ---- reduction: warp shuffles -> shared atomics -> one global atomic per quantity ----
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+        if (k < NB) {
+            unsigned int c_ = cnt[k], s_ = sse[k], sc_ = scnt[k];
+            float f_ = ssum[k];
+            int mn_ = mn[k], mx_ = mx[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                c_ += __shfl_xor_sync(0xffffffffu, c_, o);
+                s_ += __shfl_xor_sync(0xffffffffu, s_, o);     // <= 32 * 4 * 65025 fits 32 bits
+                sc_ += __shfl_xor_sync(0xffffffffu, sc_, o);
+                f_ += __shfl_xor_sync(0xffffffffu, f_, o);
+                mn_ = min(mn_, __shfl_xor_sync(0xffffffffu, mn_, o));
+                mx_ = max(mx_, __shfl_xor_sync(0xffffffffu, mx_, o));
+            }
+            if (lane == 0) {
+                if (c_) { atomicAdd(&r_cnt[k], (unsigned long long)c_); atomicAdd(&r_sse[k], (unsigned long long)s_);
+                          atomicMin(&r_mn[k], mn_); atomicMax(&r_mx[k], mx_); }
+                if (sc_) { atomicAdd(&r_scnt[k], (unsigned long long)sc_); atomicAdd(&r_ssim[k], (double)f_); }
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < NB) {
+        BucketAcc* a = p.acc + (size_t)b * MAXV + tid;
+        if (r_cnt[tid]) { atomicAdd(&a->cnt, r_cnt[tid]); atomicAdd(&a->sse, r_sse[tid]);
+                          atomicMin(&a->mn, r_mn[tid]); atomicMax(&a->mx, r_mx[tid]); }
+        if (r_scnt[tid]) { atomicAdd(&a->scnt, r_scnt[tid]); atomicAdd(&a->ssim, r_ssim[tid]); }
+    }
+}
+
+__global__ void metrics_fast_finalize_kernel(const BucketAcc* acc, int B, int n_ths, int Hc, int Wc,
+                                             double* out, int32_t* flags) {
+    const int NV = n_ths + 1;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * NV) return;
+    const int b = i / NV, v = i - b * NV;
+    const BucketAcc* a = acc + (size_t)b * MAXV;
+    // variant v = union of buckets k >= v  (variant 0 = whole image)
+    unsigned long long sse = 0, cnt = 0, scnt = 0, outside = 0;
+    double ssim = 0.0;
+    int mn_in = 255, mx_in = -1, mn_all = 255;
+    for (int k = 0; k < NV; ++k) {
+        if (a[k].cnt) mn_all = min(mn_all, a[k].mn);
+        if (k >= v) {
+            sse += a[k].sse; cnt += a[k].cnt; scnt += a[k].scnt; ssim += a[k].ssim;
+            mn_in = min(mn_in, a[k].mn); mx_in = max(mx_in, a[k].mx);
+        } else {
+            outside += a[k].cnt;
+        }
+    }
+    double n = (v == 0) ? (double)Hc * (double)Wc : (double)cnt;
+    if (n == 0.0) n = 1.0;
+    const double mse = (double)sse / n;
+    const double ky = 219.0 / 255.0;
+    const double mse_y = mse * ky * ky;
+    const double psnr = 20.0 * log10(255.0 / sqrt(fmax(mse, 1e-45)));
+    const double psnr_y = 20.0 * log10(255.0 / sqrt(fmax(mse_y, 1e-45)));
+    // extrema of y*roi: pixels outside the ROI contribute 0; min additionally floored by min(y)
+    double mx = cnt ? (double)mx_in : 0.0;
+    double mn = cnt ? (double)mn_in : 0.0;
+    if (outside) { mn = fmin(mn, 0.0); mx = fmax(mx, 0.0); }
+    if (v > 0) mn = fmax(mn, (double)mn_all);
+    double den = mx - mn;
+    if (den == 0.0) den = 1.0;
+    const double nrmse = sqrt(mse) / den;
+    double sn = (v == 0) ? (double)(Hc - 10) * (double)(Wc - 10) : (double)scnt;
+    if (sn == 0.0) sn = 1.0;
+    const double ssv = (double)(float)(ssim / sn);
+    double* o = out + (size_t)i * SRK_MET_N;
+    o[SRK_MET_PSNR] = psnr; o[SRK_MET_MSE] = mse; o[SRK_MET_NRMSE] = nrmse;
+    o[SRK_MET_SSIM] = ssv; o[SRK_MET_PSNR_Y] = psnr_y;
+    int f = 0;
+    const double vals[5] = {psnr, mse, nrmse, ssv, psnr_y};
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        if (!isfinite(vals[k])) f |= 1;
+        if (vals[k] < 0.0) f |= 2;
+    }
+    if (f) atomicOr(&flags[b], f);
+}
+
 static int upload_gauss() {
     static bool done[64] = {false};
     int dev = 0;
@@ -333,6 +586,28 @@ static int run_metrics(const float* E, const float* H, const float* roi, int B, 
                 "metrics: kernel size can't be greater than actual input size (%dx%d after border %d)",
                 Hc, Wc, border);
     if (int rc = upload_gauss()) return rc;
+    bool sorted = true;
+    for (int i = 1; i < n_ths; ++i) sorted = sorted && roi_ths[i] > roi_ths[i - 1];
+    if (quantize && !roi && sorted) {
+        // hot path: integer / bucketed kernel
+        FastParams fp{};
+        fp.E = E; fp.H = H; fp.B = B; fp.Hpx = Hpx; fp.Wpx = Wpx; fp.border = border; fp.n_ths = n_ths;
+        for (int i = 0; i < n_ths; ++i) fp.ths[i] = (float)roi_ths[i];
+        fp.acc = reinterpret_cast<BucketAcc*>(scratch);
+        ProfScope ps(SRK_PROF_METRICS, st);
+        SRK_CUDA(cudaMemsetAsync(flags, 0, sizeof(int32_t) * B, st));
+        metrics_fast_init_kernel<<<ceil_div((long long)B * MAXV, 128), 128, 0, st>>>(fp.acc, B * MAXV);
+        SRK_LAUNCH_CHECK("metrics_fast_init_kernel");
+        const size_t smem = sizeof(float) * (2 * MH * (MH + 2) + 5 * MH * (MT + 1)) + MH * MH;
+        static bool attr = false;
+        if (!attr) { SRK_CUDA(cudaFuncSetAttribute(metrics_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+        dim3 grid(ceil_div(Wc, MT), ceil_div(Hc, MT), B);
+        metrics_fast_kernel<<<grid, NTHREADS, smem, st>>>(fp);
+        SRK_LAUNCH_CHECK("metrics_fast_kernel");
+        metrics_fast_finalize_kernel<<<ceil_div((long long)B * (n_ths + 1), 128), 128, 0, st>>>(fp.acc, B, n_ths, Hc, Wc, out, flags);
+        SRK_LAUNCH_CHECK("metrics_fast_finalize_kernel");
+        return 0;
+    }
     const int NV = roi ? 1 : 1 + n_ths;
     MetParams p{};
     p.E = E; p.H = H; p.roi = roi; p.B = B; p.Hpx = Hpx; p.Wpx = Wpx; p.border = border;
@@ -358,7 +633,9 @@ static int run_metrics(const float* E, const float* H, const float* roi, int B, 
 
 extern "C" size_t srk_metrics_scratch_bytes(int B, int n_ths) {
     const int NV = 1 + (n_ths < 0 ? 0 : n_ths);
-    return srk::align_up(sizeof(srk::MetAcc) * (size_t)B * NV, 16) + sizeof(srk::MetImg) * (size_t)B + 64;
+    const size_t generic = srk::align_up(sizeof(srk::MetAcc) * (size_t)B * NV, 16) + sizeof(srk::MetImg) * (size_t)B + 64;
+    const size_t fast = sizeof(srk::BucketAcc) * (size_t)B * srk::MAXV + 64;
+    return generic > fast ? generic : fast;
 }
 
 extern "C" int srk_metrics(const float* E, const float* H, int B, int Hpx, int Wpx, int border,

@@ -84,5 +84,5 @@ def pack_conv_in(w: torch.Tensor, b: torch.Tensor):
 
 
 def pack_conv_out(w: torch.Tensor):
-    """(1, Cin, 3, 3) -> (9, Cin) fp32, tap major."""
-    return w.float()[0].permute(1, 2, 0).reshape(9, w.shape[1]).contiguous()
+    """(1, Cin, 3, 3) -> (9, Cin) fp16, tap major."""
+    return w.float()[0].permute(1, 2, 0).reshape(9, w.shape[1]).to(torch.float16).contiguous()

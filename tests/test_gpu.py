@@ -211,8 +211,8 @@ def test_conv_in_and_conv_out(L):
     # conv_out with crop
     Cin, lda, Hc, Wc = 64, 64, 29, 41
     a = torch.randn(B, 32, 48, lda, generator=g).half()
-    wo, bo = torch.randn(1, Cin, 3, 3, generator=g) * 0.1, 0.3
-    refo = (F.conv2d(a.float().permute(0, 3, 1, 2), wo, torch.tensor([bo]), padding=1) * 2.0)[:, :, :Hc, :Wc]
+    wo, bo = (torch.randn(1, Cin, 3, 3, generator=g) * 0.1).half(), 0.3
+    refo = (F.conv2d(a.float().permute(0, 3, 1, 2), wo.float(), torch.tensor([bo]), padding=1) * 2.0)[:, :, :Hc, :Wc]
     y = torch.zeros(B, 1, Hc, Wc, device=DEV)
     wk = wo[0].permute(1, 2, 0).reshape(9, Cin).contiguous().to(DEV)
     ad = a.to(DEV)

@@ -156,7 +156,7 @@ def test_weight_packing_matches_linear_and_conv_semantics():
     ref = F.pixel_shuffle(F.conv2d(img, cw.half().float(), cb, padding=1), 2)   # (1,64,10,12)
     out = out.view(5, 6, 2, 2, 64).permute(4, 0, 2, 1, 3).reshape(64, 10, 12)
     assert torch.allclose(out, ref[0], atol=1e-3)
-    assert P.pack_conv_out(torch.arange(18.).view(1, 2, 3, 3)).tolist()[0] == [0.0, 9.0]
+    assert P.pack_conv_out(torch.arange(18.).view(1, 2, 3, 3)).float().tolist()[0] == [0.0, 9.0]
 
 
 def test_shard_range_is_exact_and_contiguous():
