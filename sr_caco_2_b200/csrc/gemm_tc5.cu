@@ -143,20 +143,27 @@ struct TcParams {
     GemmP g;
     int n_tiles, m_tiles, nkb;
     int conv_bw, conv_bh, conv_tx, conv_ty;     // conv-mode M tiling (box BW x BH = 128 pixels)
+    // shared-memory plan (host computed): B-stationary keeps the CTA's whole weight tile
+    // (nkb x BN x 64) resident and streams only A through `stages` 16 KB slots
+    int bstat, stages, stage_bytes, bres_bytes;
 };
 
-template <int BN>
+template <int BN, int EPI>
 struct TcCfg {
+    static constexpr bool kStage16 = EPI == E_O16 || EPI == E_PIXSHUF;   // 16-bit staging (math in phase T)
+    static constexpr int EPI_WARPS = kStage16 ? 16 : 8;       // warps per TMEM lane group: 4 or 2
+    static constexpr int THREADS = 64 + 32 * EPI_WARPS;
     static constexpr int A_BYTES = TBM * TBK * 2;
     static constexpr int B_BYTES = BN * TBK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int SROW = BN + 4;                       // staging row stride (floats): conflict-free float4 / float2
-    static constexpr int STAGING_BYTES = TBM * SROW * 4;
-    static constexpr int AVAIL = TC_SMEM_TOTAL - STAGING_BYTES - 1024 - 256;
-    static constexpr int STAGES = (AVAIL / STAGE_BYTES) > 6 ? 6 : (AVAIL / STAGE_BYTES);
+    static constexpr int SROW = BN + 4;                       // fp32 staging row stride (floats)
+    static constexpr int SROW16 = BN * 2 + 16;                // 16-bit staging row stride (bytes)
+    static constexpr int STAGING_BYTES = kStage16 ? TBM * SROW16 : TBM * SROW * 4;
+    static constexpr int AUX_BYTES = 256 + 8 * (BN + 32) * 4;   // barriers + per-lane-group bias row / row map
+    static constexpr int AVAIL = TC_SMEM_TOTAL - STAGING_BYTES - 1024 - AUX_BYTES;   // operand bytes available
+    static constexpr int MAX_STAGES = 8;
     static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
-    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-    static_assert(STAGES >= 3, "not enough shared memory for the operand pipeline");
+    static_assert(AVAIL / STAGE_BYTES >= 3, "not enough shared memory for the operand pipeline");
     static_assert(BN % 64 == 0 && BN <= 192, "BN must be 64, 128 or 192");
 };
 
@@ -177,20 +184,26 @@ __device__ __forceinline__ int tile_row_to_m(const TcParams& p, int mt, int r) {
 }
 
 template <int BN, int EPI, int ACT, int DT>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__((TcCfg<BN, EPI>::THREADS), 1)
 gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 const TcParams p) {
-    using Cfg = TcCfg<BN>;
+    using Cfg = TcCfg<BN, EPI>;
     extern __shared__ unsigned char tc_smem_raw[];
     const uint32_t raw = smem_u32(tc_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                     // SW128 tiles need 1024 B alignment
-    const uint32_t stg_base = base + Cfg::STAGES * Cfg::STAGE_BYTES;  // fp32 staging tile [128][SROW]
-    const uint32_t bars = stg_base + Cfg::STAGING_BYTES;              // full[S] empty[S] tfull[2] tempty[2] tmem_ptr
+    // [resident B (B-stationary only)] [operand stages] [epilogue staging] [barriers]
+    const uint32_t stages_base = base + p.bres_bytes;
+    const uint32_t stg_base = stages_base + p.stages * p.stage_bytes;
+    const uint32_t bars = stg_base + Cfg::STAGING_BYTES;    // full[8] empty[8] tfull[2] tempty[2] bfull tmem_ptr
     auto full_bar = [&](int s) { return bars + 8u * s; };
-    auto empty_bar = [&](int s) { return bars + 8u * (Cfg::STAGES + s); };
-    auto tfull_bar = [&](int s) { return bars + 8u * (2 * Cfg::STAGES + s); };
-    auto tempty_bar = [&](int s) { return bars + 8u * (2 * Cfg::STAGES + 2 + s); };
-    const uint32_t tmem_slot = bars + 8u * (2 * Cfg::STAGES + 4);
+    auto empty_bar = [&](int s) { return bars + 8u * (Cfg::MAX_STAGES + s); };
+    auto tfull_bar = [&](int s) { return bars + 8u * (2 * Cfg::MAX_STAGES + s); };
+    auto tempty_bar = [&](int s) { return bars + 8u * (2 * Cfg::MAX_STAGES + 2 + s); };
+    const uint32_t bfull_bar = bars + 8u * (2 * Cfg::MAX_STAGES + 4);
+    const uint32_t tmem_slot = bars + 8u * (2 * Cfg::MAX_STAGES + 5);
+    const int NS = p.stages;
+    // B-stationary: CTA c owns n-tile c % n_tiles and M tiles c / n_tiles, + gridDim / n_tiles, ...
+    // (the host makes gridDim a multiple of n_tiles), so "tile += gridDim.x" keeps nt fixed.
     volatile uint32_t* tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t*>(tc_smem_raw + (tmem_slot - raw));
 
@@ -199,8 +212,9 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int total_tiles = p.m_tiles * p.n_tiles;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
+        for (int s = 0; s < Cfg::MAX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(bfull_bar, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), Cfg::EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
@@ -219,6 +233,12 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         // ================================ TMA producer ================================
         if (lane == 0) {
             int stage = 0, phase = 0;
+            if (p.bstat && (int)blockIdx.x < total_tiles) {          // resident weight tile, loaded once
+                const int ntb = blockIdx.x % p.n_tiles;
+                mbar_expect_tx(bfull_bar, (uint32_t)p.bres_bytes);
+                for (int kb = 0; kb < p.nkb; ++kb)
+                    tma_load_2d(base + kb * Cfg::B_BYTES, &map_b, bfull_bar, kb * TBK, ntb * BN);
+            }
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
                 int cb_, cx = 0, cy = 0;
@@ -233,8 +253,8 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 }
                 for (int kb = 0; kb < p.nkb; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
-                    const uint32_t sa = base + stage * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
-                    mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+                    const uint32_t sa = stages_base + stage * p.stage_bytes, sb = sa + Cfg::A_BYTES;
+                    mbar_expect_tx(full_bar(stage), (uint32_t)p.stage_bytes);
                     if (g.a_mode == SRK_A_CONV3X3) {
                         const int tap = kb / g.cpb, cblk = kb - tap * g.cpb;
                         const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
@@ -242,8 +262,8 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     } else {
                         tma_load_2d(sa, &map_a, full_bar(stage), kb * TBK, mt * TBM);
                     }
-                    tma_load_2d(sb, &map_b, full_bar(stage), kb * TBK, nt * BN);
-                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                    if (!p.bstat) tma_load_2d(sb, &map_b, full_bar(stage), kb * TBK, nt * BN);
+                    if (++stage == NS) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -252,6 +272,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         if (lane == 0) {
             const uint32_t idesc = umma_idesc(g.dtype == SRK_BF16 ? 1 : 0, TBM, BN);
             int stage = 0, phase = 0, it = 0;
+            if (p.bstat && (int)blockIdx.x < total_tiles) { mbar_wait(bfull_bar, 0); tc_fence_after(); }
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
                 const int as = it & 1, aphase = (it >> 1) & 1;
                 mbar_wait(tempty_bar(as), aphase ^ 1);
@@ -260,20 +281,96 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 for (int kb = 0; kb < p.nkb; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
-                    const uint32_t sa = base + stage * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
+                    const uint32_t sa = stages_base + stage * p.stage_bytes;
+                    const uint32_t sb = p.bstat ? base + kb * Cfg::B_BYTES : sa + Cfg::A_BYTES;
                     const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sb);
 #pragma unroll
                     for (int k = 0; k < TBK / 16; ++k)        // +32 B per UMMA_K inside the swizzle atom
                         tc_mma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
                                    (kb | k) != 0 ? 1u : 0u);
                     tc_commit(empty_bar(stage));               // frees the smem slot when the MMAs retire
-                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == NS) { stage = 0; phase ^= 1; }
                 }
                 tc_commit(tfull_bar(as));                      // accumulator complete
             }
         }
     } else {
         // ================================ epilogue ================================
+        if constexpr (Cfg::kStage16) {
+            // ---- 16-bit outputs: bias + activation + pack in phase T (thread = row), then a pure
+            //      coalesced 16 B/lane copy of the staged rows in phase R ----
+            // four warps per TMEM lane group: quarter q drains 16-column sub-chunks q, q+4, ... in
+            // phase T and copies rows 8q .. 8q+7 of the lane group in phase R
+            const int ew = warp - 2, lg = warp & 3, q = ew >> 2;
+            unsigned char* stg16 = tc_smem_raw + (stg_base - raw) + (size_t)(lg * 32) * Cfg::SROW16;
+            // per-lane-group bias row + row map of the current tile (written by the q == 0 warp)
+            float* sbias0 = reinterpret_cast<float*>(tc_smem_raw + (bars + 256 - raw)) + lg * 2 * (BN + 32);
+            constexpr int SC = BN / 16;                            // 16-column sub-chunks
+            constexpr int CPR = BN / 8;                            // 16 B chunks per row
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+                const int as = it & 1, aphase = (it >> 1) & 1;
+                const int n0 = nt * BN;
+                float* sbias = sbias0 + (it & 1) * (BN + 32);      // double buffered: late readers of tile it-1
+                int* srowm = reinterpret_cast<int*>(sbias + BN);
+                if (q == 0) {
+#pragma unroll
+                    for (int j = 0; j < BN / 32; ++j) sbias[lane + 32 * j] = __ldg(g.bias + n0 + lane + 32 * j);
+                    srowm[lane] = tile_row_to_m(p, mt, lg * 32 + lane);
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + lg) : "memory");
+                mbar_wait(tfull_bar(as), aphase);
+                tc_fence_after();
+                {
+                    const uint32_t t_row = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN);
+                    unsigned char* srow = stg16 + (size_t)lane * Cfg::SROW16;
+#pragma unroll
+                    for (int jj = 0; jj < SC / 4; ++jj) {
+                        const int c = q + 4 * jj;
+                        uint32_t v[16];
+                        asm volatile(
+                            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                            : "r"(t_row + c * 16));
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        const float4* bp = reinterpret_cast<const float4*>(sbias + c * 16);
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 bb = bp[j];
+                            pk[2 * j] = packf<DT>(actf<ACT>(__uint_as_float(v[4 * j]) + bb.x),
+                                                  actf<ACT>(__uint_as_float(v[4 * j + 1]) + bb.y));
+                            pk[2 * j + 1] = packf<DT>(actf<ACT>(__uint_as_float(v[4 * j + 2]) + bb.z),
+                                                      actf<ACT>(__uint_as_float(v[4 * j + 3]) + bb.w));
+                        }
+                        *reinterpret_cast<uint4*>(srow + c * 32) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        *reinterpret_cast<uint4*>(srow + c * 32 + 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(as));
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + lg) : "memory");
+                // phase R: this warp's 8 rows, CPR 16 B chunks each
+                const unsigned char* sbase = stg16 + (size_t)(q * 8) * Cfg::SROW16;
+#pragma unroll
+                for (int jj = 0; jj < (8 * CPR) / 32; ++jj) {
+                    const int idx = lane + 32 * jj;
+                    const int row = idx / CPR, col = idx - row * CPR;
+                    const int m = srowm[q * 8 + row];
+                    const uint4 val = *reinterpret_cast<const uint4*>(sbase + (size_t)row * Cfg::SROW16 + col * 16);
+                    if (m >= 0) {
+                        uint16_t* dst = EPI == E_PIXSHUF ? g.out16 + off16_of(g, m, n0 + col * 8)
+                                                         : g.out16 + (size_t)m * g.ld16 + n0 + col * 8;
+                        *reinterpret_cast<uint4*>(dst) = val;
+                    }
+                }
+                // (the bar.sync at the top of the next iteration also protects the staging rows)
+            }
+        } else {
         const int ew = warp - 2;                               // 0..7
         const int lg = warp & 3;                               // TMEM lane group this warp may access
         const int half = ew >> 2;                              // column half in phase T, row half in phase R
@@ -368,17 +465,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 const int m = __shfl_sync(0xffffffffu, my_m, i);
                 const int r32 = __shfl_sync(0xffffffffu, my_r32, i);
                 const int r16 = __shfl_sync(0xffffffffu, my_r16, i);
-                if (m < 0) {
-                    if (kPrefetch) {
-                        const int mx = __shfl_sync(0xffffffffu, nx_m, i);
-                        const int rx = __shfl_sync(0xffffffffu, nx_r32, i);
-                        const float* rn = g.res + (size_t)rx * g.ld32 + n0x + 2 * lane;
-#pragma unroll
-                        for (int k = 0; k < NP; ++k)
-                            rslot[k] = mx >= 0 ? __ldg(reinterpret_cast<const float2*>(rn + 64 * k)) : make_float2(0.f, 0.f);
-                    }
-                    return;
-                }
+                const bool valid = m >= 0;                     // predicate the stores, keep one basic block
                 const float* srow = stg + (size_t)(half * 16 + i) * Cfg::SROW;
                 float2 v[NP];
 #pragma unroll
@@ -409,7 +496,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                             rslot[k] = mx >= 0 ? __ldg(reinterpret_cast<const float2*>(rn + 64 * k)) : make_float2(0.f, 0.f);
                     }
                 }
-                if ((EPI == E_GENERIC || kRes) && g.out32) {
+                if ((EPI == E_GENERIC || kRes) && g.out32 && valid) {
                     float* oo = g.out32 + (size_t)r32 * g.ld32 + n0 + 2 * lane;
 #pragma unroll
                     for (int k = 0; k < NP; ++k) *reinterpret_cast<float2*>(oo + 64 * k) = v[k];
@@ -434,9 +521,11 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         const bool in = 64 * k + 2 * lane < g.ln_C;
                         const float y0 = in ? (v[k].x - mean) * rstd * lng[k].x + lnb[k].x : 0.f;
                         const float y1 = in ? (v[k].y - mean) * rstd * lng[k].y + lnb[k].y : 0.f;
-                        *reinterpret_cast<uint32_t*>(oo + 64 * k) =
-                            EPI == E_GENERIC ? pack2(y0, y1, g.out16_dtype) : packf<DT>(y0, y1);
+                        if (valid)
+                            *reinterpret_cast<uint32_t*>(oo + 64 * k) =
+                                EPI == E_GENERIC ? pack2(y0, y1, g.out16_dtype) : packf<DT>(y0, y1);
                     }
+                } else if (!valid) {
                 } else if (EPI == E_PIXSHUF || (EPI == E_GENERIC && g.out16 && g.out16_mode == SRK_O16_PIXSHUF2)) {
                     // PixelShuffle(2): a 64-column group never straddles a sub-pixel (N/4 % 64 == 0)
 #pragma unroll
@@ -450,7 +539,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         *reinterpret_cast<uint32_t*>(oo + 64 * k) =
                             EPI == E_GENERIC ? pack2(v[k].x, v[k].y, g.out16_dtype) : packf<DT>(v[k].x, v[k].y);
                 }
-                if (EPI == E_GENERIC && g.img) {
+                if (EPI == E_GENERIC && g.img && valid) {
 #pragma unroll
                     for (int k = 0; k < NP; ++k) {
                         size_t off;
@@ -469,6 +558,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             asm volatile("bar.sync %0, 64;" ::"r"(1 + lg) : "memory");   // staging free for the next tile
             my_m = nx_m; my_r32 = nx_r32; my_r16 = nx_r16;
         }
+        }  // !kStage16
     }
     tc_fence_before();
     __syncthreads();
@@ -521,17 +611,33 @@ static int num_sms() {
 }
 
 template <int BN, int EPI, int ACT, int DT>
-static int launch_tc5(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st) {
-    using Cfg = TcCfg<BN>;
+static int launch_tc5(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p_in, cudaStream_t st) {
+    using Cfg = TcCfg<BN, EPI>;
     static bool attr_set = false;
     if (!attr_set) {
         SRK_CUDA(cudaFuncSetAttribute(gemm_tc5_kernel<BN, EPI, ACT, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)Cfg::SMEM));
+                                      TC_SMEM_TOTAL));
         attr_set = true;
     }
+    TcParams p = p_in;
     const int total = p.m_tiles * p.n_tiles;
-    const int grid = total < num_sms() ? total : num_sms();
-    gemm_tc5_kernel<BN, EPI, ACT, DT><<<grid, TC_THREADS, Cfg::SMEM, st>>>(ma, mb, p);
+    int grid = total < num_sms() ? total : num_sms();
+    // shared-memory plan: keep the weight tile resident when it fits and every CTA sees >= 2 M tiles
+    const int bres = p.nkb * Cfg::B_BYTES;
+    p.bstat = (bres + 3 * Cfg::A_BYTES <= Cfg::AVAIL) && (p.m_tiles * p.n_tiles >= 2 * num_sms()) &&
+              (num_sms() >= p.n_tiles);
+    if (p.bstat) {
+        grid = (num_sms() / p.n_tiles) * p.n_tiles;             // multiple of n_tiles: nt is fixed per CTA
+        p.bres_bytes = bres;
+        p.stage_bytes = Cfg::A_BYTES;
+    } else {
+        p.bres_bytes = 0;
+        p.stage_bytes = Cfg::STAGE_BYTES;
+    }
+    p.stages = (Cfg::AVAIL - p.bres_bytes) / p.stage_bytes;
+    if (p.stages > Cfg::MAX_STAGES) p.stages = Cfg::MAX_STAGES;
+    const size_t smem = (size_t)p.bres_bytes + (size_t)p.stages * p.stage_bytes + Cfg::STAGING_BYTES + 1024 + Cfg::AUX_BYTES;
+    gemm_tc5_kernel<BN, EPI, ACT, DT><<<grid, Cfg::THREADS, smem, st>>>(ma, mb, p);
     SRK_LAUNCH_CHECK("gemm_tc5_kernel");
     return 0;
 }
