@@ -10,6 +10,7 @@
 // (calculate_mask :260-285: -100 where the 3x3 region labels of the shifted frame differ),
 // softmax(-1), @ v, head merge (:176).  The attention matrix is never materialised in HBM.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace srk {
 
@@ -38,20 +39,23 @@ __device__ __forceinline__ uint32_t packbf(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&t);
 }
 
-constexpr int ATT_THREADS = 256;
+constexpr int ATT_THREADS = 128;          // 4 warps = the four 16-query strips of a window
 
-// DP = padded head dim (16, 32, 48 or 64)
+// DP = padded head dim (16, 32, 48 or 64).  grid = (windows, head groups): a CTA stages only the
+// q|k|v columns of its HG heads (small footprint -> many CTAs per SM hide the load latency).
 template <int DP>
 __global__ void __launch_bounds__(ATT_THREADS)
 window_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int ldq,
                         __nv_bfloat16* __restrict__ out, int ldo, const float* __restrict__ rel_table, int H, int W, int nH,
-                        float scale, int shift) {
+                        int HG, float scale, int shift) {
     extern __shared__ __align__(16) unsigned char att_smem[];
-    const int nq = 3 * nH * DP;                  // valid elements per qkv row (ldq >= nq)
-    const int RS = nq * 2 + 16;                  // padded smem row stride (bytes)
-    unsigned char* rows = att_smem;              // [64][RS]
-    float* tab = reinterpret_cast<float*>(att_smem + 64 * RS);   // [nH][225]
-    int* lab = reinterpret_cast<int*>(tab + nH * 225);            // [64]
+    const int h0 = blockIdx.y * HG;              // first head of this CTA
+    const int nhl = min(HG, nH - h0);            // heads handled here
+    const int seg = HG * DP;                     // local elements per q / k / v section
+    const int RS = 3 * seg * 2 + 16;             // padded smem row stride (bytes)
+    unsigned char* rows = att_smem;              // [64][RS]  local layout [q(HG x DP) | k | v]
+    float* tab = reinterpret_cast<float*>(att_smem + 64 * RS);   // [HG][225]
+    int* lab = reinterpret_cast<int*>(tab + HG * 225);            // [64]
 
     const int nW = (H >> 3) * (W >> 3);
     const int win_g = blockIdx.x;                // global window index (b * nW + win)
@@ -60,14 +64,16 @@ window_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int ldq,
 
     // ---- stage q|k|v of the window -------------------------------------------------------
     const __nv_bfloat16* src = qkv + (size_t)win_g * 64 * ldq;
-    const int chunks_per_row = nq / 8;
+    const int cps = nhl * DP / 8;                // 16 B chunks per section actually present
+    const int chunks_per_row = 3 * cps;
     const uint32_t rows_s = (uint32_t)__cvta_generic_to_shared(rows);
     for (int i = tid; i < 64 * chunks_per_row; i += ATT_THREADS) {
         const int r = i / chunks_per_row, c = i - r * chunks_per_row;
-        cp_async16(rows_s + r * RS + c * 16, src + (size_t)r * ldq + c * 8);
+        const int w = c / cps, cc = c - w * cps;
+        cp_async16(rows_s + r * RS + (w * seg + cc * 8) * 2, src + (size_t)r * ldq + (w * nH + h0) * DP + cc * 8);
     }
     asm volatile("cp.async.commit_group;\n");
-    for (int i = tid; i < nH * 225; i += ATT_THREADS) tab[i] = __ldg(rel_table + i);
+    for (int i = tid; i < nhl * 225; i += ATT_THREADS) tab[i] = __ldg(rel_table + h0 * 225 + i);
     const int wpr = W >> 3;
     const int wi = win / wpr, wj = win - wi * wpr;
     const bool masked = shift > 0 && (wi == (H >> 3) - 1 || wj == wpr - 1);
@@ -80,8 +86,8 @@ window_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int ldq,
     const int r0 = strip * 16;
     const float LOG2E = 1.4426950408889634f;
 
-    for (int h = warp >> 2; h < nH; h += ATT_THREADS / 128) {
-        const int qc = h * DP, kc = (nH + h) * DP, vc = (2 * nH + h) * DP;   // element columns
+    for (int h = 0; h < nhl; ++h) {
+        const int qc = h * DP, kc = seg + h * DP, vc = 2 * seg + h * DP;     // local element columns
         float s[8][4];
 #pragma unroll
         for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
@@ -186,8 +192,10 @@ window_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int ldq,
     }
     __syncthreads();
     // ---- write the window's output rows (coalesced 16 B chunks, pad columns zeroed) -------------
-    __nv_bfloat16* dst = out + (size_t)win_g * 64 * ldo;
-    const int oc = ldo / 8, valid = nH * DP / 8;
+    __nv_bfloat16* dst = out + (size_t)win_g * 64 * ldo + h0 * DP;
+    const bool last = h0 + nhl >= nH;            // the last group also zeroes the pad columns
+    const int valid = nhl * DP / 8;
+    const int oc = last ? (ldo - h0 * DP) / 8 : valid;
     for (int i = tid; i < 64 * oc; i += ATT_THREADS) {
         const int r = i / oc, c = i - r * oc;
         uint4 v = make_uint4(0, 0, 0, 0);
@@ -212,9 +220,13 @@ extern "C" int srk_window_attention(const void* qkv, int ldq, void* out, int ldo
     SRK_REQUIRE(nH >= 1 && ldo % 8 == 0 && ldo >= nH * dp, "window_attention: bad nH/ldo");
     const int nq = 3 * nH * dp;
     SRK_REQUIRE(ldq % 8 == 0 && ldq >= nq, "window_attention: bad ldq");
-    const size_t smem = (size_t)64 * (nq * 2 + 16) + (size_t)nH * 225 * 4 + 64 * 4;
+    static int hg_env = -1;
+    if (hg_env < 0) { const char* e = getenv("SRK_ATT_HG"); hg_env = e ? atoi(e) : 0; }
+    int HG = hg_env > 0 ? hg_env : (nH % 2 == 0 ? 2 : (nH % 3 == 0 ? 3 : 1));
+    if (HG > nH) HG = nH;
+    const size_t smem = (size_t)64 * (3 * HG * dp * 2 + 16) + (size_t)HG * 225 * 4 + 64 * 4;
     SRK_REQUIRE(smem <= 227 * 1024, "window_attention: window does not fit shared memory");
-    const int grid = nB * (H / 8) * (W / 8);
+    const dim3 grid(nB * (H / 8) * (W / 8), (nH + HG - 1) / HG);
     cudaStream_t st = (cudaStream_t)stream;
     ProfScope ps(SRK_PROF_ATTENTION, stream);
 #define LAUNCH(D)                                                                             \
@@ -222,7 +234,7 @@ extern "C" int srk_window_attention(const void* qkv, int ldq, void* out, int ldo
         SRK_CUDA(cudaFuncSetAttribute(window_attention_kernel<D>,                             \
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         window_attention_kernel<D><<<grid, ATT_THREADS, smem, st>>>(                          \
-            (const __nv_bfloat16*)qkv, ldq, (__nv_bfloat16*)out, ldo, rel_table, H, W, nH, scale,  \
+            (const __nv_bfloat16*)qkv, ldq, (__nv_bfloat16*)out, ldo, rel_table, H, W, nH, HG, scale,  \
             shift);                                                                           \
     } while (0)
     if (dp == 16) LAUNCH(16);

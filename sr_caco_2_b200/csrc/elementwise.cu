@@ -130,6 +130,107 @@ conv_in_kernel(const float* __restrict__ x, int B, int h, int w, int H, int W, f
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// conv_in + patch_embed.norm + norm1 of the first Swin block in one pass (one warp per pixel,
+// lane = channel pair): writes the shallow feature F0 (fp32), the residual stream X = LN_pe(F0)
+// (fp32) and the first block's GEMM operand LN_1(X) (16-bit, window-major rows).
+// network_swinir.py:939 (conv_first), :610-614 (patch_embed + norm), :293-306 (norm1 + partition).
+// ------------------------------------------------------------------------------------------
+template <int NP>
+__global__ void __launch_bounds__(256)
+conv_in_ln_kernel(const float* __restrict__ x, int B, int h, int w, int H, int W, float in_scale,
+                  const float* __restrict__ wgt, const float* __restrict__ bias, int C,
+                  float* __restrict__ f0, float* __restrict__ xa, int ld32,
+                  const float* __restrict__ g1, const float* __restrict__ b1,
+                  const float* __restrict__ g2, const float* __restrict__ b2,
+                  uint16_t* __restrict__ a16, int ld16, int dt16, int win_shift) {
+    extern __shared__ float cws[];                // [9][ld32] weights (tap major, zero padded), then bias[ld32]
+    for (int i = threadIdx.x; i < 9 * ld32; i += blockDim.x) {
+        const int t = i / ld32, c = i - t * ld32;
+        cws[i] = c < C ? wgt[c * 9 + t] : 0.f;
+    }
+    for (int i = threadIdx.x; i < ld32; i += blockDim.x) cws[9 * ld32 + i] = i < C ? bias[i] : 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long npix = (long long)B * H * W;
+    const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+    float2 G1[NP], B1[NP], G2[NP], B2[NP];
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+        const int c = 64 * k + 2 * lane;
+        const bool in = c < C;
+        G1[k] = in ? *reinterpret_cast<const float2*>(g1 + c) : make_float2(0.f, 0.f);
+        B1[k] = in ? *reinterpret_cast<const float2*>(b1 + c) : make_float2(0.f, 0.f);
+        G2[k] = in ? *reinterpret_cast<const float2*>(g2 + c) : make_float2(0.f, 0.f);
+        B2[k] = in ? *reinterpret_cast<const float2*>(b2 + c) : make_float2(0.f, 0.f);
+    }
+    const float inv_c = 1.f / (float)C;
+    for (long long pix = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pix < npix; pix += wstride) {
+        const int px = (int)(pix % W), py = (int)((pix / W) % H), bi = (int)(pix / ((long long)W * H));
+        float in[9];
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                int yy = py + dy - 1, xx = px + dx - 1;
+                float val = 0.f;
+                if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+                    if (yy >= h) yy = 2 * (h - 1) - yy;
+                    if (xx >= w) xx = 2 * (w - 1) - xx;
+                    val = __ldg(x + ((size_t)bi * h + yy) * w + xx) * in_scale;
+                }
+                in[dy * 3 + dx] = val;
+            }
+        float2 v[NP];
+        float sm = 0.f;
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+            const int c = 64 * k + 2 * lane;
+            float2 acc = *reinterpret_cast<const float2*>(cws + 9 * ld32 + c);
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const float2 ww = *reinterpret_cast<const float2*>(cws + t * ld32 + c);
+                acc.x = fmaf(ww.x, in[t], acc.x); acc.y = fmaf(ww.y, in[t], acc.y);
+            }
+            v[k] = acc;
+            sm += acc.x + acc.y;
+            *reinterpret_cast<float2*>(f0 + (size_t)pix * ld32 + c) = acc;
+        }
+        // patch_embed.norm
+        float mean = warp_sum(sm) * inv_c, q = 0.f;
+#pragma unroll
+        for (int k = 0; k < NP; ++k)
+            if (64 * k + 2 * lane < C) { const float a0 = v[k].x - mean, a1 = v[k].y - mean; q += a0 * a0 + a1 * a1; }
+        float rstd = 1.f / sqrtf(warp_sum(q) * inv_c + 1e-5f);
+        sm = 0.f;
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+            const bool inb = 64 * k + 2 * lane < C;
+            v[k].x = inb ? (v[k].x - mean) * rstd * G1[k].x + B1[k].x : 0.f;
+            v[k].y = inb ? (v[k].y - mean) * rstd * G1[k].y + B1[k].y : 0.f;
+            sm += v[k].x + v[k].y;
+            *reinterpret_cast<float2*>(xa + (size_t)pix * ld32 + 64 * k + 2 * lane) = v[k];
+        }
+        // norm1 of the first block, stored at the token's window-major row
+        mean = warp_sum(sm) * inv_c; q = 0.f;
+#pragma unroll
+        for (int k = 0; k < NP; ++k)
+            if (64 * k + 2 * lane < C) { const float a0 = v[k].x - mean, a1 = v[k].y - mean; q += a0 * a0 + a1 * a1; }
+        rstd = 1.f / sqrtf(warp_sum(q) * inv_c + 1e-5f);
+        const int T = H * W;
+        const int tok = py * W + px;
+        const size_t row16 = (size_t)bi * T + (win_shift >= 0 ? token_to_win_pos(tok, H, W, win_shift) : tok);
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+            const bool inb = 64 * k + 2 * lane < C;
+            const float y0 = inb ? (v[k].x - mean) * rstd * G2[k].x + B2[k].x : 0.f;
+            const float y1 = inb ? (v[k].y - mean) * rstd * G2[k].y + B2[k].y : 0.f;
+            *reinterpret_cast<uint32_t*>(a16 + row16 * ld16 + 64 * k + 2 * lane) = pack2(y0, y1, dt16);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // conv_out: 3x3, 64 -> 1 channel on an NHWC fp16 image (conv_last network_swinir.py:868,942;
 // EDSR tail.1 network_nlsn.py:352-356).  Tensor-core direct convolution from a shared-memory
@@ -285,6 +386,28 @@ extern "C" int srk_conv_in(const float* x, int B, int h, int w, int H, int W, fl
     conv_in_kernel<<<grid, 256, (size_t)C * 10 * sizeof(float), (cudaStream_t)stream>>>(
         x, B, h, w, H, W, in_scale, wgt, bias, C, out32, ld32, (uint16_t*)out16, ld16, out16_dtype);
     SRK_LAUNCH_CHECK("conv_in_kernel");
+    return 0;
+}
+
+
+extern "C" int srk_conv_in_ln(const float* x, int B, int h, int w, int H, int W, float in_scale,
+                              const float* wgt, const float* bias, int C, float* f0, float* xa, int ld32,
+                              const float* g1, const float* b1, const float* g2, const float* b2,
+                              void* a16, int ld16, int out16_dtype, int win_shift, void* stream) {
+    SRK_REQUIRE(x && wgt && bias && f0 && xa && g1 && b1 && g2 && b2 && a16, "conv_in_ln: null pointer");
+    SRK_REQUIRE(B > 0 && h > 0 && w > 0 && H >= h && W >= w && H - h < h && W - w < w, "conv_in_ln: bad shape");
+    SRK_REQUIRE(H % 8 == 0 && W % 8 == 0 && (win_shift == -1 || win_shift == 0 || win_shift == 4), "conv_in_ln: bad window geometry");
+    SRK_REQUIRE(ld32 % 64 == 0 && ld32 == ld16 && ld32 >= C && ld32 <= 256 && C % 2 == 0, "conv_in_ln: channels must be padded to a multiple of 64 (<= 256)");
+    const long long npix = (long long)B * H * W;
+    const long long blocks = (npix + 7) / 8;
+    const int grid = (int)(blocks < 148 * 8 ? blocks : 148 * 8);
+    const size_t smem = (size_t)10 * ld32 * sizeof(float);
+    ProfScope ps(SRK_PROF_CONV_IN, stream);
+    cudaStream_t st = (cudaStream_t)stream;
+#define L(NP) conv_in_ln_kernel<NP><<<grid, 256, smem, st>>>(x, B, h, w, H, W, in_scale, wgt, bias, C, f0, xa, ld32, g1, b1, g2, b2, (uint16_t*)a16, ld16, out16_dtype, win_shift)
+    switch (ld32 / 64) { case 1: L(1); break; case 2: L(2); break; case 3: L(3); break; default: L(4); break; }
+#undef L
+    SRK_LAUNCH_CHECK("conv_in_ln_kernel");
     return 0;
 }
 

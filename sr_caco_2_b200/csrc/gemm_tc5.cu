@@ -20,6 +20,7 @@
 //   The epilogue of tile i overlaps the MMAs of tile i+1 (two TMEM stages).
 #include "gemm_common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace srk {
 
@@ -146,6 +147,7 @@ struct TcParams {
     // shared-memory plan (host computed): B-stationary keeps the CTA's whole weight tile
     // (nkb x BN x 64) resident and streams only A through `stages` 16 KB slots
     int bstat, stages, stage_bytes, bres_bytes;
+    int dbg;      // SRK_TC5_DBG (profiling experiments only): 1 skip phase R, 2 skip phase T body, 4 skip MMAs
 };
 
 template <int BN, int EPI>
@@ -164,7 +166,7 @@ struct TcCfg {
     static constexpr int MAX_STAGES = 8;
     static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
     static_assert(AVAIL / STAGE_BYTES >= 3, "not enough shared memory for the operand pipeline");
-    static_assert(BN % 64 == 0 && BN <= 192, "BN must be 64, 128 or 192");
+    static_assert(BN % 64 == 0 && (BN <= 192 || (BN == 256 && kStage16)), "BN must be 64, 128, 192 (or 256 with 16-bit staging)");
 };
 
 // row (0..127) of M tile `mt` -> GEMM row index m (or -1 when the row is outside the problem)
@@ -286,7 +288,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sb);
 #pragma unroll
                     for (int k = 0; k < TBK / 16; ++k)        // +32 B per UMMA_K inside the swizzle atom
-                        tc_mma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                        if (!(p.dbg & 4)) tc_mma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
                                    (kb | k) != 0 ? 1u : 0u);
                     tc_commit(empty_bar(stage));               // frees the smem slot when the MMAs retire
                     if (++stage == NS) { stage = 0; phase ^= 1; }
@@ -327,6 +329,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     unsigned char* srow = stg16 + (size_t)lane * Cfg::SROW16;
 #pragma unroll
                     for (int jj = 0; jj < SC / 4; ++jj) {
+                        if (p.dbg & 2) break;
                         const int c = q + 4 * jj;
                         uint32_t v[16];
                         asm volatile(
@@ -358,6 +361,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 const unsigned char* sbase = stg16 + (size_t)(q * 8) * Cfg::SROW16;
 #pragma unroll
                 for (int jj = 0; jj < (8 * CPR) / 32; ++jj) {
+                    if (p.dbg & 1) break;
                     const int idx = lane + 32 * jj;
                     const int row = idx / CPR, col = idx - row * CPR;
                     const int m = srowm[q * 8 + row];
@@ -620,6 +624,7 @@ static int launch_tc5(const CUtensorMap& ma, const CUtensorMap& mb, const TcPara
         attr_set = true;
     }
     TcParams p = p_in;
+    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("SRK_TC5_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
     const int total = p.m_tiles * p.n_tiles;
     int grid = total < num_sms() ? total : num_sms();
     // shared-memory plan: keep the weight tile resident when it fits and every CTA sees >= 2 M tiles
@@ -659,6 +664,8 @@ static int dispatch_tc5(const srk_gemm_args* a, const CUtensorMap& ma, const CUt
     }
     if (!img && res && ln && act == SRK_ACT_NONE && dt == SRK_BF16)
         return launch_tc5<BN, E_RES_LN, SRK_ACT_NONE, SRK_BF16>(ma, mb, p, st);
+    if (!img && res && ln && act == SRK_ACT_NONE && dt == SRK_FP16)
+        return launch_tc5<BN, E_RES_LN, SRK_ACT_NONE, SRK_FP16>(ma, mb, p, st);
     if (!img && res && !ln && !ps && act == SRK_ACT_NONE && (!o16 || dt == SRK_FP16))
         return launch_tc5<BN, E_RES, SRK_ACT_NONE, SRK_FP16>(ma, mb, p, st);
     if (!img && !res && !o32 && ps && act == SRK_ACT_NONE && dt == SRK_FP16)
@@ -671,7 +678,9 @@ int gemm_tcgen05(const srk_gemm_args* a, cudaStream_t st) {
     SRK_REQUIRE(((uintptr_t)a->A & 15) == 0 && ((uintptr_t)a->Wt & 15) == 0, "gemm(tcgen05): operands must be 16 B aligned");
     TcParams p{};
     p.g = make_gemm_params(a);
-    const int BN = a->N % 192 == 0 ? 192 : (a->N % 128 == 0 ? 128 : 64);
+    const bool ps256 = a->out16 && a->out16_mode == SRK_O16_PIXSHUF2 && !a->res && !a->out32 && !a->img && !a->ln_g &&
+                       a->act == SRK_ACT_NONE && a->out16_dtype == SRK_FP16 && a->N % 256 == 0;
+    const int BN = ps256 ? 256 : (a->N % 192 == 0 ? 192 : (a->N % 128 == 0 ? 128 : 64));
     if (a->ln_g) {
         SRK_REQUIRE(a->N == BN, "gemm(tcgen05): fused LayerNorm needs the whole row in one tile (N=%d)", a->N);
         SRK_REQUIRE(a->out16 && a->out16_mode == SRK_O16_ROWS && a->ln_b && a->ln_C > 0 && a->ln_C <= a->N,
@@ -712,6 +721,7 @@ int gemm_tcgen05(const srk_gemm_args* a, cudaStream_t st) {
         if (int rc = encode_map(&mb, a->dtype, 2, a->Wt, dims, strides, box)) return rc;
     }
     switch (BN) {
+        case 256: return launch_tc5<256, E_PIXSHUF, SRK_ACT_NONE, SRK_FP16>(ma, mb, p, st);
         case 192: return dispatch_tc5<192>(a, ma, mb, p, st);
         case 128: return dispatch_tc5<128>(a, ma, mb, p, st);
         default: return dispatch_tc5<64>(a, ma, mb, p, st);

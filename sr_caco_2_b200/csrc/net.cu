@@ -109,12 +109,24 @@ extern "C" int srk_swinir_forward(const srk_swinir_plan* p, const float* x, floa
     };
 
     // conv_first (+ reflect pad + input scaling), patch_embed.norm
-    TRY(srk_conv_in(x, B, h, w, H, W, p->img_range, p->conv_first_w, p->conv_first_b, C, b.F0, Cp,
-                    nullptr, 0, 0, stream));
-    TRY(srk_layernorm(b.F0, Cp, M, C, p->pe_norm_g, p->pe_norm_b, eps, nullptr, 0, 0, b.XA, H, W, -1, stream));
+    int nblk_total = 0;
+    for (int l = 0; l < p->n_layers; ++l) nblk_total += p->depths[l];
+    const bool first_fused = nblk_total > 0 && p->depths[0] > 0 && Cp <= 256;
+    if (first_fused) {
+        const srk_stb_params& s0 = p->stbs[0];
+        TRY(srk_conv_in_ln(x, B, h, w, H, W, p->img_range, p->conv_first_w, p->conv_first_b, C, b.F0, b.XA, Cp,
+                           p->pe_norm_g, p->pe_norm_b, s0.ln1_g, s0.ln1_b, b.A16, Cp, ldt, s0.shift, stream));
+    } else {
+        TRY(srk_conv_in(x, B, h, w, H, W, p->img_range, p->conv_first_w, p->conv_first_b, C, b.F0, Cp,
+                        nullptr, 0, 0, stream));
+        TRY(srk_layernorm(b.F0, Cp, M, C, p->pe_norm_g, p->pe_norm_b, eps, nullptr, 0, 0, b.XA, H, W, -1, stream));
+    }
 
     int blk = 0;
-    bool a16_ready = false;      // A16 already holds LN1 of the next block (fused epilogue)
+    void* a16 = b.A16;           // 16-bit operand buffer in use; `alt` is its ping-pong partner (the conv
+    void* alt = b.Y1;            // epilogue may not overwrite the image it is convolving)
+    bool a16_ready = first_fused; // A16 already holds LN1 of the next block (fused producer)
+    bool final_norm_done = false;
     for (int l = 0; l < p->n_layers; ++l) {
         const float* cur = b.XA;
         for (int d = 0; d < p->depths[l]; ++d, ++blk) {
@@ -124,11 +136,11 @@ extern "C" int srk_swinir_forward(const srk_swinir_plan* p, const float* x, floa
             SRK_REQUIRE(s.shift == 0 || s.shift == 4, "swinir: shift must be 0 or window_size/2");
             const int hd = C / nH;
             if (!a16_ready)
-                TRY(srk_layernorm(cur, Cp, M, C, s.ln1_g, s.ln1_b, eps, b.A16, Cp, ldt, nullptr, H, W, s.shift, stream));
+                TRY(srk_layernorm(cur, Cp, M, C, s.ln1_g, s.ln1_b, eps, a16, Cp, ldt, nullptr, H, W, s.shift, stream));
             a16_ready = false;
             // qkv
             {
-                srk_gemm_args g = lin_gemm(b.A16, Cp, s.w_qkv, s.b_qkv, b.nq_p, Cp);
+                srk_gemm_args g = lin_gemm(a16, Cp, s.w_qkv, s.b_qkv, b.nq_p, Cp);
                 g.out16 = b.QKV; g.ld16 = b.nq_p;
                 TRY(srk_gemm(&g, stream));
             }
@@ -140,15 +152,15 @@ extern "C" int srk_swinir_forward(const srk_swinir_plan* p, const float* x, floa
                 g.res = cur; g.out32 = b.XB; g.ld32 = Cp; g.win_shift = s.shift;
                 if (fuse_ln) {
                     g.ln_g = s.ln2_g; g.ln_b = s.ln2_b; g.ln_C = C; g.ln_win_shift = -1;   // LN2 rows in token order
-                    g.out16 = b.A16; g.ld16 = Cp;
+                    g.out16 = a16; g.ld16 = Cp;
                 }
                 TRY(srk_gemm(&g, stream));
             }
             if (!fuse_ln)
-                TRY(srk_layernorm(b.XB, Cp, M, C, s.ln2_g, s.ln2_b, eps, b.A16, Cp, ldt, nullptr, H, W, -1, stream));
+                TRY(srk_layernorm(b.XB, Cp, M, C, s.ln2_g, s.ln2_b, eps, a16, Cp, ldt, nullptr, H, W, -1, stream));
             // fc1 + GELU
             {
-                srk_gemm_args g = lin_gemm(b.A16, Cp, s.w_fc1, s.b_fc1, p->hid_p, Cp);
+                srk_gemm_args g = lin_gemm(a16, Cp, s.w_fc1, s.b_fc1, p->hid_p, Cp);
                 g.act = SRK_ACT_GELU; g.out16 = b.HID; g.ld16 = p->hid_p;
                 TRY(srk_gemm(&g, stream));
             }
@@ -158,11 +170,11 @@ extern "C" int srk_swinir_forward(const srk_swinir_plan* p, const float* x, floa
                 g.res = b.XB; g.out32 = b.XB; g.ld32 = Cp;
                 const bool last = d == p->depths[l] - 1;
                 if (last) {
-                    g.out16 = b.A16; g.ld16 = Cp; g.out16_dtype = cdt;
+                    g.out16 = a16; g.ld16 = Cp; g.out16_dtype = cdt;
                 } else if (fuse_ln) {
                     const srk_stb_params& nx = p->stbs[blk + 1];
                     g.ln_g = nx.ln1_g; g.ln_b = nx.ln1_b; g.ln_C = C; g.ln_win_shift = nx.shift;
-                    g.out16 = b.A16; g.ld16 = Cp;
+                    g.out16 = a16; g.ld16 = Cp;
                     a16_ready = true;
                 }
                 TRY(srk_gemm(&g, stream));
@@ -170,26 +182,44 @@ extern "C" int srk_swinir_forward(const srk_swinir_plan* p, const float* x, floa
             cur = b.XB;
         }
         if (p->depths[l] == 0)  // degenerate RSTB: conv of its own input
-            TRY(srk_layernorm(b.XA, Cp, M, C, nullptr, nullptr, eps, b.A16, Cp, cdt, nullptr, H, W, -1, stream));
-        // RSTB tail conv + residual with the RSTB input
+            TRY(srk_layernorm(b.XA, Cp, M, C, nullptr, nullptr, eps, a16, Cp, cdt, nullptr, H, W, -1, stream));
+        // RSTB tail conv + residual with the RSTB input  [+ fused LN: norm1 of the next RSTB's
+        // first block (window order), or the final `norm` after the last RSTB (token order)]
         {
-            srk_gemm_args g = conv_gemm(b.A16, Cp, H, W, p->rstb_convs[l]);
+            srk_gemm_args g = conv_gemm(a16, Cp, H, W, p->rstb_convs[l]);
             g.res = b.XA; g.out32 = b.XA; g.ld32 = Cp;
+            bool swap_after = false;
+            if (fuse_ln) {
+                if (l + 1 < p->n_layers && p->depths[l + 1] > 0) {
+                    const srk_stb_params& nx = p->stbs[blk];
+                    g.ln_g = nx.ln1_g; g.ln_b = nx.ln1_b; g.ln_C = C; g.ln_win_shift = nx.shift;
+                    g.out16 = alt; g.ld16 = Cp; g.out16_dtype = ldt;
+                    a16_ready = true; swap_after = true;
+                } else if (l + 1 == p->n_layers) {
+                    g.ln_g = p->norm_g; g.ln_b = p->norm_b; g.ln_C = C; g.ln_win_shift = -1;
+                    g.out16 = alt; g.ld16 = Cp; g.out16_dtype = cdt;
+                    final_norm_done = true; swap_after = true;
+                }
+            }
             TRY(srk_gemm(&g, stream));
+            if (swap_after) { void* t = a16; a16 = alt; alt = t; }
         }
     }
     // final norm -> conv_after_body + shallow residual
-    TRY(srk_layernorm(b.XA, Cp, M, C, p->norm_g, p->norm_b, eps, b.A16, Cp, cdt, nullptr, H, W, -1, stream));
+    if (!final_norm_done)
+        TRY(srk_layernorm(b.XA, Cp, M, C, p->norm_g, p->norm_b, eps, a16, Cp, cdt, nullptr, H, W, -1, stream));
+    const void* normed = a16;            // LN(norm) of the body output, fp16 NHWC
+    void* y1 = alt;                      // conv_after_body output
     const float out_scale = 1.f / p->img_range;
     const int s_up = p->upscale;
     {
-        srk_gemm_args g = conv_gemm(b.A16, Cp, H, W, p->conv_after_body);
-        g.res = b.F0; g.ld32 = Cp; g.out16 = b.Y1; g.ld16 = Cp;
+        srk_gemm_args g = conv_gemm(normed, Cp, H, W, p->conv_after_body);
+        g.res = b.F0; g.ld32 = Cp; g.out16 = y1; g.ld16 = Cp;
         TRY(srk_gemm(&g, stream));
     }
     if (p->upsampler == SRK_UPSAMPLER_PIXELSHUFFLE) {
         {
-            srk_gemm_args g = conv_gemm(b.Y1, Cp, H, W, p->conv_before_upsample);
+            srk_gemm_args g = conv_gemm(y1, Cp, H, W, p->conv_before_upsample);
             g.act = SRK_ACT_LRELU; g.out16 = b.U[0]; g.ld16 = 64;
             TRY(srk_gemm(&g, stream));
         }
@@ -203,7 +233,7 @@ extern "C" int srk_swinir_forward(const srk_swinir_plan* p, const float* x, floa
         TRY(srk_conv_out(b.U[p->n_upsample], 64, B, Hh, Ww, 64, p->conv_last_w, p->conv_last_b,
                          out_scale, y, h * s_up, w * s_up, stream));
     } else {
-        srk_gemm_args g = conv_gemm(b.Y1, Cp, H, W, p->upsample[0]);
+        srk_gemm_args g = conv_gemm(y1, Cp, H, W, p->upsample[0]);
         g.img = y; g.img_s = s_up; g.img_scale = out_scale; g.img_hc = h * s_up; g.img_wc = w * s_up;
         TRY(srk_gemm(&g, stream));
     }

