@@ -283,7 +283,7 @@ def main():
     step_tflops = value / world * gflop_patch / 1e3
     roofline = {"bound": "tensor", "achieved": None, "peak": peak, "unit": "TFLOP/s", "frac": None,
                 "traffic": None, "peak_source": peaks["source"] + ", sustained bf16",
-                "whole_step_achieved": step_tflops, "whole_step_frac": step_tflops / peak,
+                "scope": "per GPU (rank 0)", "whole_step_achieved": step_tflops, "whole_step_frac": step_tflops / peak,
                 "gflop_per_patch": gflop_patch}
     if prof_ms.get("gemm", 0) > 0:
         gf = fl(kw, hn, wn, gemm_only=True)
