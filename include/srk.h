@@ -134,6 +134,20 @@ typedef struct {
 } srk_gemm_args;
 int srk_gemm(const srk_gemm_args* g, void* stream);
 
+/* Fused Swin MLP (tcgen05 engine):  v = res + fc2(GELU(fc1(A) + b1)) + b2 ; out32 = v ;
+ * out16 = LayerNorm(v; ln_g, ln_b) written at the token's row (ln_win_shift = -1) or at its
+ * window-major row for the next block's cyclic shift, or a plain 16-bit cast when ln_g == NULL.
+ * A: (M, lda) bf16 rows in token order; W1: (hid_p, Cp) bf16; W2: (Cp, hid_p) bf16; hid_p %% 128 == 0.
+ * Replaces Mlp.forward network_swinir.py:39-45 + the residual / norm of :335, :293. */
+typedef struct {
+    const void* A; int lda; int M; int C; int Cp; int hid_p;
+    const void* W1; const float* b1; const void* W2; const float* b2;
+    const float* res; float* out32; int ld32;
+    void* out16; int ld16; int out16_dtype;
+    const float* ln_g; const float* ln_b; int ln_C; int ln_win_shift; int H, W;
+} srk_mlp_args;
+int srk_mlp(const srk_mlp_args* a, void* stream);
+
 /* LayerNorm over the first C of ld32 columns of fp32 rows -> 16-bit rows (pad columns zeroed).
  * mode 0: out row m <- LN(x row m); mode 1 (win_shift>=0): out row m (window-major) <-
  * LN(x row token(m)); g == NULL: plain cast without normalisation.  Optionally also writes

@@ -55,6 +55,26 @@ W2 = t16(192, 384)
 us = run("fc2", A=HID, a_mode=0, lda=384, nB=B, H=H, W=W, Wt=W2, M=M, N=192, K=384, dtype=0, bias=bias, res=X, out32=X2, ld32=Cp,
          ln_g=lng, ln_b=lnb, ln_C=180, ln_win_shift=4, out16=A16, ld16=Cp, out16_dtype=0)
 report("fc2 N192 K384 +res+LN", us, 2*M*192*384, M*(768+768+768+384))
+# fused MLP
+def run_mlp():
+    m = L.MlpArgs()
+    m.A, m.lda, m.M, m.C, m.Cp, m.hid_p = L.ptr(A), Cp, M, 180, Cp, 384
+    m.W1, m.b1, m.W2, m.b2 = L.ptr(W1), L.ptr(bias), L.ptr(W2), L.ptr(bias)
+    m.res, m.out32, m.ld32, m.out16, m.ld16 = L.ptr(X), L.ptr(X2), Cp, L.ptr(A16), Cp
+    m.H, m.W, m.out16_dtype, m.ln_g, m.ln_b, m.ln_C, m.ln_win_shift = H, W, 0, L.ptr(lng), L.ptr(lnb), 180, 4
+    lib = L.load()
+    if os.environ.get("SRK_PROFILE_ONCE"):
+        L.check(lib.srk_mlp(C.byref(m), L.stream_ptr())); torch.cuda.synchronize(); return 1.0
+    for _ in range(3): L.check(lib.srk_mlp(C.byref(m), L.stream_ptr()))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10): L.check(lib.srk_mlp(C.byref(m), L.stream_ptr()))
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / 10 * 1e3
+if eng == "tcgen05":
+    us = run_mlp()
+    report("fused MLP 192-384-192 +LN", us, 2*M*192*384*2, M*(384+768+768+384))
 Ah = t16(M, Cp, dt=torch.float16); Wc = t16(192, 9*192, dt=torch.float16)
 us = run("convCC", A=Ah, a_mode=1, lda=Cp, nB=B, H=H, W=W, Wt=Wc, M=M, N=192, K=9*192, dtype=1, bias=bias, res=X, out32=X2, ld32=Cp)
 report("conv 192->192 +res", us, 2*M*192*1728, M*(384+768+768))

@@ -31,6 +31,14 @@ class GemmArgs(C.Structure):
                 ("img_wc", C.c_int)]
 
 
+class MlpArgs(C.Structure):
+    _fields_ = [("A", vp), ("lda", C.c_int), ("M", C.c_int), ("C", C.c_int), ("Cp", C.c_int),
+                ("hid_p", C.c_int), ("W1", vp), ("b1", fp), ("W2", vp), ("b2", fp), ("res", fp),
+                ("out32", fp), ("ld32", C.c_int), ("out16", vp), ("ld16", C.c_int),
+                ("out16_dtype", C.c_int), ("ln_g", fp), ("ln_b", fp), ("ln_C", C.c_int),
+                ("ln_win_shift", C.c_int), ("H", C.c_int), ("W", C.c_int)]
+
+
 class ConvParams(C.Structure):
     _fields_ = [("w", vp), ("b", fp), ("cin_p", C.c_int), ("n_p", C.c_int)]
 
@@ -80,6 +88,7 @@ PROTOTYPES = {
     "srk_metrics_roi": (C.c_int, [fp, fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp,
                                   vp, vp]),
     "srk_gemm": (C.c_int, [C.POINTER(GemmArgs), vp]),
+    "srk_mlp": (C.c_int, [C.POINTER(MlpArgs), vp]),
     "srk_layernorm": (C.c_int, [fp, C.c_int, C.c_int, C.c_int, fp, fp, C.c_float, vp, C.c_int,
                                 C.c_int, fp, C.c_int, C.c_int, C.c_int, vp]),
     "srk_window_attention": (C.c_int, [vp, C.c_int, vp, C.c_int, fp, C.c_int, C.c_int, C.c_int,

@@ -3,6 +3,7 @@
 // token-major (NHWC) activations with an fp32 residual stream.
 #include "common.cuh"
 #include <vector>
+#include <stdlib.h>
 
 namespace srk {
 
@@ -158,6 +159,30 @@ extern "C" int srk_swinir_forward(const srk_swinir_plan* p, const float* x, floa
             }
             if (!fuse_ln)
                 TRY(srk_layernorm(b.XB, Cp, M, C, s.ln2_g, s.ln2_b, eps, a16, Cp, ldt, nullptr, H, W, -1, stream));
+            const bool last = d == p->depths[l] - 1;
+            // the fused MLP kernel is correct but not yet faster than fc1 + fc2 (epilogue bound): opt-in
+            static const bool mlp_env = getenv("SRK_FUSED_MLP") && atoi(getenv("SRK_FUSED_MLP")) != 0;
+            const bool fused_mlp = mlp_env && fuse_ln && (Cp == 64 || Cp == 128 || Cp == 192) && p->hid_p % 128 == 0;
+            if (fused_mlp) {
+                // fc1 + GELU + fc2 + residual [+ next norm1 | + fp16 cast] in one tcgen05 kernel
+                srk_mlp_args m{};
+                m.A = a16; m.lda = Cp; m.M = M; m.C = C; m.Cp = Cp; m.hid_p = p->hid_p;
+                m.W1 = s.w_fc1; m.b1 = s.b_fc1; m.W2 = s.w_fc2; m.b2 = s.b_fc2;
+                m.res = b.XB; m.out32 = b.XB; m.ld32 = Cp; m.out16 = a16; m.ld16 = Cp; m.H = H; m.W = W;
+                m.ln_win_shift = -1;
+                if (last) {
+                    m.out16_dtype = cdt;
+                } else {
+                    const srk_stb_params& nx = p->stbs[blk + 1];
+                    m.ln_g = nx.ln1_g; m.ln_b = nx.ln1_b; m.ln_C = C; m.ln_win_shift = nx.shift; m.out16_dtype = ldt;
+                    a16_ready = true;
+                }
+                // the kernel reads A (a16) by TMA tile-by-tile and writes out16 rows of OTHER tiles when the
+                // next block is shifted, so the 16-bit output must not alias the operand: ping-pong
+                m.out16 = alt;
+                TRY(srk_mlp(&m, stream));
+                { void* t = a16; a16 = alt; alt = t; }
+            } else {
             // fc1 + GELU
             {
                 srk_gemm_args g = lin_gemm(a16, Cp, s.w_fc1, s.b_fc1, p->hid_p, Cp);
@@ -168,7 +193,6 @@ extern "C" int srk_swinir_forward(const srk_swinir_plan* p, const float* x, floa
             {
                 srk_gemm_args g = lin_gemm(b.HID, p->hid_p, s.w_fc2, s.b_fc2, Cp, p->hid_p);
                 g.res = b.XB; g.out32 = b.XB; g.ld32 = Cp;
-                const bool last = d == p->depths[l] - 1;
                 if (last) {
                     g.out16 = a16; g.ld16 = Cp; g.out16_dtype = cdt;
                 } else if (fuse_ln) {
@@ -178,6 +202,7 @@ extern "C" int srk_swinir_forward(const srk_swinir_plan* p, const float* x, floa
                     a16_ready = true;
                 }
                 TRY(srk_gemm(&g, stream));
+            }
             }
             cur = b.XB;
         }

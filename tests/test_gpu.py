@@ -328,6 +328,60 @@ def test_gemm_conv3x3_pixelshuffle_and_image_epilogues(L, engine):
     assert float((img.cpu() - exp).abs().max()) < 3e-3 * max(1.0, float(exp.abs().max()))
 
 
+@pytest.mark.parametrize("dims", [(180, 192, 360, 384), (60, 64, 120, 128), (128, 128, 256, 256)])
+def test_fused_mlp_kernel(L, dims):
+    """srk_mlp (tcgen05): x + fc2(GELU(fc1(A)+b1))+b2 with fused LayerNorm / cast, vs fp32 torch on
+    the same bf16-rounded operands."""
+    if "tcgen05" not in ENGINES:
+        pytest.skip("tcgen05 engine not under test")
+    L.set_engine("tcgen05")
+    Cc, Cp, hid, hid_p = dims
+    g = torch.Generator().manual_seed(8)
+    B, H, W = 3, 16, 24
+    M = B * H * W
+    A = torch.zeros(M, Cp); A[:, :Cc] = torch.randn(M, Cc, generator=g)
+    W1 = torch.zeros(hid_p, Cp); W1[:hid, :Cc] = torch.randn(hid, Cc, generator=g) * 0.08
+    W2 = torch.zeros(Cp, hid_p); W2[:Cc, :hid] = torch.randn(Cc, hid, generator=g) * 0.08
+    b1 = torch.zeros(hid_p); b1[:hid] = torch.randn(hid, generator=g) * 0.1
+    b2 = torch.zeros(Cp); b2[:Cc] = torch.randn(Cc, generator=g) * 0.1
+    res = torch.zeros(M, Cp); res[:, :Cc] = torch.randn(M, Cc, generator=g)
+    gam, bet = torch.randn(Cc, generator=g), torch.randn(Cc, generator=g)
+    Ab, W1b, W2b = A.bfloat16(), W1.bfloat16(), W2.bfloat16()
+    hidv = F.gelu(Ab.float() @ W1b.float().t() + b1).bfloat16().float()
+    ref = res + hidv @ W2b.float().t() + b2
+    refln = F.layer_norm(ref[:, :Cc], (Cc,), gam, bet, 1e-5)
+    dv = lambda t: t.to(DEV)
+    Ad, W1d, W2d, b1d, b2d, gd, bd = dv(Ab), dv(W1b), dv(W2b), dv(b1), dv(b2), dv(gam), dv(bet)
+    for shift in (-1, 0, 4, None):
+        x32 = dv(res.clone())
+        o16 = torch.full((M, Cp), 5.0, dtype=torch.bfloat16 if shift is not None else torch.float16, device=DEV)
+        m = L.MlpArgs()
+        m.A, m.lda, m.M, m.C, m.Cp, m.hid_p = L.ptr(Ad), Cp, M, Cc, Cp, hid_p
+        m.W1, m.b1, m.W2, m.b2 = L.ptr(W1d), L.ptr(b1d), L.ptr(W2d), L.ptr(b2d)
+        m.res, m.out32, m.ld32, m.out16, m.ld16 = L.ptr(x32), L.ptr(x32), Cp, L.ptr(o16), Cp
+        m.H, m.W, m.ln_win_shift = H, W, -1
+        if shift is None:
+            m.out16_dtype = L.SRK_FP16
+        else:
+            m.out16_dtype, m.ln_g, m.ln_b, m.ln_C, m.ln_win_shift = L.SRK_BF16, L.ptr(gd), L.ptr(bd), Cc, shift
+        L.check(L.load().srk_mlp(C.byref(m), L.stream_ptr()))
+        got32 = x32.cpu()
+        assert float((got32[:, :Cc] - ref[:, :Cc]).abs().max()) < 4e-3 * max(1.0, float(ref.abs().max()))
+        if Cp > Cc:
+            assert float(got32[:, Cc:].abs().max()) == 0.0
+        if shift is None:
+            assert float((o16.float().cpu()[:, :Cc] - ref[:, :Cc]).abs().max()) < 0.02 * max(1.0, float(ref.abs().max()))
+        else:
+            exp = refln
+            if shift >= 0:
+                gm = O.window_gather_map(H, W, 8, shift)
+                idx = (torch.arange(B)[:, None] * H * W + gm[None, :]).reshape(-1)
+                exp = refln[idx]
+            assert float((o16.float().cpu()[:, :Cc] - exp).abs().max()) < 0.05
+            if Cp > Cc:
+                assert float(o16.float().cpu()[:, Cc:].abs().max()) == 0.0
+
+
 @pytest.mark.parametrize("geom", [(60, 6, 16, 16, 24), (180, 6, 32, 24, 16), (64, 2, 32, 8, 8)])
 def test_window_attention(L, geom):
     Cdim, nh, dp, H, W = geom
