@@ -18,8 +18,7 @@
 //                 map), fp32 / 16-bit stores, PixelShuffle(2) / pixelshuffle-direct addressing
 //                 and, optionally, LayerNorm of the finished row (warp-shuffle statistics).
 //   The epilogue of tile i overlaps the MMAs of tile i+1 (two TMEM stages).
-#include "gemm_common.cuh"
-#include <cuda.h>
+#include "tc5_ptx.cuh"
 #include <stdlib.h>
 
 namespace srk {
@@ -27,118 +26,6 @@ namespace srk {
 constexpr int TBM = 128, TBK = 64;
 constexpr int TC_THREADS = 320;           // 10 warps: TMA, MMA, 8 epilogue
 constexpr int TC_SMEM_TOTAL = 227 * 1024;
-
-// ---- PTX wrappers ----------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
-        "@P1 bra DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "DONE:\n"
-        "}\n" ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
-                                            int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                           uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n"
-        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
-          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
-          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-        : "memory");
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
-
-// K-major, 128-byte swizzled operand tile (rows of 64 x 16-bit = 128 B, 8-row groups of 1024 B):
-// start address >> 4 | LBO (unused for swizzled K-major, 1) | SBO = 1024 B | version 1 | SWIZZLE_128B
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-// kind::f16 instruction descriptor: D fp32, A/B both `fmt` (0 = F16, 1 = BF16), K-major A and B
-__host__ __device__ constexpr uint32_t umma_idesc(int fmt, int M, int N) {
-    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) |
-           ((uint32_t)(M >> 4) << 24);
-}
-
-// epilogue specialisations (E_GENERIC keeps every option as a run-time flag)
-enum { E_GENERIC = 0, E_O16 = 1, E_RES_LN = 2, E_RES = 3, E_PIXSHUF = 4 };
-
-template <int DT>
-__device__ __forceinline__ uint32_t packf(float a, float b) {
-    if (DT == SRK_BF16) {
-        __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-        return *reinterpret_cast<uint32_t*>(&t);
-    }
-    a = fminf(fmaxf(a, -65504.f), 65504.f);
-    b = fminf(fmaxf(b, -65504.f), 65504.f);
-    __half2 t = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&t);
-}
-template <int ACT>
-__device__ __forceinline__ float actf(float v) {
-    if (ACT == SRK_ACT_GELU) return gelu_erf(v);
-    if (ACT == SRK_ACT_LRELU) return v > 0.f ? v : 0.01f * v;
-    if (ACT == SRK_ACT_RELU) return fmaxf(v, 0.f);
-    return v;
-}
 
 struct TcParams {
     GemmP g;
@@ -590,7 +477,7 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-static int encode_map(CUtensorMap* map, int dtype, int rank, const void* ptr, const cuuint64_t* dims,
+int encode_map(CUtensorMap* map, int dtype, int rank, const void* ptr, const cuuint64_t* dims,
                       const cuuint64_t* strides_bytes, const cuuint32_t* box) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return fail(SRK_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
@@ -603,7 +490,7 @@ static int encode_map(CUtensorMap* map, int dtype, int rank, const void* ptr, co
     return 0;
 }
 
-static int num_sms() {
+int num_sms() {
     static int n[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
