@@ -206,7 +206,15 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 if (q == 0) {
 #pragma unroll
                     for (int j = 0; j < BN / 32; ++j) sbias[lane + 32 * j] = __ldg(g.bias + n0 + lane + 32 * j);
-                    srowm[lane] = tile_row_to_m(p, mt, lg * 32 + lane);
+                    int mm = tile_row_to_m(p, mt, lg * 32 + lane);
+                    if (EPI == E_PIXSHUF && mm >= 0) {
+                        // PixelShuffle(2): store the index of output pixel (b, 2y, 2x) instead of m, so the
+                        // per-chunk address needs no integer division
+                        const int bi = mm / g.T, rem = mm - bi * g.T;
+                        const int y = rem / g.W, x = rem - y * g.W;
+                        mm = (bi * 2 * g.H + 2 * y) * (2 * g.W) + 2 * x;
+                    }
+                    srowm[lane] = mm;
                 }
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + lg) : "memory");
                 mbar_wait(tfull_bar(as), aphase);
@@ -254,8 +262,15 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     const int m = srowm[q * 8 + row];
                     const uint4 val = *reinterpret_cast<const uint4*>(sbase + (size_t)row * Cfg::SROW16 + col * 16);
                     if (m >= 0) {
-                        uint16_t* dst = EPI == E_PIXSHUF ? g.out16 + off16_of(g, m, n0 + col * 8)
-                                                         : g.out16 + (size_t)m * g.ld16 + n0 + col * 8;
+                        uint16_t* dst;
+                        if (EPI == E_PIXSHUF) {
+                            // column n -> sub-pixel group n / (N/4), channel n % (N/4); N/4 is a multiple of 64
+                            const int cq = g.N >> 2, n = n0 + col * 8;
+                            const int grp = n / cq, ch = n - grp * cq;
+                            dst = g.out16 + ((size_t)m + (grp >> 1) * (2 * g.W) + (grp & 1)) * g.ld16 + ch;
+                        } else {
+                            dst = g.out16 + (size_t)m * g.ld16 + n0 + col * 8;
+                        }
                         *reinterpret_cast<uint4*>(dst) = val;
                     }
                 }
