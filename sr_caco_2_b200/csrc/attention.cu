@@ -65,12 +65,34 @@ window_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int ldq,
     // ---- stage q|k|v of the window -------------------------------------------------------
     const __nv_bfloat16* src = qkv + (size_t)win_g * 64 * ldq;
     const int cps = nhl * DP / 8;                // 16 B chunks per section actually present
-    const int chunks_per_row = 3 * cps;
     const uint32_t rows_s = (uint32_t)__cvta_generic_to_shared(rows);
-    for (int i = tid; i < 64 * chunks_per_row; i += ATT_THREADS) {
-        const int r = i / chunks_per_row, c = i - r * chunks_per_row;
-        const int w = c / cps, cc = c - w * cps;
-        cp_async16(rows_s + r * RS + (w * seg + cc * 8) * 2, src + (size_t)r * ldq + (w * nH + h0) * DP + cc * 8);
+    {
+        // (row, chunk) decomposition: with cps a power of two (the usual case) every thread keeps a
+        // fixed 16 B column and walks down the rows with pointer increments
+        const bool pow2 = (cps & (cps - 1)) == 0 && cps <= ATT_THREADS;
+        if (pow2) {
+            const int sh = 31 - __clz(cps);
+            const int r0 = tid >> sh, cc = tid & (cps - 1), rstep = ATT_THREADS >> sh;
+#pragma unroll
+            for (int w = 0; w < 3; ++w) {
+                const __nv_bfloat16* sp = src + (w * nH + h0) * DP + (size_t)r0 * ldq + cc * 8;
+                uint32_t dp = rows_s + w * seg * 2 + r0 * RS + cc * 16;
+                for (int r = r0; r < 64; r += rstep) {
+                    cp_async16(dp, sp);
+                    sp += (size_t)rstep * ldq;
+                    dp += rstep * RS;
+                }
+            }
+        } else {
+            for (int w = 0; w < 3; ++w) {
+                const __nv_bfloat16* sw = src + (w * nH + h0) * DP;
+                const uint32_t dw = rows_s + w * seg * 2;
+                for (int i = tid; i < 64 * cps; i += ATT_THREADS) {
+                    const int r = i / cps, cc = i - r * cps;
+                    cp_async16(dw + r * RS + cc * 16, sw + (size_t)r * ldq + cc * 8);
+                }
+            }
+        }
     }
     asm volatile("cp.async.commit_group;\n");
     for (int i = tid; i < nhl * 225; i += ATT_THREADS) tab[i] = __ldg(rel_table + h0 * 225 + i);
@@ -86,8 +108,12 @@ window_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int ldq,
     const int r0 = strip * 16;
     const float LOG2E = 1.4426950408889634f;
 
+    // per-lane ldmatrix base addresses (head / k-step offsets are added as immediates)
+    const uint32_t a_addr = rows_s + (r0 + (lane & 7) + ((lane >> 3) & 1) * 8) * RS + (lane >> 4) * 16;
+    const uint32_t k_addr = rows_s + ((lane & 7) + (lane >> 4) * 8) * RS + ((lane >> 3) & 1) * 16 + seg * 2;
+    const uint32_t v_addr = rows_s + ((lane & 7) + ((lane >> 3) & 1) * 8) * RS + (lane >> 4) * 16 + 2 * seg * 2;
     for (int h = 0; h < nhl; ++h) {
-        const int qc = h * DP, kc = seg + h * DP, vc = 2 * seg + h * DP;     // local element columns
+        const int qc = h * DP;                                               // local element column of this head
         float s[8][4];
 #pragma unroll
         for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
@@ -95,13 +121,11 @@ window_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int ldq,
 #pragma unroll
         for (int ks = 0; ks < DP / 16; ++ks) {
             uint32_t a[4];
-            ldsm_x4(a, rows_s + (r0 + (lane & 7) + ((lane >> 3) & 1) * 8) * RS +
-                           (qc + ks * 16 + (lane >> 4) * 8) * 2);
+            ldsm_x4(a, a_addr + (qc + ks * 16) * 2);
 #pragma unroll
             for (int np = 0; np < 4; ++np) {
                 uint32_t b[4];
-                ldsm_x4(b, rows_s + (np * 16 + (lane & 7) + (lane >> 4) * 8) * RS +
-                               (kc + ks * 16 + ((lane >> 3) & 1) * 8) * 2);
+                ldsm_x4(b, k_addr + np * 16 * RS + (qc + ks * 16) * 2);
                 mma_bf16(s[2 * np], a, b[0], b[1]);
                 mma_bf16(s[2 * np + 1], a, b[2], b[3]);
             }
@@ -173,8 +197,7 @@ window_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int ldq,
 #pragma unroll
             for (int nd = 0; nd < DP / 16; ++nd) {
                 uint32_t b[4];
-                ldsm_x4_trans(b, rows_s + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * RS +
-                                     (vc + nd * 16 + (lane >> 4) * 8) * 2);
+                ldsm_x4_trans(b, v_addr + kk * 16 * RS + (qc + nd * 16) * 2);
                 mma_bf16(o[2 * nd], a, b[0], b[1]);
                 mma_bf16(o[2 * nd + 1], a, b[2], b[3]);
             }
@@ -196,11 +219,25 @@ window_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int ldq,
     const bool last = h0 + nhl >= nH;            // the last group also zeroes the pad columns
     const int valid = nhl * DP / 8;
     const int oc = last ? (ldo - h0 * DP) / 8 : valid;
-    for (int i = tid; i < 64 * oc; i += ATT_THREADS) {
-        const int r = i / oc, c = i - r * oc;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (c < valid) v = *reinterpret_cast<const uint4*>(rows + (size_t)r * RS + c * 16);
-        *reinterpret_cast<uint4*>(dst + (size_t)r * ldo + c * 8) = v;
+    if ((oc & (oc - 1)) == 0 && oc <= ATT_THREADS) {
+        const int sh = 31 - __clz(oc);
+        const int r0w = tid >> sh, c = tid & (oc - 1), rstep = ATT_THREADS >> sh;
+        const unsigned char* sp = rows + (size_t)r0w * RS + c * 16;
+        __nv_bfloat16* dp = dst + (size_t)r0w * ldo + c * 8;
+        for (int r = r0w; r < 64; r += rstep) {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (c < valid) v = *reinterpret_cast<const uint4*>(sp);
+            *reinterpret_cast<uint4*>(dp) = v;
+            sp += (size_t)rstep * RS;
+            dp += (size_t)rstep * ldo;
+        }
+    } else {
+        for (int i = tid; i < 64 * oc; i += ATT_THREADS) {
+            const int r = i / oc, c = i - r * oc;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (c < valid) v = *reinterpret_cast<const uint4*>(rows + (size_t)r * RS + c * 16);
+            *reinterpret_cast<uint4*>(dst + (size_t)r * ldo + c * 8) = v;
+        }
     }
 }
 
