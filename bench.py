@@ -231,8 +231,6 @@ def main():
         sampler.start()
     acc.zero_()
     L.launch_count(reset=True)
-    L.profile_read(reset=True)
-    L.profile(True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
@@ -245,6 +243,14 @@ def main():
     ms = ev0.elapsed_time(ev1)
     launches = L.launch_count()
     clocks = sampler.stop() if rank == 0 else None
+    # the same K steps again with a CUDA-event pair around every kernel-family call (srk_profile):
+    # per-family device time for the roofline of the dominant kernel (kept out of `value`'s region
+    # because the ~400 event records per step cost ~2 %)
+    L.profile_read(reset=True)
+    L.profile(True)
+    for i in range(K):
+        device_step(i)
+    torch.cuda.synchronize()
     L.profile(False)
     prof_ms, prof_calls = L.profile_read(reset=True)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -307,6 +313,13 @@ def main():
     else:
         roofline.update(achieved=step_tflops, frac=step_tflops / peak,
                         kernel="whole step (per-kernel event timing unavailable)")
+    tp = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    if os.path.exists(tp) and args.workload == "cfg3" and args.geometry == "direct" and B == 32:
+        tj = json.load(open(tp))["gemm_family"]
+        roofline["traffic"] = tj["dram_bytes"]
+        roofline["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum summed over the %d GEMM launches of one "
+                                    "step (ncu launch list profiles/r01_launches_cfg3_step.csv); same per-step scope "
+                                    "as `achieved`" % tj["launches"])
 
     line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

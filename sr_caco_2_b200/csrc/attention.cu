@@ -49,6 +49,8 @@ window_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int ldq,
                         __nv_bfloat16* __restrict__ out, int ldo, const float* __restrict__ rel_table, int H, int W, int nH,
                         int HG, float scale, int shift) {
     extern __shared__ __align__(16) unsigned char att_smem[];
+    pdl_launch_dependents();
+    pdl_wait();
     const int h0 = blockIdx.y * HG;              // first head of this CTA
     const int nhl = min(HG, nH - h0);            // heads handled here
     const int seg = HG * DP;                     // local elements per q / k / v section
@@ -270,9 +272,9 @@ extern "C" int srk_window_attention(const void* qkv, int ldq, void* out, int ldo
     do {                                                                                      \
         SRK_CUDA(cudaFuncSetAttribute(window_attention_kernel<D>,                             \
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        window_attention_kernel<D><<<grid, ATT_THREADS, smem, st>>>(                          \
+        SRK_CUDA(launch_pdl(window_attention_kernel<D>, grid, dim3(ATT_THREADS), smem, st,     \
             (const __nv_bfloat16*)qkv, ldq, (__nv_bfloat16*)out, ldo, rel_table, H, W, nH, HG, scale,  \
-            shift);                                                                           \
+            shift));                                                                          \
     } while (0)
     if (dp == 16) LAUNCH(16);
     else if (dp == 32) LAUNCH(32);

@@ -99,6 +99,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const GemmP& g = p.g;
     const int total_tiles = p.m_tiles * p.n_tiles;
+    pdl_launch_dependents();                                          // the next kernel may queue up behind us
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < Cfg::MAX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -117,6 +118,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();                                                       // prologue done; now the previous grid's data
 
     if (warp == 0) {
         // ================================ TMA producer ================================
@@ -544,7 +546,7 @@ static int launch_tc5(const CUtensorMap& ma, const CUtensorMap& mb, const TcPara
     p.stages = (Cfg::AVAIL - p.bres_bytes) / p.stage_bytes;
     if (p.stages > Cfg::MAX_STAGES) p.stages = Cfg::MAX_STAGES;
     const size_t smem = (size_t)p.bres_bytes + (size_t)p.stages * p.stage_bytes + Cfg::STAGING_BYTES + 1024 + Cfg::AUX_BYTES;
-    gemm_tc5_kernel<BN, EPI, ACT, DT><<<grid, Cfg::THREADS, smem, st>>>(ma, mb, p);
+    SRK_CUDA(launch_pdl(gemm_tc5_kernel<BN, EPI, ACT, DT>, dim3(grid), dim3(Cfg::THREADS), smem, st, ma, mb, p));
     SRK_LAUNCH_CHECK("gemm_tc5_kernel");
     return 0;
 }
