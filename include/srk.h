@@ -131,6 +131,12 @@ typedef struct {
     /* pixelshuffle-direct image output (1 channel), cropped to img_hc x img_wc:
      * img[b, y*s+i, x*s+j] = v[m, i*s+j] * img_scale */
     float* img; int img_s; float img_scale; int img_hc, img_wc;
+    /* optional fused window attention (tcgen05 engine): the GEMM is the qkv projection of
+     * window-major rows (N = 3*attn_heads*32, rows [q|k|v][head][32]); each CTA keeps a head
+     * pair's q|k|v tile in shared memory, runs the 8x8-window attention on it (rel-pos bias
+     * attn_table (heads,225), shift mask for cyclic shift attn_shift, softmax, P v) and writes
+     * only the attention output to out16 (M, ld16 = attn_heads*32): q, k, v never reach HBM. */
+    const float* attn_table; int attn_heads; float attn_scale; int attn_shift;
 } srk_gemm_args;
 int srk_gemm(const srk_gemm_args* g, void* stream);
 

@@ -28,7 +28,8 @@ class GemmArgs(C.Structure):
                 ("out16", vp), ("ld16", C.c_int), ("out16_dtype", C.c_int), ("out16_mode", C.c_int),
                 ("ln_g", fp), ("ln_b", fp), ("ln_C", C.c_int), ("ln_win_shift", C.c_int),
                 ("img", fp), ("img_s", C.c_int), ("img_scale", C.c_float), ("img_hc", C.c_int),
-                ("img_wc", C.c_int)]
+                ("img_wc", C.c_int), ("attn_table", fp), ("attn_heads", C.c_int),
+                ("attn_scale", C.c_float), ("attn_shift", C.c_int)]
 
 
 class MlpArgs(C.Structure):

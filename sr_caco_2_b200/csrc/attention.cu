@@ -9,35 +9,10 @@
 // + relative_position_bias_table[relative_position_index] (:116-129, :156-162), + mask
 // (calculate_mask :260-285: -100 where the 3x3 region labels of the shifted frame differ),
 // softmax(-1), @ v, head merge (:176).  The attention matrix is never materialised in HBM.
-#include "common.cuh"
+#include "attention.cuh"
 #include <stdlib.h>
 
 namespace srk {
-
-__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0,
-                                         uint32_t b1) {
-    asm volatile(
-        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
-        "{%8,%9}, {%0,%1,%2,%3};\n"
-        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src));
-}
-
-__device__ __forceinline__ uint32_t packbf(float a, float b) {
-    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&t);
-}
 
 constexpr int ATT_THREADS = 128;          // 4 warps = the four 16-query strips of a window
 
@@ -105,116 +80,9 @@ window_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int ldq,
     asm volatile("cp.async.wait_group 0;\n");
     __syncthreads();
 
-    const int g = lane >> 2, t = lane & 3;
-    const int strip = warp & 3;                  // 16-query strip
-    const int r0 = strip * 16;
-    const float LOG2E = 1.4426950408889634f;
-
-    // per-lane ldmatrix base addresses (head / k-step offsets are added as immediates)
-    const uint32_t a_addr = rows_s + (r0 + (lane & 7) + ((lane >> 3) & 1) * 8) * RS + (lane >> 4) * 16;
-    const uint32_t k_addr = rows_s + ((lane & 7) + (lane >> 4) * 8) * RS + ((lane >> 3) & 1) * 16 + seg * 2;
-    const uint32_t v_addr = rows_s + ((lane & 7) + ((lane >> 3) & 1) * 8) * RS + (lane >> 4) * 16 + 2 * seg * 2;
-    for (int h = 0; h < nhl; ++h) {
-        const int qc = h * DP;                                               // local element column of this head
-        float s[8][4];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
-        // ---- S = Q K^T -----------------------------------------------------------------
-#pragma unroll
-        for (int ks = 0; ks < DP / 16; ++ks) {
-            uint32_t a[4];
-            ldsm_x4(a, a_addr + (qc + ks * 16) * 2);
-#pragma unroll
-            for (int np = 0; np < 4; ++np) {
-                uint32_t b[4];
-                ldsm_x4(b, k_addr + np * 16 * RS + (qc + ks * 16) * 2);
-                mma_bf16(s[2 * np], a, b[0], b[1]);
-                mma_bf16(s[2 * np + 1], a, b[2], b[3]);
-            }
-        }
-        // ---- + bias + mask, softmax --------------------------------------------------------
-        // rel_pos_index(i, j) with i = r0 + g (+8), j = nt*8 + 2t + e collapses to
-        //   base - 15*nt - e   (+15 for the second row): compile-time offsets from one pointer
-        const float* bp = tab + h * 225 + (2 * strip + 7) * 15 + (g - 2 * t + 7);
-        const int i0 = r0 + g, i1 = r0 + g + 8;
-        float m0 = -3.0e38f, m1 = -3.0e38f;
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const float v0 = fmaf(s[nt][e], scale, bp[-15 * nt - e]);
-                const float v1 = fmaf(s[nt][2 + e], scale, bp[15 - 15 * nt - e]);
-                s[nt][e] = v0; s[nt][2 + e] = v1;
-            }
-        }
-        if (masked) {                                          // only the last window row / column
-            const int l0 = lab[i0], l1 = lab[i1];
-#pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int lj = lab[nt * 8 + 2 * t + e];
-                    if (l0 != lj) s[nt][e] += -100.f;
-                    if (l1 != lj) s[nt][2 + e] += -100.f;
-                }
-            }
-        }
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
-            m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
-        }
-        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
-        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
-        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-        const float mb0 = m0 * LOG2E, mb1 = m1 * LOG2E;
-        float sum0 = 0.f, sum1 = 0.f;
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const float p0 = ex2_approx(fmaf(s[nt][e], LOG2E, -mb0));
-                const float p1 = ex2_approx(fmaf(s[nt][2 + e], LOG2E, -mb1));
-                s[nt][e] = p0; s[nt][2 + e] = p1;
-                sum0 += p0; sum1 += p1;
-            }
-        }
-        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
-        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
-        sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
-        sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
-        const float inv0 = rcp_approx(sum0), inv1 = rcp_approx(sum1);
-        // ---- O = P V  (P in [0,1] is rounded to bf16 un-normalised; 1/sum is applied to O) ----
-        float o[DP / 8][4];
-#pragma unroll
-        for (int i = 0; i < DP / 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-            uint32_t a[4];
-            a[0] = packbf(s[2 * kk][0], s[2 * kk][1]);
-            a[1] = packbf(s[2 * kk][2], s[2 * kk][3]);
-            a[2] = packbf(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-            a[3] = packbf(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-#pragma unroll
-            for (int nd = 0; nd < DP / 16; ++nd) {
-                uint32_t b[4];
-                ldsm_x4_trans(b, v_addr + kk * 16 * RS + (qc + nd * 16) * 2);
-                mma_bf16(o[2 * nd], a, b[0], b[1]);
-                mma_bf16(o[2 * nd + 1], a, b[2], b[3]);
-            }
-        }
-        // ---- O overwrites this strip's own q slot (only this warp reads it, and it is done) --
-        __syncwarp();
-#pragma unroll
-        for (int nt = 0; nt < DP / 8; ++nt) {
-            const int col = qc + nt * 8 + 2 * t;
-            *reinterpret_cast<uint32_t*>(rows + (size_t)(r0 + g) * RS + col * 2) =
-                packbf(o[nt][0] * inv0, o[nt][1] * inv0);
-            *reinterpret_cast<uint32_t*>(rows + (size_t)(r0 + g + 8) * RS + col * 2) =
-                packbf(o[nt][2] * inv1, o[nt][3] * inv1);
-        }
-    }
+    for (int h = 0; h < nhl; ++h)
+        attn_unit<DP>(rows_s, rows, RS, warp & 3, h * DP, seg + h * DP, 2 * seg + h * DP, tab + h * 225, lab, masked,
+                      scale, lane);
     __syncthreads();
     // ---- write the window's output rows (coalesced 16 B chunks, pad columns zeroed) -------------
     __nv_bfloat16* dst = out + (size_t)win_g * 64 * ldo + h0 * DP;

@@ -13,6 +13,7 @@ struct GemmP {
     uint16_t* out16; int ld16; int out16_dtype; int out16_mode;
     const float* ln_g; const float* ln_b; int ln_C; int ln_win_shift;
     float* img; int img_s; float img_scale; int img_hc, img_wc;
+    const float* attn_table; int attn_heads; float attn_scale; int attn_shift;
     int T;            // H*W (tokens per image) when H, W are set, else 0
     int cpb;          // channel blocks of 64 per conv tap (lda / 64)
 };
@@ -30,6 +31,7 @@ inline GemmP make_gemm_params(const srk_gemm_args* g) {
     p.ln_g = g->ln_g; p.ln_b = g->ln_b; p.ln_C = g->ln_C; p.ln_win_shift = g->ln_win_shift;
     p.img = g->img; p.img_s = g->img_s; p.img_scale = g->img_scale;
     p.img_hc = g->img_hc; p.img_wc = g->img_wc;
+    p.attn_table = g->attn_table; p.attn_heads = g->attn_heads; p.attn_scale = g->attn_scale; p.attn_shift = g->attn_shift;
     p.T = (g->H > 0 && g->W > 0) ? g->H * g->W : 0;
     p.cpb = g->lda / 64;
     return p;

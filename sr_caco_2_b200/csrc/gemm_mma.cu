@@ -190,15 +190,25 @@ int validate_gemm(const srk_gemm_args* g) {
         if (g->out16_mode == SRK_O16_PIXSHUF2)
             SRK_REQUIRE(g->N % 4 == 0 && g->ld16 >= g->N / 4 && g->ld16 % 8 == 0 && (g->N / 4) % 8 == 0, "gemm: bad pixel-shuffle output");
         else
-            SRK_REQUIRE(g->out16_mode == SRK_O16_ROWS && g->ld16 >= g->N && g->ld16 % 8 == 0, "gemm: bad ld16");
+            SRK_REQUIRE(g->out16_mode == SRK_O16_ROWS && (g->ld16 >= g->N || g->attn_table) && g->ld16 % 8 == 0, "gemm: bad ld16");
     }
     if (g->img) SRK_REQUIRE(g->img_s > 0 && g->img_s * g->img_s <= g->N && g->img_hc > 0 && g->img_wc > 0, "gemm: bad image output");
     SRK_REQUIRE(g->out32 || g->out16 || g->img, "gemm: no output");
+    if (g->attn_table) {
+        SRK_REQUIRE(g->a_mode == SRK_A_ROWS && g->attn_heads >= 2 && g->attn_heads % 2 == 0 && g->N == 3 * g->attn_heads * 32,
+                    "gemm: fused attention needs an even head count and N == 3*heads*32");
+        SRK_REQUIRE(g->out16 && g->ld16 == g->attn_heads * 32 && g->out16_mode == SRK_O16_ROWS && g->out16_dtype == SRK_BF16 &&
+                    g->dtype == SRK_BF16 && !g->res && !g->out32 && !g->ln_g && !g->img && g->act == SRK_ACT_NONE,
+                    "gemm: fused attention writes only the bf16 attention output (ld16 == heads*32)");
+        SRK_REQUIRE(g->H > 0 && g->W > 0 && g->H % 8 == 0 && g->W % 8 == 0 && g->M % 64 == 0 && g->M % (g->H * g->W) == 0 &&
+                    (g->attn_shift == 0 || g->attn_shift == 4), "gemm: fused attention needs window-major rows of whole images");
+    }
     return 0;
 }
 
 int gemm_mma_sync(const srk_gemm_args* g, cudaStream_t st) {
     if (g->ln_g) return fail(SRK_ERR_UNSUPPORTED, "gemm(mma.sync): fused LayerNorm epilogue is tcgen05-only");
+    if (g->attn_table) return fail(SRK_ERR_UNSUPPORTED, "gemm(mma.sync): fused attention epilogue is tcgen05-only");
     SRK_REQUIRE(g->N % MBN == 0, "gemm(mma.sync): N=%d must be a multiple of %d", g->N, MBN);
     GemmP p = make_gemm_params(g);
     const size_t smem = (size_t)MSTAGES * MSTAGE_BYTES;

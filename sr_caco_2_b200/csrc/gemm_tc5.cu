@@ -19,6 +19,7 @@
 //                 and, optionally, LayerNorm of the finished row (warp-shuffle statistics).
 //   The epilogue of tile i overlaps the MMAs of tile i+1 (two TMEM stages).
 #include "tc5_ptx.cuh"
+#include "attention.cuh"
 #include <stdlib.h>
 
 namespace srk {
@@ -39,7 +40,7 @@ struct TcParams {
 
 template <int BN, int EPI>
 struct TcCfg {
-    static constexpr bool kStage16 = EPI == E_O16 || EPI == E_PIXSHUF;   // 16-bit staging (math in phase T)
+    static constexpr bool kStage16 = EPI == E_O16 || EPI == E_PIXSHUF || EPI == E_ATTN;   // 16-bit staging (math in phase T)
     static constexpr int EPI_WARPS = kStage16 ? 16 : 8;       // warps per TMEM lane group: 4 or 2
     static constexpr int THREADS = 64 + 32 * EPI_WARPS;
     static constexpr int A_BYTES = TBM * TBK * 2;
@@ -127,8 +128,17 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             if (p.bstat && (int)blockIdx.x < total_tiles) {          // resident weight tile, loaded once
                 const int ntb = blockIdx.x % p.n_tiles;
                 mbar_expect_tx(bfull_bar, (uint32_t)p.bres_bytes);
-                for (int kb = 0; kb < p.nkb; ++kb)
-                    tma_load_2d(base + kb * Cfg::B_BYTES, &map_b, bfull_bar, kb * TBK, ntb * BN);
+                for (int kb = 0; kb < p.nkb; ++kb) {
+                    if (EPI == E_ATTN) {
+                        // head pair ntb: rows [q | k | v] x (2 heads x 32) gathered from the [which][head][32] weight
+#pragma unroll
+                        for (int w = 0; w < 3; ++w)
+                            tma_load_2d(base + kb * Cfg::B_BYTES + w * 8192, &map_b, bfull_bar, kb * TBK,
+                                        w * g.attn_heads * 32 + ntb * 64);
+                    } else {
+                        tma_load_2d(base + kb * Cfg::B_BYTES, &map_b, bfull_bar, kb * TBK, ntb * BN);
+                    }
+                }
             }
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
@@ -187,7 +197,89 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         }
     } else {
         // ================================ epilogue ================================
-        if constexpr (Cfg::kStage16) {
+        if constexpr (EPI == E_ATTN) {
+            // ---- fused window attention: the CTA's tile is 2 windows x (q|k|v of one head pair).
+            //      phase T stages it as bf16 rows (the attention kernel's smem layout), the 16 warps
+            //      then run one (window, head, strip) attention unit each and only O is stored ----
+            const int ew = warp - 2, lg = warp & 3, q = ew >> 2;
+            const int window = lg >> 1, head_l = lg & 1, strip = q;
+            const int tid_w = (lg & 1) * 128 + q * 32 + lane;           // 0..255 inside the window's warp group
+            unsigned char* stg_all = tc_smem_raw + (stg_base - raw);
+            unsigned char* wrows = stg_all + (size_t)(window * 64) * Cfg::SROW16;
+            const uint32_t wrows_s = stg_base + (uint32_t)(window * 64) * Cfg::SROW16;
+            float* sbias = reinterpret_cast<float*>(tc_smem_raw + (bars + 256 - raw));     // [192] local column order
+            float* stab = sbias + BN;                                                     // [2][225]
+            int* slab = reinterpret_cast<int*>(stab + 2 * 225);                           // [2][64]
+            const int pair = blockIdx.x % p.n_tiles;
+            const int nH = g.attn_heads;
+            {
+                const int et = threadIdx.x - 64;                                          // 0..511
+                if (et < BN) sbias[et] = __ldg(g.bias + (et >> 6) * nH * 32 + pair * 64 + (et & 63));
+                if (et < 450) stab[et] = __ldg(g.attn_table + pair * 450 + et);
+                asm volatile("bar.sync 7, 512;" ::: "memory");
+            }
+            const int nW = (g.H >> 3) * (g.W >> 3), wpr = g.W >> 3;
+            constexpr int SC = BN / 16;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int mt = tile / p.n_tiles;
+                const int as = it & 1, aphase = (it >> 1) & 1;
+                const int wg = mt * 2 + window;                         // global window index
+                const bool wvalid = wg * 64 < g.M;
+                const int win = wg % nW;
+                const int wi = win / wpr, wj = win - wi * wpr;
+                const bool masked = g.attn_shift > 0 && (wi == (g.H >> 3) - 1 || wj == wpr - 1);
+                if (tid_w < 64) slab[window * 64 + tid_w] = masked ? win_pos_label(win, tid_w, g.H, g.W, g.attn_shift) : 0;
+                mbar_wait(tfull_bar(as), aphase);
+                tc_fence_after();
+                {
+                    const uint32_t t_row = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN);
+                    unsigned char* srow = stg_all + (size_t)(lg * 32 + lane) * Cfg::SROW16;
+#pragma unroll
+                    for (int jj = 0; jj < SC / 4; ++jj) {
+                        const int c = q + 4 * jj;
+                        uint32_t v[16];
+                        asm volatile(
+                            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                            : "r"(t_row + c * 16));
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        const float4* bp = reinterpret_cast<const float4*>(sbias + c * 16);
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 bb = bp[j];
+                            pk[2 * j] = packf<SRK_BF16>(__uint_as_float(v[4 * j]) + bb.x, __uint_as_float(v[4 * j + 1]) + bb.y);
+                            pk[2 * j + 1] = packf<SRK_BF16>(__uint_as_float(v[4 * j + 2]) + bb.z, __uint_as_float(v[4 * j + 3]) + bb.w);
+                        }
+                        *reinterpret_cast<uint4*>(srow + c * 32) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        *reinterpret_cast<uint4*>(srow + c * 32 + 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(as));
+                asm volatile("bar.sync %0, 256;" ::"r"(5 + window) : "memory");   // window staged (+ labels)
+                if (wvalid)
+                    attn_unit<32>(wrows_s, wrows, Cfg::SROW16, strip, head_l * 32, 64 + head_l * 32, 128 + head_l * 32,
+                                  stab + head_l * 225, slab + window * 64, masked, g.attn_scale, lane);
+                asm volatile("bar.sync %0, 256;" ::"r"(5 + window) : "memory");   // every unit wrote its O
+                // attention output of the window: 64 rows x (2 heads x 32) = the first 128 B of each staged row
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                    const int idx = tid_w + 256 * jj;
+                    const int row = idx >> 3, col = idx & 7;
+                    const long long m = (long long)wg * 64 + row;
+                    if (m < g.M) {
+                        const uint4 val = *reinterpret_cast<const uint4*>(wrows + (size_t)row * Cfg::SROW16 + col * 16);
+                        *reinterpret_cast<uint4*>(g.out16 + (size_t)m * g.ld16 + pair * 64 + col * 8) = val;
+                    }
+                }
+                asm volatile("bar.sync %0, 256;" ::"r"(5 + window) : "memory");   // staging free for the next tile
+            }
+        } else if constexpr (Cfg::kStage16) {
             // ---- 16-bit outputs: bias + activation + pack in phase T (thread = row), then a pure
             //      coalesced 16 B/lane copy of the staged rows in phase R ----
             // four warps per TMEM lane group: quarter q drains 16-column sub-chunks q, q+4, ... in
@@ -533,10 +625,12 @@ static int launch_tc5(const CUtensorMap& ma, const CUtensorMap& mb, const TcPara
     int grid = total < num_sms() ? total : num_sms();
     // shared-memory plan: keep the weight tile resident when it fits and every CTA sees >= 2 M tiles
     const int bres = p.nkb * Cfg::B_BYTES;
-    p.bstat = (bres + 3 * Cfg::A_BYTES <= Cfg::AVAIL) && (p.m_tiles * p.n_tiles >= 2 * num_sms()) &&
-              (num_sms() >= p.n_tiles);
+    p.bstat = (bres + 3 * Cfg::A_BYTES <= Cfg::AVAIL) && (num_sms() >= p.n_tiles) &&
+              (EPI == E_ATTN || p.m_tiles * p.n_tiles >= 2 * num_sms());
+    if (EPI == E_ATTN && !p.bstat) return fail(SRK_ERR_UNSUPPORTED, "gemm(tcgen05): fused attention needs the resident-weight mode");
     if (p.bstat) {
         grid = (num_sms() / p.n_tiles) * p.n_tiles;             // multiple of n_tiles: nt is fixed per CTA
+        if (grid > total) grid = total;                         // total is a multiple of n_tiles too
         p.bres_bytes = bres;
         p.stage_bytes = Cfg::A_BYTES;
     } else {
@@ -595,6 +689,8 @@ int gemm_tcgen05(const srk_gemm_args* a, cudaStream_t st) {
     if (a->res || a->out32) SRK_REQUIRE(a->ld32 % 4 == 0, "gemm(tcgen05): ld32 %% 4");
     p.n_tiles = a->N / BN;
     p.nkb = a->K / TBK;
+    const bool attn = a->attn_table != nullptr;
+    if (attn) SRK_REQUIRE(BN == 192 && a->N == p.n_tiles * 192, "gemm(tcgen05): fused attention needs N == pairs * 192");
     CUtensorMap ma, mb;
     if (a->a_mode == SRK_A_CONV3X3) {
         // pick the 128-pixel box (BW x BH) that wastes the fewest out-of-image pixels
@@ -621,9 +717,10 @@ int gemm_tcgen05(const srk_gemm_args* a, cudaStream_t st) {
     {
         cuuint64_t dims[2] = {(cuuint64_t)a->K, (cuuint64_t)a->N};
         cuuint64_t strides[1] = {(cuuint64_t)a->K * 2};
-        cuuint32_t box[2] = {64, (cuuint32_t)BN};
+        cuuint32_t box[2] = {64, (cuuint32_t)(attn ? 64 : BN)};
         if (int rc = encode_map(&mb, a->dtype, 2, a->Wt, dims, strides, box)) return rc;
     }
+    if (attn) return launch_tc5<192, E_ATTN, SRK_ACT_NONE, SRK_BF16>(ma, mb, p, st);
     switch (BN) {
         case 256: return launch_tc5<256, E_PIXSHUF, SRK_ACT_NONE, SRK_FP16>(ma, mb, p, st);
         case 192: return dispatch_tc5<192>(a, ma, mb, p, st);

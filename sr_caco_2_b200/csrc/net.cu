@@ -139,6 +139,16 @@ extern "C" int srk_swinir_forward(const srk_swinir_plan* p, const float* x, floa
             if (!a16_ready)
                 TRY(srk_layernorm(cur, Cp, M, C, s.ln1_g, s.ln1_b, eps, a16, Cp, ldt, nullptr, H, W, s.shift, stream));
             a16_ready = false;
+            static const bool attn_env = !(getenv("SRK_FUSED_ATTN") && atoi(getenv("SRK_FUSED_ATTN")) == 0);
+            const bool fused_attn = attn_env && fuse_ln && p->dp == 32 && nH % 2 == 0 && p->ao_p == nH * 32 &&
+                                    b.nq_p == 3 * nH * 32;
+            if (fused_attn) {
+                // qkv projection + window attention in one kernel: q, k, v stay in shared memory
+                srk_gemm_args g = lin_gemm(a16, Cp, s.w_qkv, s.b_qkv, b.nq_p, Cp);
+                g.out16 = b.AO; g.ld16 = p->ao_p;
+                g.attn_table = s.rel_table; g.attn_heads = nH; g.attn_scale = 1.0f / sqrtf((float)hd); g.attn_shift = s.shift;
+                TRY(srk_gemm(&g, stream));
+            } else {
             // qkv
             {
                 srk_gemm_args g = lin_gemm(a16, Cp, s.w_qkv, s.b_qkv, b.nq_p, Cp);
@@ -147,6 +157,7 @@ extern "C" int srk_swinir_forward(const srk_swinir_plan* p, const float* x, floa
             }
             TRY(srk_window_attention(b.QKV, b.nq_p, b.AO, p->ao_p, s.rel_table, B, H, W, nH, p->dp,
                                      1.0f / sqrtf((float)hd), s.shift, stream));
+            }
             // proj + window_reverse + roll back + residual  [+ LN2 fused]
             {
                 srk_gemm_args g = lin_gemm(b.AO, p->ao_p, s.w_proj, s.b_proj, Cp, p->ao_p);

@@ -97,7 +97,7 @@ __host__ __device__ constexpr uint32_t umma_idesc(int fmt, int M, int N) {
 }
 
 // epilogue specialisations (E_GENERIC keeps every option as a run-time flag)
-enum { E_GENERIC = 0, E_O16 = 1, E_RES_LN = 2, E_RES = 3, E_PIXSHUF = 4 };
+enum { E_GENERIC = 0, E_O16 = 1, E_RES_LN = 2, E_RES = 3, E_PIXSHUF = 4, E_ATTN = 5 };
 
 template <int DT>
 __device__ __forceinline__ uint32_t packf(float a, float b) {

@@ -328,6 +328,40 @@ def test_gemm_conv3x3_pixelshuffle_and_image_epilogues(L, engine):
     assert float((img.cpu() - exp).abs().max()) < 3e-3 * max(1.0, float(exp.abs().max()))
 
 
+@pytest.mark.parametrize("geom", [(180, 6, 24, 16, 3), (128, 4, 16, 16, 1)])
+def test_fused_qkv_attention_equals_unfused(L, geom):
+    """E_ATTN epilogue (qkv GEMM + window attention in one tcgen05 kernel) vs srk_gemm + srk_window_attention."""
+    if "tcgen05" not in ENGINES:
+        pytest.skip("tcgen05 engine not under test")
+    L.set_engine("tcgen05")
+    Cc, nh, H, W, B = geom
+    Cp = (Cc + 63) // 64 * 64
+    d = Cc // nh
+    assert d <= 32
+    g = torch.Generator().manual_seed(12)
+    M = B * H * W
+    from sr_caco_2_b200 import packing as P
+    wq = torch.randn(3 * Cc, Cc, generator=g) * 0.08
+    bq = torch.randn(3 * Cc, generator=g) * 0.2
+    nq = 3 * nh * 32
+    wpk, bpk = P.pack_qkv(wq, bq, nh, d, 32, nq, Cp, L.SRK_BF16)
+    A = torch.zeros(M, Cp); A[:, :Cc] = torch.randn(M, Cc, generator=g)
+    table = (torch.randn(225, nh, generator=g) * 0.5).t().contiguous()
+    Ad, wd, bd, td = A.bfloat16().to(DEV), wpk.to(DEV), bpk.to(DEV), table.to(DEV)
+    for shift in (0, 4):
+        qkv = torch.empty(M, nq, dtype=torch.bfloat16, device=DEV)
+        ref = torch.empty(M, nh * 32, dtype=torch.bfloat16, device=DEV)
+        _gemm(L, A=Ad, a_mode=L.A_ROWS, lda=Cp, nB=B, H=H, W=W, Wt=wd, M=M, N=nq, K=Cp, dtype=L.SRK_BF16, bias=bd,
+              out16=qkv, ld16=nq, out16_dtype=L.SRK_BF16)
+        L.check(L.load().srk_window_attention(L.ptr(qkv), nq, L.ptr(ref), nh * 32, L.ptr(td), B, H, W, nh, 32,
+                                              d ** -0.5, shift, L.stream_ptr()))
+        got = torch.full((M, nh * 32), 3.0, dtype=torch.bfloat16, device=DEV)
+        _gemm(L, A=Ad, a_mode=L.A_ROWS, lda=Cp, nB=B, H=H, W=W, Wt=wd, M=M, N=nq, K=Cp, dtype=L.SRK_BF16, bias=bd,
+              out16=got, ld16=nh * 32, out16_dtype=L.SRK_BF16, attn_table=td, attn_heads=nh, attn_scale=d ** -0.5,
+              attn_shift=shift)
+        assert torch.equal(got, ref), float((got.float() - ref.float()).abs().max())
+
+
 @pytest.mark.parametrize("dims", [(180, 192, 360, 384), (60, 64, 120, 128), (128, 128, 256, 256)])
 def test_fused_mlp_kernel(L, dims):
     """srk_mlp (tcgen05): x + fc2(GELU(fc1(A)+b1))+b2 with fused LayerNorm / cast, vs fp32 torch on
