@@ -303,10 +303,11 @@ def main():
                 "scope": "per GPU (rank 0)", "whole_step_achieved": step_tflops, "whole_step_frac": step_tflops / peak,
                 "gflop_per_patch": gflop_patch}
     if prof_ms.get("gemm", 0) > 0:
-        gf = fl(kw, hn, wn, gemm_only=True)
+        fused_attn = kind == "swinir" and prof_ms.get("attention", 0.0) == 0.0   # attention ran inside the qkv GEMM kernel
+        gf = fl(kw, hn, wn, gemm_only=True, attention_in_gemm=True) if fused_attn else fl(kw, hn, wn, gemm_only=True)
         ach = gf * B * K / (prof_ms["gemm"] * 1e-3) / 1e12
         roofline.update(achieved=ach, frac=ach / peak,
-                        kernel="srk GEMM kernel family (every GEMM launch of the timed region, CUDA events on the launch stream)",
+                        kernel="srk tcgen05 GEMM kernel family incl. the fused qkv+window-attention kernel (every launch of K steps, CUDA events on the launch stream)",
                         algorithmic_gflop_per_patch_in_gemm=gf / 1e9,
                         launches_per_step=prof_calls["gemm"] / K, ms_per_step=prof_ms["gemm"] / K,
                         family_ms_per_step={k: v / K for k, v in prof_ms.items()})

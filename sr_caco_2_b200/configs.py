@@ -26,14 +26,19 @@ WORKLOADS = {
 }
 
 
-def swinir_flops(kw: dict, h: int, w: int, gemm_only: bool = False) -> float:
+def swinir_flops(kw: dict, h: int, w: int, gemm_only: bool = False, attention_in_gemm: bool = False) -> float:
     """FLOPs per patch at net-input size h x w (multiples of 8).  gemm_only: the part executed
     by the tensor-core GEMM kernel family (excludes the window-attention products and the
     1-channel input / output convs, which run in their own kernels)."""
     T, C = h * w, kw["embed_dim"]
     hid, nblk, s, cin = int(C * kw["mlp_ratio"]), sum(kw["depths"]), kw["upscale"], kw["in_chans"]
     gemm = T * nblk * (4 * C * C + 2 * C * hid) + T * (len(kw["depths"]) + 1) * 9 * C * C
-    other = T * nblk * 2 * 64 * C + T * 9 * cin * C
+    attn = T * nblk * 2 * 64 * C                  # q k^T and P v (fused into the qkv GEMM kernel when possible)
+    other = T * 9 * cin * C
+    if attention_in_gemm:
+        gemm += attn
+    else:
+        other += attn
     if kw["upsampler"] == "pixelshuffle":
         gemm += T * 9 * C * 64 + sum((4 ** k) * T * 9 * 64 * 256 for k in range(int(round(math.log2(s)))))
         other += s * s * T * 9 * 64 * cin
