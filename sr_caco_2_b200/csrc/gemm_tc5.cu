@@ -48,8 +48,8 @@ struct TcCfg {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int SROW = BN + 4;                       // fp32 staging row stride (floats)
     static constexpr int SROW16 = BN * 2 + 16;                // 16-bit staging row stride (bytes)
-    static constexpr int STAGING_BYTES = kStage16 ? TBM * SROW16 : TBM * SROW * 4;
-    static constexpr int AUX_BYTES = 256 + 8 * (BN + 32) * 4;   // barriers + per-lane-group bias row / row map
+    static constexpr int STAGING_BYTES = EPI == E_ATTN ? 2 * TBM * SROW16 : (kStage16 ? TBM * SROW16 : TBM * SROW * 4);
+    static constexpr int AUX_BYTES = EPI == E_ATTN ? 4096 : 256 + 8 * (BN + 32) * 4;   // barriers + per-lane-group bias row / row map
     static constexpr int AVAIL = TC_SMEM_TOTAL - STAGING_BYTES - 1024 - AUX_BYTES;   // operand bytes available
     static constexpr int MAX_STAGES = 8;
     static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
@@ -105,7 +105,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     if (threadIdx.x == 0) {
         for (int s = 0; s < Cfg::MAX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         mbar_init(bfull_bar, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), Cfg::EPI_WARPS); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI == E_ATTN ? Cfg::EPI_WARPS / 2 : Cfg::EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
@@ -199,45 +199,48 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         // ================================ epilogue ================================
         if constexpr (EPI == E_ATTN) {
             // ---- fused window attention: the CTA's tile is 2 windows x (q|k|v of one head pair).
-            //      phase T stages it as bf16 rows (the attention kernel's smem layout), the 16 warps
-            //      then run one (window, head, strip) attention unit each and only O is stored ----
-            const int ew = warp - 2, lg = warp & 3, q = ew >> 2;
-            const int window = lg >> 1, head_l = lg & 1, strip = q;
-            const int tid_w = (lg & 1) * 128 + q * 32 + lane;           // 0..255 inside the window's warp group
-            unsigned char* stg_all = tc_smem_raw + (stg_base - raw);
+            //      The 16 epilogue warps form two groups of 8 that take alternate tiles (group g uses
+            //      TMEM stage g and staging buffer g), so the drain / attention / store phases of two
+            //      tiles interleave.  Phase T stages the tile as bf16 rows (the attention kernel's smem
+            //      layout); the 4 warps of a window then run its 8 (head, strip) units and only O is stored.
+            const int ew = warp - 2, lg = warp & 3;
+            const int grp = ew >> 3, hq = (ew >> 2) & 1;
+            const int window = lg >> 1, strip = (lg & 1) * 2 + hq;
+            const int tid_w = (lg & 1) * 64 + hq * 32 + lane;             // 0..127 inside the (group, window) warps
+            unsigned char* stg_all = tc_smem_raw + (stg_base - raw) + (size_t)grp * TBM * Cfg::SROW16;
             unsigned char* wrows = stg_all + (size_t)(window * 64) * Cfg::SROW16;
-            const uint32_t wrows_s = stg_base + (uint32_t)(window * 64) * Cfg::SROW16;
+            const uint32_t wrows_s = stg_base + (uint32_t)(grp * TBM + window * 64) * Cfg::SROW16;
             float* sbias = reinterpret_cast<float*>(tc_smem_raw + (bars + 256 - raw));     // [192] local column order
             float* stab = sbias + BN;                                                     // [2][225]
-            int* slab = reinterpret_cast<int*>(stab + 2 * 225);                           // [2][64]
+            int* slab = reinterpret_cast<int*>(stab + 2 * 225) + (grp * 2 + window) * 64;  // [grp][window][64]
             const int pair = blockIdx.x % p.n_tiles;
             const int nH = g.attn_heads;
             {
                 const int et = threadIdx.x - 64;                                          // 0..511
                 if (et < BN) sbias[et] = __ldg(g.bias + (et >> 6) * nH * 32 + pair * 64 + (et & 63));
                 if (et < 450) stab[et] = __ldg(g.attn_table + pair * 450 + et);
-                asm volatile("bar.sync 7, 512;" ::: "memory");
+                asm volatile("bar.sync 9, 512;" ::: "memory");
             }
             const int nW = (g.H >> 3) * (g.W >> 3), wpr = g.W >> 3;
             constexpr int SC = BN / 16;
-            int it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int bar_id = 5 + grp * 2 + window;
+            for (int tile = blockIdx.x + grp * gridDim.x, it = grp; tile < total_tiles; tile += 2 * gridDim.x, it += 2) {
                 const int mt = tile / p.n_tiles;
-                const int as = it & 1, aphase = (it >> 1) & 1;
+                const int as = grp, aphase = (it >> 1) & 1;
                 const int wg = mt * 2 + window;                         // global window index
-                const bool wvalid = wg * 64 < g.M;
+                const bool wvalid = (long long)wg * 64 < g.M;
                 const int win = wg % nW;
                 const int wi = win / wpr, wj = win - wi * wpr;
                 const bool masked = g.attn_shift > 0 && (wi == (g.H >> 3) - 1 || wj == wpr - 1);
-                if (tid_w < 64) slab[window * 64 + tid_w] = masked ? win_pos_label(win, tid_w, g.H, g.W, g.attn_shift) : 0;
+                if (tid_w < 64) slab[tid_w] = masked ? win_pos_label(win, tid_w, g.H, g.W, g.attn_shift) : 0;
                 mbar_wait(tfull_bar(as), aphase);
                 tc_fence_after();
                 {
                     const uint32_t t_row = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN);
                     unsigned char* srow = stg_all + (size_t)(lg * 32 + lane) * Cfg::SROW16;
 #pragma unroll
-                    for (int jj = 0; jj < SC / 4; ++jj) {
-                        const int c = q + 4 * jj;
+                    for (int jj = 0; jj < SC / 2; ++jj) {
+                        const int c = hq + 2 * jj;
                         uint32_t v[16];
                         asm volatile(
                             "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -261,15 +264,18 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty_bar(as));
-                asm volatile("bar.sync %0, 256;" ::"r"(5 + window) : "memory");   // window staged (+ labels)
-                if (wvalid)
-                    attn_unit<32>(wrows_s, wrows, Cfg::SROW16, strip, head_l * 32, 64 + head_l * 32, 128 + head_l * 32,
-                                  stab + head_l * 225, slab + window * 64, masked, g.attn_scale, lane);
-                asm volatile("bar.sync %0, 256;" ::"r"(5 + window) : "memory");   // every unit wrote its O
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");       // window staged (+ labels)
+                if (wvalid) {
+#pragma unroll 1
+                    for (int hl = 0; hl < 2; ++hl)
+                        attn_unit<32>(wrows_s, wrows, Cfg::SROW16, strip, hl * 32, 64 + hl * 32, 128 + hl * 32,
+                                      stab + hl * 225, slab, masked, g.attn_scale, lane);
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");       // every unit wrote its O
                 // attention output of the window: 64 rows x (2 heads x 32) = the first 128 B of each staged row
 #pragma unroll
-                for (int jj = 0; jj < 2; ++jj) {
-                    const int idx = tid_w + 256 * jj;
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int idx = tid_w + 128 * jj;
                     const int row = idx >> 3, col = idx & 7;
                     const long long m = (long long)wg * 64 + row;
                     if (m < g.M) {
@@ -277,7 +283,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         *reinterpret_cast<uint4*>(g.out16 + (size_t)m * g.ld16 + pair * 64 + col * 8) = val;
                     }
                 }
-                asm volatile("bar.sync %0, 256;" ::"r"(5 + window) : "memory");   // staging free for the next tile
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");       // staging free for this group's next tile
             }
         } else if constexpr (Cfg::kStage16) {
             // ---- 16-bit outputs: bias + activation + pack in phase T (thread = row), then a pure
