@@ -677,6 +677,13 @@ static int dispatch_tc5(const srk_gemm_args* a, const CUtensorMap& ma, const CUt
     return launch_tc5<BN, E_GENERIC, 0, 0>(ma, mb, p, st);
 }
 
+int qkv_attention_tcgen05(const srk_gemm_args* a, cudaStream_t st);      // attn_tc5.cu
+static bool attn_tc5_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SRK_ATTN_TC5"); v = e ? atoi(e) != 0 : 1; }
+    return v != 0;
+}
+
 int gemm_tcgen05(const srk_gemm_args* a, cudaStream_t st) {
     SRK_REQUIRE(a->N % 64 == 0, "gemm(tcgen05): N=%d must be a multiple of 64", a->N);
     SRK_REQUIRE(((uintptr_t)a->A & 15) == 0 && ((uintptr_t)a->Wt & 15) == 0, "gemm(tcgen05): operands must be 16 B aligned");
@@ -696,6 +703,7 @@ int gemm_tcgen05(const srk_gemm_args* a, cudaStream_t st) {
     p.n_tiles = a->N / BN;
     p.nkb = a->K / TBK;
     const bool attn = a->attn_table != nullptr;
+    if (attn && a->K == 192 && attn_tc5_enabled()) return qkv_attention_tcgen05(a, st);
     if (attn) SRK_REQUIRE(BN == 192 && a->N == p.n_tiles * 192, "gemm(tcgen05): fused attention needs N == pairs * 192");
     CUtensorMap ma, mb;
     if (a->a_mode == SRK_A_CONV3X3) {

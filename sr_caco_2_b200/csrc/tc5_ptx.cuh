@@ -29,6 +29,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "DONE:\n"
         "}\n" ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");
 }
+// pure spin (no suspend-time hint): for waits on the critical dependency chain of a tile
+__device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"

@@ -328,7 +328,7 @@ def test_gemm_conv3x3_pixelshuffle_and_image_epilogues(L, engine):
     assert float((img.cpu() - exp).abs().max()) < 3e-3 * max(1.0, float(exp.abs().max()))
 
 
-@pytest.mark.parametrize("geom", [(180, 6, 24, 16, 3), (128, 4, 16, 16, 1)])
+@pytest.mark.parametrize("geom", [(180, 6, 24, 16, 3), (128, 4, 16, 16, 1), (180, 6, 64, 64, 9), (180, 6, 40, 24, 5)])
 def test_fused_qkv_attention_equals_unfused(L, geom):
     """E_ATTN epilogue (qkv GEMM + window attention in one tcgen05 kernel) vs srk_gemm + srk_window_attention."""
     if "tcgen05" not in ENGINES:
@@ -359,7 +359,13 @@ def test_fused_qkv_attention_equals_unfused(L, geom):
         _gemm(L, A=Ad, a_mode=L.A_ROWS, lda=Cp, nB=B, H=H, W=W, Wt=wd, M=M, N=nq, K=Cp, dtype=L.SRK_BF16, bias=bd,
               out16=got, ld16=nh * 32, out16_dtype=L.SRK_BF16, attn_table=td, attn_heads=nh, attn_scale=d ** -0.5,
               attn_shift=shift)
-        assert torch.equal(got, ref), float((got.float() - ref.float()).abs().max())
+        # K = 192 runs the all-tcgen05 kernel (attn_tc5.cu): other summation order, P rounded to bf16
+        # before normalisation -> compare at bf16 resolution; other widths share the mma.sync unit bit for bit
+        err = float((got.float() - ref.float()).abs().max())
+        if Cp == 192 and os.environ.get("SRK_ATTN_TC5", "1") != "0":
+            assert err <= 0.02 * float(ref.float().abs().max()) + 1e-3, err
+        else:
+            assert torch.equal(got, ref), err
 
 
 @pytest.mark.parametrize("dims", [(180, 192, 360, 384), (60, 64, 120, 128), (128, 128, 256, 256)])
