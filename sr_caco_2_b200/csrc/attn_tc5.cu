@@ -1,21 +1,25 @@
 // Fused qkv projection + 8x8-window attention with ALL matrix products on tcgen05 (TMEM):
 //   per 128-token tile (2 windows) and head pair:   QKV = A . Wpair^T        (M128 N192 K192)
-//                                                   S_h = Q'_h K'_h^T        (M128 N64  K64, per head)
-//                                                   O_h = P_h [V_w0 | V_w1]  (M128 N32  K64, per head and window)
-// The two windows of a tile share the 128-row MMAs.  For S the window selection is folded into the
-// K dimension: row r of Q'_h holds q(r) in the 32 columns of ITS window and zeros in the other 32,
-// row j of K'_h holds [k_w0(j) | k_w1(j)], so S_h[r][j] = q(r) . k_{window(r)}(j) with only 64
-// accumulator columns.  For P V the product is issued once per window into separate accumulator
-// columns and each row reads the 32 columns of its own window.
+//                                                   S_h = Q'_h K'_h^T        (M128 N64  K64,  per head)
+//                                                   O_h = P'_h [V_w0; V_w1]  (M128 N32  K128, per head, A from TMEM)
+// The two windows of a tile share the 128-row MMAs; the window selection is folded into the K
+// dimension of both products.  Row r of Q'_h holds q(r) in the 32 columns of ITS window and zeros in
+// the other 32, row j of K'_h holds [k_w0(j) | k_w1(j)], so S_h[r][j] = q(r) . k_{window(r)}(j) with
+// only 64 accumulator columns.  Row r of P'_h holds its 64 probabilities in the key range of its
+// window and zeros in the other window's range, and the K = 128 keys of [V_w0; V_w1] are contracted
+// in one chain.  P'_h is written by the softmax threads straight into the TMEM columns of S_h
+// (tcgen05.st) and read from there as the A operand, so P never touches shared memory.
 //
 //   warp 0       TMA producer (A tiles; the head pair's 192 weight rows are loaded once and stay resident)
-//   warp 1       tcgen05.mma issuer, software pipelined:  S(t), QKV(t+1), PV(t-1)
-//   warps 2..9   "T" warps: drain the QKV accumulator of tile t (+ bias, bf16) into the UMMA operand
-//                tiles of set t&1 (Q', K': 128B-swizzled K-major rows; V: transposed, keys along K);
+//   warp 1       tcgen05.mma issuer of the projection (free running, one accumulator)
+//   warp 2       tcgen05.mma issuer of S(t) and PV(t-1)
+//   warps 3..10  "T" warps: drain the QKV accumulator of tile t (+ bias, bf16) into the UMMA operand
+//                tiles (Q', K': 128B-swizzled K-major rows; V: transposed, keys along K, double buffered);
 //                they also read the finished O_h rows of tile t-2 out of TMEM (* 1/sum, bf16, 64 B store)
-//   warps 10..17 softmax warps (thread = row, head = warp group): tcgen05.ld S_h row, * scale + rel-pos
-//                bias + shift mask, exp2, write P_h (bf16 operand tile, over the consumed Q'_h) and 1/sum
-// Two tiles are in flight (operand-tile sets and S/O accumulators are double buffered), so every
+//   warps 11..26 softmax warps, two per (TMEM lane group, head): thread = (row, 32 of its 64 keys):
+//                tcgen05.ld S_h, * scale + rel-pos bias + shift mask, row max exchanged with the partner
+//                warp, exp2, tcgen05.st P'_h (bf16) over S_h, partial row sum to shared memory
+// Two tiles are in flight (S/P' accumulators and V^T are double buffered), so every
 // MMA -> mbarrier -> warp hop of one tile is covered by work on the other.  q, k, v, S and P never
 // leave the SM.  Restates WindowAttention.forward (dlib/models/network_swinir.py:148-176) and
 // calculate_mask (:260-285).
@@ -24,15 +28,18 @@
 
 namespace srk {
 
-constexpr int QA_THREADS = 64 + 32 * 16;
-constexpr int QA_ASTAGES = 2;
+__device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define QA_TR(role, t, ev) do { if (p.trace && blockIdx.x == 0 && lane == 0 && (t) < 16) p.trace[((role) * 16 + (t)) * 8 + (ev)] = gtime(); } while (0)
+
+constexpr int QA_THREADS = 96 + 32 * 24;        // TMA, 2 MMA issuers, 8 T warps, 16 softmax warps
+constexpr int QA_ASTAGES = 4;
 constexpr int QA_B_BYTES = 3 * 24576;                  // resident weight tile: 3 k-blocks x (192 rows x 128 B)
 constexpr int QA_A_OFF = QA_B_BYTES;
-constexpr int QA_QP_OFF = QA_A_OFF + QA_ASTAGES * 16384;   // [set][head] Q'_h [128][64], later P_h [128][64]
-constexpr int QA_K_OFF = QA_QP_OFF + 2 * 32768;            // [head] K'_h [64][64]
+constexpr int QA_Q_OFF = QA_A_OFF + QA_ASTAGES * 16384;    // [head] Q'_h [128][64]
+constexpr int QA_K_OFF = QA_Q_OFF + 32768;                 // [head] K'_h [64][64]
 constexpr int QA_VT_OFF = QA_K_OFF + 16384;                // [set][window] V^T [64 d-rows (2 heads x 32)][64 keys]
 constexpr int QA_BAR_OFF = QA_VT_OFF + 2 * 16384;
-constexpr int QA_AUX = 6144;                               // barriers, bias, tables, labels, 1/sum
+constexpr int QA_AUX = 9728;                               // barriers, bias, tables, labels, max exchange, row sums
 constexpr size_t QA_SMEM = (size_t)QA_BAR_OFF + QA_AUX + 1024;
 static_assert(QA_SMEM <= 232448, "shared memory plan exceeds the 227 KB per-CTA limit");
 
@@ -41,6 +48,7 @@ struct QaP {
     float scale;
     const float* bias; const float* table;
     uint16_t* out; int ldo;
+    long long* trace;          // SRK_QA_TRACE: [role 4][tile 16][event 8] globaltimer stamps of CTA 0
 };
 
 __global__ void __launch_bounds__(QA_THREADS, 1)
@@ -49,22 +57,24 @@ qkv_attn_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const uint32_t raw = smem_u32(qa_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     unsigned char* sm = qa_raw + (base - raw);
-    const uint32_t sB = base, sA = base + QA_A_OFF, sQP = base + QA_QP_OFF, sK = base + QA_K_OFF,
+    const uint32_t sB = base, sA = base + QA_A_OFF, sQ = base + QA_Q_OFF, sK = base + QA_K_OFF,
                    sVT = base + QA_VT_OFF, bars = base + QA_BAR_OFF;
     const uint32_t bfull = bars;
     auto a_full = [&](int s) { return bars + 8 + 8u * s; };
-    auto a_empty = [&](int s) { return bars + 24 + 8u * s; };
-    const uint32_t qkv_full = bars + 40, qkv_empty = bars + 48;
-    auto stg_full = [&](int s) { return bars + 56 + 8u * s; };            // T warps -> MMA : operand set s written
-    auto s_full = [&](int s) { return bars + 72 + 8u * s; };              // MMA -> softmax : S_0, S_1 of set s
-    auto p_full = [&](int s, int h) { return bars + 88 + 8u * (2 * s + h); };   // softmax -> MMA : P_h of set s
-    auto o_full = [&](int s, int h) { return bars + 120 + 8u * (2 * s + h); };  // MMA -> softmax / T warps
-    auto o_empty = [&](int s) { return bars + 152 + 8u * s; };            // softmax -> MMA : accumulators of set s drained
-    const uint32_t tmem_slot = bars + 176;
+    auto a_empty = [&](int s) { return bars + 40 + 8u * s; };
+    const uint32_t qkv_full = bars + 72, qkv_empty = bars + 80;
+    auto stg_full = [&](int s) { return bars + 88 + 8u * s; };            // T warps -> MMA : Q', K', V^T[s] written
+    auto s_full = [&](int s) { return bars + 104 + 8u * s; };             // MMA -> softmax / T warps : S_0, S_1 of set s
+    auto p_full = [&](int s, int h) { return bars + 120 + 8u * (2 * s + h); };   // softmax -> MMA : P'_h of set s in TMEM
+    auto o_full = [&](int h) { return bars + 152 + 8u * h; };             // MMA -> T warps : O_h
+    auto o_empty = [&](int h) { return bars + 168 + 8u * h; };            // T warps -> MMA : O_h read out
+    const uint32_t tmem_slot = bars + 184;
+    auto vt_free = [&](int s) { return bars + 192 + 8u * s; };            // MMA -> T warps : P V chains of set s retired
     float* sbias = reinterpret_cast<float*>(sm + QA_BAR_OFF + 256);     // [192] local column order
     float* stab = sbias + 192;                                          // [2 heads][225], pre-multiplied by log2(e)
-    int* slab = reinterpret_cast<int*>(stab + 450);                     // [2 sets][2 windows][64]
-    float* sinv = reinterpret_cast<float*>(slab + 256);                 // [2 sets][2 heads][128] 1 / softmax denominator
+    unsigned char* slab = reinterpret_cast<unsigned char*>(stab + 450); // [2 sets][2 windows][64] shift-mask region labels
+    float* smax = reinterpret_cast<float*>(slab + 256);                 // [8 warp pairs][2 halves][32] row-max exchange
+    float* ssum = smax + 512;                                           // [2 sets][2 heads][2 halves][128] partial row sums
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pair = blockIdx.x % p.n_pairs;
@@ -77,8 +87,9 @@ qkv_attn_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         for (int s = 0; s < QA_ASTAGES; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
         mbar_init(qkv_full, 1); mbar_init(qkv_empty, 8);
         for (int s = 0; s < 2; ++s) {
-            mbar_init(stg_full(s), 8); mbar_init(s_full(s), 1); mbar_init(o_empty(s), 8);
-            for (int h = 0; h < 2; ++h) { mbar_init(p_full(s, h), 4); mbar_init(o_full(s, h), 1); }
+            mbar_init(stg_full(s), 8); mbar_init(s_full(s), 1); mbar_init(vt_free(s), 1);
+            mbar_init(o_full(s), 1); mbar_init(o_empty(s), 8);
+            for (int h = 0; h < 2; ++h) mbar_init(p_full(s, h), 8);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -93,9 +104,10 @@ qkv_attn_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sm + QA_BAR_OFF + 176);
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sm + QA_BAR_OFF + 184);
     const uint32_t tQKV = tmem_base;
-    auto tS = [&](int s, int h) { return tmem_base + 192u + 128u * s + 64u * h; };   // S_h, later O_h (2 windows x 32)
+    auto tSP = [&](int s, int h) { return tmem_base + 192u + 128u * s + 64u * h; };   // S_h fp32, later P'_h bf16 (128 keys)
+    auto tO = [&](int h) { return tmem_base + 448u + 32u * h; };
 
     if (warp == 0) {
         // ======================================= TMA producer =======================================
@@ -116,15 +128,17 @@ qkv_attn_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
         }
     } else if (warp == 1) {
-        // ======================================= MMA issuer =======================================
+        // ======================================= projection MMA issuer =======================================
         if (lane == 0 && n_my > 0) {
-            const uint32_t id_qkv = umma_idesc(1, 128, 192), id_s = umma_idesc(1, 128, 64), id_o = umma_idesc(1, 128, 32);
+            const uint32_t id_qkv = umma_idesc(1, 128, 192);
             int stage = 0, phase = 0;
             mbar_wait(bfull, 0);
             tc_fence_after();
-            auto issue_qkv = [&](int t) {                       // needs the accumulator drained by the T warps (tile t-1)
-                mbar_wait(qkv_empty, (t & 1) ^ 1);
+            for (int t = 0; t < n_my; ++t) {
+                QA_TR(0, t, 0);
+                mbar_wait(qkv_empty, (t & 1) ^ 1);              // accumulator drained by the T warps (tile t-1)
                 tc_fence_after();
+                QA_TR(0, t, 1);
                 for (int kb = 0; kb < 3; ++kb) {
                     mbar_wait(a_full(stage), phase);
                     tc_fence_after();
@@ -136,97 +150,89 @@ qkv_attn_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     if (++stage == QA_ASTAGES) { stage = 0; phase ^= 1; }
                 }
                 tc_commit(qkv_full);
-            };
+                QA_TR(0, t, 2);
+            }
+        }
+    } else if (warp == 2) {
+        // ======================================= attention MMA issuer =======================================
+        if (lane == 0 && n_my > 0) {
+            const uint32_t id_s = umma_idesc(1, 128, 64), id_o = umma_idesc(1, 128, 32);
             auto issue_s = [&](int t) {                         // S_h = Q'_h K'_h^T, K = 64 = 4 x UMMA_K
-                const int s = t & 1, ph = (t >> 1) & 1;
-                mbar_wait(stg_full(s), ph);
-                mbar_wait(o_empty(s), ph ^ 1);                  // O of tile t-2 has been read out of these columns
+                const int s = t & 1;
+                QA_TR(1, t, 0);
+                mbar_wait(stg_full(s), (t >> 1) & 1);
                 tc_fence_after();
+                QA_TR(1, t, 1);
+                // the columns of set s held P'(t-2): its P V chain was issued by this thread before, in order
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const uint64_t dq = umma_desc_sw128(sQP + s * 32768 + h * 16384), dk = umma_desc_sw128(sK + h * 8192);
+                    const uint64_t dq = umma_desc_sw128(sQ + h * 16384), dk = umma_desc_sw128(sK + h * 8192);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        tc_mma_f16(tS(s, h), dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), id_s, k != 0 ? 1u : 0u);
+                        tc_mma_f16(tSP(s, h), dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), id_s, k != 0 ? 1u : 0u);
                 }
                 tc_commit(s_full(s));
             };
-            auto issue_pv = [&](int t) {                        // O_h[:, 32w..] = P_h V_w, K = 64 keys
-                const int s = t & 1, ph = (t >> 1) & 1;
+            auto issue_pv = [&](int t) {                        // O_h = P'_h [V_w0; V_w1], K = 128 keys, A from TMEM
+                const int s = t & 1;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    mbar_wait(p_full(s, h), ph);
+                    if (h == 0) QA_TR(1, t, 2);
+                    mbar_wait(p_full(s, h), (t >> 1) & 1);
+                    QA_TR(1, t, 3 + 2 * h);
+                    mbar_wait(o_empty(h), (t & 1) ^ 1);         // O_h of tile t-1 has been read out
                     tc_fence_after();
-                    const uint64_t dp = umma_desc_sw128(sQP + s * 32768 + h * 16384);
+                    QA_TR(1, t, 4 + 2 * h);
 #pragma unroll
                     for (int w = 0; w < 2; ++w) {
                         const uint64_t dv = umma_desc_sw128(sVT + s * 16384 + w * 8192 + h * 4096);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            tc_mma_f16(tS(s, h) + 32u * w, dp + (uint64_t)(2 * k), dv + (uint64_t)(2 * k), id_o, k != 0 ? 1u : 0u);
+                            tc_mma_f16_ts(tO(h), tSP(s, h) + (uint32_t)(w * 32 + k * 8), dv + (uint64_t)(2 * k), id_o,
+                                          (w | k) != 0 ? 1u : 0u);
                     }
-                    tc_commit(o_full(s, h));
+                    tc_commit(o_full(h));
                 }
+                tc_commit(vt_free(s));
             };
-            issue_qkv(0);
             for (int t = 0; t < n_my; ++t) {
                 issue_s(t);
-                if (t + 1 < n_my) issue_qkv(t + 1);
                 if (t > 0) issue_pv(t - 1);
             }
             issue_pv(n_my - 1);
         }
-    } else if (warp < 10) {
+    } else if (warp < 11) {
         // ======================================= T warps =======================================
-        const int lg = warp & 3, hq = (warp - 2) >> 2;           // TMEM lane group, half (0/1) = head of the output job
+        const int lg = warp & 3, hq = (warp - 3) >> 2;           // TMEM lane group, half (0/1) = head of the output job
         const int r = lg * 32 + lane;                            // tile row (= TMEM lane) of this thread
         const int wdw = r >> 6, j64 = r & 63;
         const int nW = (p.H >> 3) * (p.W >> 3), wpr = p.W >> 3;
         const int kc = j64 >> 3;
-        auto load_o = [&](int t, uint32_t (&ov)[32], float& inv) {      // O_hq row of tile t -> registers
-            const int s = t & 1;
-            mbar_wait(o_full(s, 0), (t >> 1) & 1);
-            mbar_wait(o_full(s, 1), (t >> 1) & 1);
-            tc_fence_after();
-            tc_ld32(tS(s, hq) + ((uint32_t)(lg * 32) << 16) + (uint32_t)(wdw * 32), ov);
-            inv = sinv[(s * 2 + hq) * 128 + r];
-            tc_fence_before();
-        };
-        auto store_o = [&](int mtile, const uint32_t (&ov)[32], float inv) {
-            const long long m = (long long)mtile * 128 + r;
-            if (m < p.M) {
-                uint16_t* dst = p.out + (size_t)m * p.ldo + pair * 64 + hq * 32;
-#pragma unroll
-                for (int j = 0; j < 32; j += 8)
-                    *reinterpret_cast<uint4*>(dst + j) = make_uint4(
-                        packf<SRK_BF16>(__uint_as_float(ov[j]) * inv, __uint_as_float(ov[j + 1]) * inv),
-                        packf<SRK_BF16>(__uint_as_float(ov[j + 2]) * inv, __uint_as_float(ov[j + 3]) * inv),
-                        packf<SRK_BF16>(__uint_as_float(ov[j + 4]) * inv, __uint_as_float(ov[j + 5]) * inv),
-                        packf<SRK_BF16>(__uint_as_float(ov[j + 6]) * inv, __uint_as_float(ov[j + 7]) * inv));
-            }
-        };
         int mt = first_mt;
         for (int t = 0; t < n_my; ++t, mt += mt_step) {
             const int s = t & 1;
-            // ---- 1. drain the QKV accumulator: k -> K' (shared by both sets: free once S(t-1) retired),
-            //         q and v stay packed in registers until set s is free
+            // ---- A. drain the QKV accumulator.  Q' and K' are single buffered: free once S(t-1) has
+            //         retired.  v stays packed in registers until V^T[s] is free.
+            if (warp == 3) QA_TR(2, t, 0);
             mbar_wait(qkv_full, t & 1);
+            if (warp == 3) QA_TR(2, t, 1);
             if (t >= 1) mbar_wait(s_full((t - 1) & 1), ((t - 1) >> 1) & 1);
             tc_fence_after();
-            uint32_t pq[2][8], pv[2][8];
+            if (warp == 3) QA_TR(2, t, 2);
+            uint32_t pv[2][8];
+            const uint32_t tq = tQKV + ((uint32_t)(lg * 32) << 16) + (uint32_t)(hq * 32);
+            uint32_t va[16], vb[16];
+            tc_ld16_nowait(tq, va);
+            tc_wait_ld16(va);
 #pragma unroll
             for (int jj = 0; jj < 6; ++jj) {
                 const int sec = jj >> 1;                         // 0 = q, 1 = k, 2 = v
                 const int cs = hq * 2 + (jj & 1);                // 16-column group inside the section
                 const int c = sec * 4 + cs;                      // 16-column sub-chunk of the accumulator
-                uint32_t v[16];
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                    : "r"(tQKV + ((uint32_t)(lg * 32) << 16) + (uint32_t)(c * 16)));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                uint32_t (&v)[16] = (jj & 1) ? vb : va;
+                uint32_t (&vn)[16] = (jj & 1) ? va : vb;
+                // the next sub-chunk is in flight while this one is converted
+                if (jj < 5) tc_ld16_nowait(tq + (uint32_t)(((jj + 1) >> 1) * 64 + ((jj + 1) & 1) * 16), vn);
                 const float4* bp = reinterpret_cast<const float4*>(sbias + c * 16);
                 uint32_t pk[8];
 #pragma unroll
@@ -235,48 +241,45 @@ qkv_attn_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     pk[2 * j] = packf<SRK_BF16>(__uint_as_float(v[4 * j]) + bb.x, __uint_as_float(v[4 * j + 1]) + bb.y);
                     pk[2 * j + 1] = packf<SRK_BF16>(__uint_as_float(v[4 * j + 2]) + bb.z, __uint_as_float(v[4 * j + 3]) + bb.w);
                 }
-                if (sec == 1) {
+                const int h = cs >> 1, dh = cs & 1;              // head, half of the head dim
+                if (sec == 0) {
+                    // Q'_h row r: this window's 32 columns hold q, the other window's 32 columns are zero
+                    unsigned char* row = sm + QA_Q_OFF + h * 16384 + r * 128;
+                    const int ch = wdw * 4 + dh * 2, cz = (wdw ^ 1) * 4 + dh * 2;
+                    *reinterpret_cast<uint4*>(row + (((ch) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    *reinterpret_cast<uint4*>(row + (((ch + 1) ^ (r & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    *reinterpret_cast<uint4*>(row + (((cz) ^ (r & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+                    *reinterpret_cast<uint4*>(row + (((cz + 1) ^ (r & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+                } else if (sec == 1) {
                     // K'_h row j (key index inside the window): columns 32*window + d
-                    const int h = cs >> 1, dh = cs & 1;
                     unsigned char* row = sm + QA_K_OFF + h * 8192 + j64 * 128;
                     const int ch = wdw * 4 + dh * 2;
                     *reinterpret_cast<uint4*>(row + (((ch) ^ (j64 & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     *reinterpret_cast<uint4*>(row + (((ch + 1) ^ (j64 & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                 } else {
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) { if (sec == 0) pq[jj & 1][e] = pk[e]; else pv[jj & 1][e] = pk[e]; }
+                    for (int e = 0; e < 8; ++e) pv[jj & 1][e] = pk[e];
                 }
+                if (jj < 5) tc_wait_ld16(vn);
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(qkv_empty);
-            // ---- 2. set s was last used by tile t-2: wait for its P V products, pull its O row out of TMEM
-            uint32_t ov[32];
-            float inv = 0.f;
-            if (t >= 2) {
-                load_o(t - 2, ov, inv);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(o_empty(s));
-            }
-            // ---- 3. operand tiles of set s: labels, Q'_h (zero-extended over the other window), V^T
+            if (warp == 3) QA_TR(2, t, 3);
+            // ---- B. V^T[s] was last read by the P V chain of tile t-2: wait for it, pull its O row out of TMEM
+            if (t >= 2) mbar_wait(vt_free(s), ((t - 2) >> 1) & 1);
+            if (warp == 3) QA_TR(2, t, 4);
+            // ---- C. labels and V^T of set s: element (key j, d) -> row d (0..63 = head*32 + d), key column j
             if (hq == 0) {
                 const int win = (mt * 2 + wdw) % nW;
                 const int wi = win / wpr, wj = win - wi * wpr;
                 const bool masked = p.shift > 0 && (wi == (p.H >> 3) - 1 || wj == wpr - 1);
-                slab[(s * 2 + wdw) * 64 + j64] = masked ? win_pos_label(win, j64, p.H, p.W, p.shift) : 0;
+                slab[(s * 2 + wdw) * 64 + j64] = (unsigned char)(masked ? win_pos_label(win, j64, p.H, p.W, p.shift) : 0);
             }
             unsigned char* vt = sm + QA_VT_OFF + s * 16384 + wdw * 8192 + (r & 7) * 2;
 #pragma unroll
             for (int e2 = 0; e2 < 2; ++e2) {
                 const int cs = hq * 2 + e2;
-                const int h = cs >> 1, dh = cs & 1;
-                unsigned char* row = sm + QA_QP_OFF + s * 32768 + h * 16384 + r * 128;
-                const int ch = wdw * 4 + dh * 2, cz = (wdw ^ 1) * 4 + dh * 2;
-                *reinterpret_cast<uint4*>(row + (((ch) ^ (r & 7)) << 4)) = make_uint4(pq[e2][0], pq[e2][1], pq[e2][2], pq[e2][3]);
-                *reinterpret_cast<uint4*>(row + (((ch + 1) ^ (r & 7)) << 4)) = make_uint4(pq[e2][4], pq[e2][5], pq[e2][6], pq[e2][7]);
-                *reinterpret_cast<uint4*>(row + (((cz) ^ (r & 7)) << 4)) = make_uint4(0, 0, 0, 0);
-                *reinterpret_cast<uint4*>(row + (((cz + 1) ^ (r & 7)) << 4)) = make_uint4(0, 0, 0, 0);
-                // V^T of window wdw: element (key j, d) -> row d (0..63 = head*32 + d), key column j
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const int d = cs * 16 + i;
@@ -287,44 +290,67 @@ qkv_attn_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(stg_full(s));
-            // ---- 4. off the dependency chain: scale and store the output of tile t-2
-            if (t >= 2) store_o(mt - 2 * mt_step, ov, inv);
-        }
-        for (int t = n_my >= 2 ? n_my - 2 : 0; t < n_my; ++t) {
-            uint32_t ov[32];
-            float inv;
-            load_o(t, ov, inv);
-            store_o(first_mt + t * mt_step, ov, inv);
+            if (warp == 3) QA_TR(2, t, 5);
         }
     } else {
         // ======================================= softmax warps =======================================
-        const int lg = warp & 3, h = (warp - 10) >> 2;           // TMEM lane group, head
+        // two warps per (TMEM lane group, head): each thread owns one row and 32 of its 64 keys; the
+        // row maximum is exchanged through shared memory with a 64-thread named barrier
+        const int idx = warp - 11;
+        const int lg = warp & 3, h = (idx >> 2) & 1, half = idx >> 3;
         const int r = lg * 32 + lane;
         const int wdw = r >> 6, i = r & 63;                      // window and query position of the row
         const int nW = (p.H >> 3) * (p.W >> 3), wpr = p.W >> 3;
         const float sc2 = p.scale * LOG2E;
-        const float* bp = stab + h * 225 + ((i >> 3) + 7) * 15 + ((i & 7) + 7);   // bias(i, j) = bp[-15*(j>>3) - (j&7)]
+        // bias(i, j) = bp[-15*(j>>3) - (j&7)], this thread's keys are j = 32*half + jj
+        const float* bp = stab + h * 225 + ((i >> 3) + 7 - 4 * half) * 15 + ((i & 7) + 7);
+        const int bar_id = 1 + lg * 2 + h;
+        float* mine = smax + ((lg * 2 + h) * 2 + half) * 32 + lane;
+        const float* theirs = smax + ((lg * 2 + h) * 2 + (half ^ 1)) * 32 + lane;
+        auto output = [&](int t, int mtile) {                  // O_h row of tile t, this thread's 16 of the 32 columns
+            mbar_wait(o_full(h), t & 1);
+            tc_fence_after();
+            uint32_t ov[16];
+            tc_ld16_nowait(tO(h) + ((uint32_t)(lg * 32) << 16) + (uint32_t)(half * 16), ov);
+            tc_wait_ld16(ov);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(o_empty(h));
+            const float* ps = ssum + (((t & 1) * 2 + h) * 2) * 128 + r;
+            const float inv = rcp_approx(ps[0] + ps[128]);
+            const long long m = (long long)mtile * 128 + r;
+            if (m < p.M) {
+                uint16_t* dst = p.out + (size_t)m * p.ldo + pair * 64 + h * 32 + half * 16;
+#pragma unroll
+                for (int j = 0; j < 16; j += 8)
+                    *reinterpret_cast<uint4*>(dst + j) = make_uint4(
+                        packf<SRK_BF16>(__uint_as_float(ov[j]) * inv, __uint_as_float(ov[j + 1]) * inv),
+                        packf<SRK_BF16>(__uint_as_float(ov[j + 2]) * inv, __uint_as_float(ov[j + 3]) * inv),
+                        packf<SRK_BF16>(__uint_as_float(ov[j + 4]) * inv, __uint_as_float(ov[j + 5]) * inv),
+                        packf<SRK_BF16>(__uint_as_float(ov[j + 6]) * inv, __uint_as_float(ov[j + 7]) * inv));
+            }
+        };
         int mt = first_mt;
         for (int t = 0; t < n_my; ++t, mt += mt_step) {
             const int s = t & 1;
             const int win = (mt * 2 + wdw) % nW;
             const int wi = win / wpr, wj = win - wi * wpr;
             const bool masked = p.shift > 0 && (wi == (p.H >> 3) - 1 || wj == wpr - 1);
+            const uint32_t trow = tSP(s, h) + ((uint32_t)(lg * 32) << 16);
+            if (warp == 11) QA_TR(3, t, 0);
             mbar_wait(s_full(s), (t >> 1) & 1);
             tc_fence_after();
-            float sv[64];
+            if (warp == 11) QA_TR(3, t, 1);
+            float sv[32];
             {
                 uint32_t v[32];
-                tc_ld32(tS(s, h) + ((uint32_t)(lg * 32) << 16), v);
+                tc_ld32(trow + (uint32_t)(half * 32), v);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) sv[j] = __uint_as_float(v[j]);
-                tc_ld32(tS(s, h) + ((uint32_t)(lg * 32) << 16) + 32u, v);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) sv[32 + j] = __uint_as_float(v[j]);
             }
             // scores in the log2 domain: (s * scale + bias) * log2(e); 8 bias loads in flight per batch
 #pragma unroll
-            for (int jh = 0; jh < 8; ++jh) {
+            for (int jh = 0; jh < 4; ++jh) {
                 float b[8];
 #pragma unroll
                 for (int jw = 0; jw < 8; ++jw) b[jw] = bp[-15 * jh - jw];
@@ -332,37 +358,47 @@ qkv_attn_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 for (int jw = 0; jw < 8; ++jw) sv[jh * 8 + jw] = fmaf(sv[jh * 8 + jw], sc2, b[jw]);
             }
             if (masked) {
-                const int* lw = slab + (s * 2 + wdw) * 64;
-                const int li = lw[i];
+                const unsigned char* lw = slab + (s * 2 + wdw) * 64;
+                const unsigned char li = lw[i];
 #pragma unroll
-                for (int j = 0; j < 64; ++j) if (lw[j] != li) sv[j] += -100.f * LOG2E;
+                for (int j = 0; j < 32; ++j) if (lw[half * 32 + j] != li) sv[j] += -100.f * LOG2E;
             }
             float mx0 = -3.0e38f, mx1 = -3.0e38f, mx2 = -3.0e38f, mx3 = -3.0e38f;
 #pragma unroll
-            for (int j = 0; j < 64; j += 4) {
+            for (int j = 0; j < 32; j += 4) {
                 mx0 = fmaxf(mx0, sv[j]); mx1 = fmaxf(mx1, sv[j + 1]); mx2 = fmaxf(mx2, sv[j + 2]); mx3 = fmaxf(mx3, sv[j + 3]);
             }
-            const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+            float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");     // partner has read the previous tile's maximum
+            *mine = mx;
+            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+            if (warp == 11) QA_TR(3, t, 2);
+            mx = fmaxf(mx, *theirs);
             float sum0 = 0.f, sum1 = 0.f;
-            unsigned char* prow = sm + QA_QP_OFF + s * 32768 + h * 16384 + r * 128;
+            uint32_t pk[16];
 #pragma unroll
-            for (int ch = 0; ch < 8; ++ch) {
-                uint32_t pk[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float p0 = ex2_approx(sv[ch * 8 + 2 * e] - mx);
-                    const float p1 = ex2_approx(sv[ch * 8 + 2 * e + 1] - mx);
-                    sum0 += p0; sum1 += p1;
-                    pk[e] = packf<SRK_BF16>(p0, p1);
-                }
-                *reinterpret_cast<uint4*>(prow + ((ch ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            for (int e = 0; e < 16; ++e) {
+                const float p0 = ex2_approx(sv[2 * e] - mx);
+                const float p1 = ex2_approx(sv[2 * e + 1] - mx);
+                sum0 += p0; sum1 += p1;
+                pk[e] = packf<SRK_BF16>(p0, p1);
             }
-            sinv[(s * 2 + h) * 128 + r] = rcp_approx(sum0 + sum1);
+            // P'_h row: probabilities in the key range of this row's window, zeros in the other window's range
+            uint32_t zz[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) zz[e] = 0u;
+            tc_st16_nowait(trow + (uint32_t)(wdw * 32 + half * 16), pk);
+            tc_st16_nowait(trow + (uint32_t)((wdw ^ 1) * 32 + half * 16), zz);
+            ssum[((s * 2 + h) * 2 + half) * 128 + r] = sum0 + sum1;
+            tc_wait_st();
             tc_fence_before();
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(p_full(s, h));
+            if (warp == 11) QA_TR(3, t, 3);
+            if (t > 0) output(t - 1, mt - mt_step);
+            if (warp == 11) QA_TR(3, t, 4);             // its P V chain ran under this tile's softmax
         }
+        if (n_my > 0) output(n_my - 1, first_mt + (n_my - 1) * mt_step);
     }
     tc_fence_before();
     __syncthreads();
@@ -400,6 +436,29 @@ int qkv_attention_tcgen05(const srk_gemm_args* a, cudaStream_t st) {
     }
     int grid = (num_sms() / p.n_pairs) * p.n_pairs;
     if (grid > p.m_tiles * p.n_pairs) grid = p.m_tiles * p.n_pairs;
+    static int trace = -1;
+    if (trace < 0) { const char* e = getenv("SRK_QA_TRACE"); trace = e ? atoi(e) : 0; }
+    if (trace > 0) {                                         // debugging aid: per-tile time stamps of CTA 0
+        --trace;
+        long long* d; const size_t nb = 4 * 16 * 8 * sizeof(long long);
+        SRK_CUDA(cudaMalloc(&d, nb)); SRK_CUDA(cudaMemset(d, 0, nb));
+        p.trace = d;
+        qkv_attn_tc5_kernel<<<grid, QA_THREADS, QA_SMEM, st>>>(ma, mb, p);
+        SRK_CUDA(cudaDeviceSynchronize());
+        static long long hbuf[4 * 16 * 8];
+        SRK_CUDA(cudaMemcpy(hbuf, d, nb, cudaMemcpyDeviceToHost)); cudaFree(d);
+        if (trace == 0) {
+            const long long t0 = hbuf[0];
+            const char* names[4] = {"qkvmma", "attmma", "Twarp ", "smax  "};
+            for (int t = 0; t < 16; ++t)
+                for (int r = 0; r < 4; ++r) {
+                    fprintf(stderr, "tile %2d %s", t, names[r]);
+                    for (int e = 0; e < 8; ++e) { long long v = hbuf[(r * 16 + t) * 8 + e]; fprintf(stderr, " %7lld", v ? v - t0 : -1); }
+                    fprintf(stderr, "\n");
+                }
+        }
+        return 0;
+    }
     qkv_attn_tc5_kernel<<<grid, QA_THREADS, QA_SMEM, st>>>(ma, mb, p);
     SRK_LAUNCH_CHECK("qkv_attn_tc5_kernel");
     return 0;

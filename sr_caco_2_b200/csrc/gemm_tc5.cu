@@ -678,10 +678,13 @@ static int dispatch_tc5(const srk_gemm_args* a, const CUtensorMap& ma, const CUt
 }
 
 int qkv_attention_tcgen05(const srk_gemm_args* a, cudaStream_t st);      // attn_tc5.cu
+// SRK_ATTN_TC5=1 routes the fused qkv + attention call to the all-tcgen05 kernel of attn_tc5.cu
+// (S and P V on tensor memory).  It is parity-tested but measured slower than the mma.sync attention
+// epilogue below (80 vs 67 us at cfg3: it is bound by the 64 B/clk TMEM read port and by per-row
+// softmax latency), so it stays opt-in.  Read per call so that a test can flip it.
 static bool attn_tc5_enabled() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("SRK_ATTN_TC5"); v = e ? atoi(e) != 0 : 1; }
-    return v != 0;
+    const char* e = getenv("SRK_ATTN_TC5");
+    return e && atoi(e) != 0;
 }
 
 int gemm_tcgen05(const srk_gemm_args* a, cudaStream_t st) {

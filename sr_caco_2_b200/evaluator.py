@@ -84,11 +84,26 @@ def make_cuda_step(net, scale: int, swinir_padding: bool, border: Optional[int] 
 
     b = scale if border is None else border      # fast_eval: border = args.scale (:562)
 
+    copy_stream = {}
+
     def step(lr_b: torch.Tensor, hr_b: torch.Tensor) -> torch.Tensor:
         dev = next(net.parameters()).device
+        cur = torch.cuda.current_stream(dev)
         lr_b = lr_b.to(dev, non_blocking=True)
-        hr_b = hr_b.to(dev, non_blocking=True)
-        e = forward_with_padding(net, lr_b, scale, swinir_padding)
+        if hr_b.device != dev:
+            # the target image is 8^2 x larger than the input and only the metrics kernel reads it:
+            # its host->device copy runs on a side stream underneath the network forward
+            if dev not in copy_stream:
+                copy_stream[dev] = torch.cuda.Stream(dev)
+            side = copy_stream[dev]
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                hr_b = hr_b.to(dev, non_blocking=True)
+            hr_b.record_stream(cur)
+            e = forward_with_padding(net, lr_b, scale, swinir_padding)
+            cur.wait_stream(side)
+        else:
+            e = forward_with_padding(net, lr_b, scale, swinir_padding)
         m = UI.compute_metrics(e, hr_b, b, roi_ths, check=check)
         cols = [m[k] for k in METRICS]
         if len(roi_ths):
