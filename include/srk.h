@@ -111,7 +111,9 @@ int srk_metrics_roi(const float* E, const float* H, const float* roi, int B, int
  * + res[r32];  out32[r32] = v;  out16[r16] = cvt(v)
  *   SRK_A_ROWS    : A is (M, lda) 16-bit, K = padded channels
  *   SRK_A_CONV3X3 : A is the (nB, H, W, lda) image, implicit im2col, zero padding 1,
- *                   K = 9 * lda, k = tap * lda + c, tap = ky*3+kx   (nn.Conv2d(.,.,3,1,1))
+ *                   K = 9 * lda, k = tap * lda + c, tap = ky*3+kx   (nn.Conv2d(.,.,3,1,1));
+ *                   conv_k = 5 makes it a 5x5 window (zero padding 2, K = 25 * lda) -- used by
+ *                   the folded reconstruction tail (srk_tail_fold)
  *   Wt : (N, K) 16-bit, K contiguous (nn.Linear weight layout; conv weight repacked)
  *   win_shift >= 0: GEMM row m is a window-major position; res / out32 rows are the token it
  *                   came from (window_reverse + roll back), -1: identity
@@ -137,6 +139,7 @@ typedef struct {
      * attn_table (heads,225), shift mask for cyclic shift attn_shift, softmax, P v) and writes
      * only the attention output to out16 (M, ld16 = attn_heads*32): q, k, v never reach HBM. */
     const float* attn_table; int attn_heads; float attn_scale; int attn_shift;
+    int conv_k;                          /* SRK_A_CONV3X3 window: 0 or 3 -> 3x3, 5 -> 5x5 */
 } srk_gemm_args;
 int srk_gemm(const srk_gemm_args* g, void* stream);
 
@@ -193,6 +196,30 @@ int srk_conv_in_ln(const float* x, int B, int h, int w, int H, int W, float in_s
 int srk_conv_out(const void* a, int lda, int B, int H, int W, int Cin, const void* wgt,
                  float bias, float out_scale, float* y, int Hc, int Wc, void* stream);
 
+/* Folded reconstruction tail.  After the last non-linearity the `pixelshuffle` upsampler is
+ * log2(s) x [Conv3x3(F -> 4F) + PixelShuffle(2)] followed by Conv3x3(F -> 1) (network_swinir.py:
+ * 661-680, 862-868, 960-963; network_nlsn.py Upsampler + tail conv): a LINEAR map from the
+ * F-channel h x w feature image to the s*h x s*w image.  Composed offline (packing.fold_tail) it
+ * is ONE 5x5 convolution F -> s*s, output n = i*s + j of feature pixel (y, x) being image pixel
+ * (s*y + i, s*x + j): 30x fewer FLOPs at s = 8 and none of the 4F-channel intermediates.
+ * The zero padding of the intermediate images makes the composed kernel differ on the outermost
+ * ring of feature pixels only; variant v = 3*vy + vx (vy, vx: 0 = first row / column,
+ * 1 = interior, 2 = last) holds the kernel of those pixels.  All weights and biases are
+ * pre-multiplied by w_scale (a power of two that keeps the products in fp16 range). */
+typedef struct {
+    const void* w;            /* interior kernel (64, 25*64) fp16, row n = i*s + j, k = tap*64 + c; NULL: not folded */
+    const float* b;           /* (64) fp32 */
+    const void* border_w;     /* (9, 64, 25*64) fp16 variant kernels */
+    const float* border_b;    /* (9, 64) fp32 */
+    float w_scale;
+} srk_tail_fold;
+
+/* The ring pass of the folded tail: recomputes the outermost ring of feature pixels of
+ * a: (B,H,W,64) fp16 with their variant kernels and overwrites those pixels of
+ * y: (B,1,Hc,Wc), y = (conv5x5 + bias) * out_scale / w_scale.  H, W >= 3. */
+int srk_tail_border(const void* a, int B, int H, int W, int s, const srk_tail_fold* f,
+                    float out_scale, float* y, int Hc, int Wc, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Network drivers.  Replace SwinIR.forward (dlib/models/network_swinir.py:930-970) and the
  * EDSR-baseline forward assembled from dlib/models/network_nlsn.py:72-128,325-369.
@@ -230,6 +257,7 @@ typedef struct {
     int n_upsample;
     const void* conv_last_w; float conv_last_b;      /* (9,64) fp16 */
     int linear_dtype, conv_dtype;                    /* SRK_BF16 / SRK_FP16 */
+    srk_tail_fold tail_fold;                         /* pixelshuffle only; w == NULL: run the convs one by one */
 } srk_swinir_plan;
 
 size_t srk_swinir_workspace_bytes(const srk_swinir_plan* p, int B, int h, int w);
@@ -245,6 +273,7 @@ typedef struct {
     srk_conv_params tail_up[4]; int n_tail_up;
     const void* tail_w; float tail_b;    /* (9,F) fp16 */
     int conv_dtype;
+    srk_tail_fold tail_fold;             /* w == NULL: run the tail convs one by one */
 } srk_edsr_plan;
 
 size_t srk_edsr_workspace_bytes(const srk_edsr_plan* p, int B, int h, int w);

@@ -18,6 +18,12 @@ for r in rows[hi + 1:]:
     name_of[i] = ((m.group(1) + (m.group(2) or '')) if m else name[:60]).replace('(int)', '')
     v = float(r[idx['Metric Value']].replace(',', '')); unit = r[idx['Metric Unit']]; met = r[idx['Metric Name']]
     per[i][met] = to_us(v, unit) if 'time' in met else to_bytes(v, unit)
+# keep ONE step: from the last launch of the network's first kernel (conv_in_ln / conv_in) to the end
+ids = sorted(per, key=lambda x: int(x))
+firsts = [i for i in ids if name_of[i].startswith("conv_in")]
+if firsts:
+    ids = [i for i in ids if int(i) >= int(firsts[-1])]
+    per = {i: per[i] for i in ids}
 agg = collections.defaultdict(lambda: [0, 0.0, 0.0]); tot = 0.0; totb = 0.0
 for i, d in per.items():
     t = d.get('gpu__time_duration.sum', 0.0); b = d.get('dram__bytes_read.sum', 0.0) + d.get('dram__bytes_write.sum', 0.0)

@@ -29,7 +29,7 @@ class GemmArgs(C.Structure):
                 ("ln_g", fp), ("ln_b", fp), ("ln_C", C.c_int), ("ln_win_shift", C.c_int),
                 ("img", fp), ("img_s", C.c_int), ("img_scale", C.c_float), ("img_hc", C.c_int),
                 ("img_wc", C.c_int), ("attn_table", fp), ("attn_heads", C.c_int),
-                ("attn_scale", C.c_float), ("attn_shift", C.c_int)]
+                ("attn_scale", C.c_float), ("attn_shift", C.c_int), ("conv_k", C.c_int)]
 
 
 class MlpArgs(C.Structure):
@@ -42,6 +42,10 @@ class MlpArgs(C.Structure):
 
 class ConvParams(C.Structure):
     _fields_ = [("w", vp), ("b", fp), ("cin_p", C.c_int), ("n_p", C.c_int)]
+
+
+class TailFold(C.Structure):
+    _fields_ = [("w", vp), ("b", fp), ("border_w", vp), ("border_b", fp), ("w_scale", C.c_float)]
 
 
 class StbParams(C.Structure):
@@ -63,7 +67,7 @@ class SwinIRPlan(C.Structure):
                 ("conv_after_body", ConvParams), ("conv_before_upsample", ConvParams),
                 ("upsample", ConvParams * 4), ("n_upsample", C.c_int),
                 ("conv_last_w", fp), ("conv_last_b", C.c_float),
-                ("linear_dtype", C.c_int), ("conv_dtype", C.c_int)]
+                ("linear_dtype", C.c_int), ("conv_dtype", C.c_int), ("tail_fold", TailFold)]
 
 
 class EDSRPlan(C.Structure):
@@ -72,7 +76,7 @@ class EDSRPlan(C.Structure):
                 ("Fp", C.c_int), ("head_w", fp), ("head_b", fp),
                 ("body", C.POINTER(ConvParams)), ("tail_up", ConvParams * 4),
                 ("n_tail_up", C.c_int), ("tail_w", fp), ("tail_b", C.c_float),
-                ("conv_dtype", C.c_int)]
+                ("conv_dtype", C.c_int), ("tail_fold", TailFold)]
 
 
 # every symbol include/srk.h declares: (restype, argtypes)
@@ -94,6 +98,8 @@ PROTOTYPES = {
                                 C.c_int, fp, C.c_int, C.c_int, C.c_int, vp]),
     "srk_window_attention": (C.c_int, [vp, C.c_int, vp, C.c_int, fp, C.c_int, C.c_int, C.c_int,
                                        C.c_int, C.c_int, C.c_float, C.c_int, vp]),
+    "srk_tail_border": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(TailFold), C.c_float, fp,
+                                  C.c_int, C.c_int, vp]),
     "srk_conv_in": (C.c_int, [fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, fp, fp,
                               C.c_int, fp, C.c_int, vp, C.c_int, C.c_int, vp]),
     "srk_conv_in_ln": (C.c_int, [fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, fp, fp,

@@ -345,6 +345,100 @@ conv_out_mma_kernel(const __half* __restrict__ a, int B, int H, int W, const __h
     }
 }
 
+// ---- ring pass of the folded reconstruction tail (srk_tail_fold) --------------------------------
+// The composed 5x5 kernel of the outermost ring of feature pixels differs from the interior one
+// (zero padding of the intermediate images).  One CTA takes up to 16 ring pixels that share a
+// variant: a stretch of an edge, or one corner.  Their 5x5 x 64-channel neighbourhoods are staged in
+// shared memory as a 16 x 1600 fp16 matrix and multiplied with the variant kernel (64 x 1600, read
+// as mma.sync B fragments straight from global / L2) on the tensor cores.
+constexpr int TB_K = 25 * 64;
+constexpr int TB_STRIDE = (TB_K + 8) * 2;            // bytes per staged pixel row (16 B skew: conflict-free ldmatrix)
+
+__global__ void __launch_bounds__(128)
+tail_border_kernel(const __half* __restrict__ a, int H, int W, int s, const __half* __restrict__ bw,
+                   const float* __restrict__ bb, float out_scale, float* __restrict__ y, int Hc, int Wc) {
+    extern __shared__ __align__(16) unsigned char tb_smem[];
+    const uint32_t sm = (uint32_t)__cvta_generic_to_shared(tb_smem);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int bi = blockIdx.y;
+    // decode the CTA's stretch: segments 0..3 = top / bottom / left / right edge without corners, 4..7 = corners
+    const int cw = (W - 2 + 15) / 16, ch = (H - 2 + 15) / 16;
+    int c = blockIdx.x, seg, first, count;
+    if (c < 2 * cw) { seg = c / cw; first = 1 + (c % cw) * 16; count = min(16, W - 1 - first); }
+    else if (c < 2 * cw + 2 * ch) { c -= 2 * cw; seg = 2 + c / ch; first = 1 + (c % ch) * 16; count = min(16, H - 1 - first); }
+    else { seg = 4 + (c - 2 * cw - 2 * ch); first = 0; count = 1; }
+    auto pixel = [&](int i, int& py, int& px) {
+        switch (seg) {
+            case 0: py = 0; px = first + i; break;
+            case 1: py = H - 1; px = first + i; break;
+            case 2: py = first + i; px = 0; break;
+            case 3: py = first + i; px = W - 1; break;
+            default: py = (seg & 2) ? H - 1 : 0; px = (seg & 1) ? W - 1 : 0; break;
+        }
+    };
+    int vy, vx;
+    switch (seg) {
+        case 0: vy = 0; vx = 1; break;
+        case 1: vy = 2; vx = 1; break;
+        case 2: vy = 1; vx = 0; break;
+        case 3: vy = 1; vx = 2; break;
+        default: vy = (seg & 2) ? 2 : 0; vx = (seg & 1) ? 2 : 0; break;
+    }
+    const int variant = vy * 3 + vx;
+    // stage the neighbourhoods: row i = pixel i of the stretch, column k = tap*64 + c
+    for (int idx = tid; idx < 16 * 25 * 8; idx += 128) {
+        const int i = idx / 200, rem = idx - i * 200, tap = rem >> 3, chunk = rem & 7;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (i < count) {
+            int py, px;
+            pixel(i, py, px);
+            const int yy = py + tap / 5 - 2, xx = px + tap % 5 - 2;
+            if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+                v = *reinterpret_cast<const uint4*>(a + (((size_t)bi * H + yy) * W + xx) * 64 + chunk * 8);
+        }
+        *reinterpret_cast<uint4*>(tb_smem + i * TB_STRIDE + tap * 128 + chunk * 16) = v;
+    }
+    __syncthreads();
+    const int n_out = s * s;
+    if (warp * 16 >= n_out) return;                              // this warp's 16 outputs do not exist for this scale
+    const int g = lane >> 2, t = lane & 3;
+    const __half* wv = bw + (size_t)variant * 64 * TB_K;
+    const uint32_t a_addr = sm + ((lane & 7) + ((lane >> 3) & 1) * 8) * TB_STRIDE + (lane >> 4) * 16;
+    float acc[2][4];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+#pragma unroll 4
+    for (int ks = 0; ks < TB_K / 16; ++ks) {
+        uint32_t af[4];
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                     : "=r"(af[0]), "=r"(af[1]), "=r"(af[2]), "=r"(af[3]) : "r"(a_addr + ks * 32));
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const __half* wp = wv + (size_t)(warp * 16 + j * 8 + g) * TB_K + ks * 16 + 2 * t;
+            const uint32_t b0 = __ldg(reinterpret_cast<const uint32_t*>(wp));
+            const uint32_t b1 = __ldg(reinterpret_cast<const uint32_t*>(wp + 8));
+            asm volatile(
+                "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                : "+f"(acc[j][0]), "+f"(acc[j][1]), "+f"(acc[j][2]), "+f"(acc[j][3])
+                : "r"(af[0]), "r"(af[1]), "r"(af[2]), "r"(af[3]), "r"(b0), "r"(b1));
+        }
+    }
+    // accumulator (row g / g+8, columns 2t, 2t+1 of n-tile j) -> image pixel (s*py + n/s, s*px + n%s)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int i = g + (e >> 1) * 8, n = warp * 16 + j * 8 + 2 * t + (e & 1);
+            if (i < count && n < n_out) {
+                int py, px;
+                pixel(i, py, px);
+                const int oy = py * s + n / s, ox = px * s + n % s;
+                if (oy < Hc && ox < Wc)
+                    y[((size_t)bi * Hc + oy) * Wc + ox] = (acc[j][e] + bb[variant * 64 + n]) * out_scale;
+            }
+        }
+}
+
 }  // namespace srk
 
 using namespace srk;
@@ -429,5 +523,25 @@ extern "C" int srk_conv_out(const void* a, int lda, int B, int H, int W, int Cin
     const int grid = (int)(tiles < 2 * 148 ? tiles : 2 * 148);
     conv_out_mma_kernel<<<grid, CO_THREADS, smem, st>>>((const __half*)a, B, H, W, (const __half*)wgt, bias, out_scale, y, Hc, Wc);
     SRK_LAUNCH_CHECK("conv_out_mma_kernel");
+    return 0;
+}
+
+extern "C" int srk_tail_border(const void* a, int B, int H, int W, int s, const srk_tail_fold* f,
+                               float out_scale, float* y, int Hc, int Wc, void* stream) {
+    SRK_REQUIRE(a && f && f->border_w && f->border_b && y, "tail_border: null pointer");
+    SRK_REQUIRE(B > 0 && H >= 3 && W >= 3 && s >= 1 && s * s <= 64, "tail_border: needs H, W >= 3 and s*s <= 64");
+    SRK_REQUIRE(f->w_scale > 0.f, "tail_border: bad w_scale");
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfScope ps(SRK_PROF_CONV_OUT, stream);
+    const size_t smem = 16 * (size_t)TB_STRIDE;
+    static bool attr = false;
+    if (!attr) {
+        SRK_CUDA(cudaFuncSetAttribute(tail_border_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    dim3 grid(2 * ((W - 2 + 15) / 16) + 2 * ((H - 2 + 15) / 16) + 4, B);
+    tail_border_kernel<<<grid, 128, smem, st>>>((const __half*)a, H, W, s, (const __half*)f->border_w, f->border_b,
+                                                out_scale / f->w_scale, y, Hc, Wc);
+    SRK_LAUNCH_CHECK("tail_border_kernel");
     return 0;
 }

@@ -16,6 +16,7 @@ struct GemmP {
     const float* attn_table; int attn_heads; float attn_scale; int attn_shift;
     int T;            // H*W (tokens per image) when H, W are set, else 0
     int cpb;          // channel blocks of 64 per conv tap (lda / 64)
+    int kt;           // conv window (3 or 5)
 };
 
 inline GemmP make_gemm_params(const srk_gemm_args* g) {
@@ -34,6 +35,7 @@ inline GemmP make_gemm_params(const srk_gemm_args* g) {
     p.attn_table = g->attn_table; p.attn_heads = g->attn_heads; p.attn_scale = g->attn_scale; p.attn_shift = g->attn_shift;
     p.T = (g->H > 0 && g->W > 0) ? g->H * g->W : 0;
     p.cpb = g->lda / 64;
+    p.kt = g->conv_k == 5 ? 5 : 3;
     return p;
 }
 

@@ -61,7 +61,7 @@ gemm_mma_kernel(const GemmP p) {
         if (p.a_mode == SRK_A_CONV3X3) {
             const int tap = kb / p.cpb;
             cb = kb - tap * p.cpb;
-            dy = tap / 3 - 1; dx = tap - (tap / 3) * 3 - 1;
+            dy = tap / p.kt - (p.kt >> 1); dx = tap - (tap / p.kt) * p.kt - (p.kt >> 1);
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -173,7 +173,9 @@ int validate_gemm(const srk_gemm_args* g) {
     SRK_REQUIRE(g->dtype == SRK_BF16 || g->dtype == SRK_FP16, "gemm: bad dtype");
     SRK_REQUIRE(g->lda % 8 == 0, "gemm: lda must be a multiple of 8");
     if (g->a_mode == SRK_A_CONV3X3) {
-        SRK_REQUIRE(g->lda % 64 == 0 && g->K == 9 * g->lda, "gemm: conv needs lda %% 64 == 0 and K == 9*lda");
+        SRK_REQUIRE(g->conv_k == 0 || g->conv_k == 3 || g->conv_k == 5, "gemm: conv_k must be 3 or 5");
+        const int taps = g->conv_k == 5 ? 25 : 9;
+        SRK_REQUIRE(g->lda % 64 == 0 && g->K == taps * g->lda, "gemm: conv needs lda %% 64 == 0 and K == %d*lda", taps);
         SRK_REQUIRE(g->nB > 0 && g->H > 0 && g->W > 0 && g->M == g->nB * g->H * g->W, "gemm: conv needs M == nB*H*W");
     } else {
         SRK_REQUIRE(g->a_mode == SRK_A_ROWS && g->lda >= g->K, "gemm: rows mode needs lda >= K");

@@ -158,7 +158,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     mbar_expect_tx(full_bar(stage), (uint32_t)p.stage_bytes);
                     if (g.a_mode == SRK_A_CONV3X3) {
                         const int tap = kb / g.cpb, cblk = kb - tap * g.cpb;
-                        const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+                        const int dy = tap / g.kt - (g.kt >> 1), dx = tap - (tap / g.kt) * g.kt - (g.kt >> 1);
                         tma_load_4d(sa, &map_a, full_bar(stage), cblk * 64, cx + dx, cy + dy, cb_);
                     } else {
                         tma_load_2d(sa, &map_a, full_bar(stage), kb * TBK, mt * TBM);

@@ -70,6 +70,26 @@ static int check_swin_plan(const srk_swinir_plan* p) {
 
 using namespace srk;
 
+namespace srk {
+// SRK_FOLD_TAIL=0 runs the upsampler convs one by one (the folded tail needs the tcgen05 engine's 5x5 conv)
+bool fold_tail_enabled() {
+    const char* e = getenv("SRK_FOLD_TAIL");
+    return (!e || atoi(e) != 0) && srk_get_engine() == SRK_ENGINE_TCGEN05;
+}
+// the folded reconstruction tail: ONE 5x5 conv F -> s*s written as image pixels + the ring pass
+int run_folded_tail(const srk_tail_fold& f, const void* feat, int B, int H, int W, int s, float out_scale, float* y,
+                    int hc, int wc, void* stream) {
+    srk_gemm_args g{};
+    g.A = feat; g.a_mode = SRK_A_CONV3X3; g.conv_k = 5; g.lda = 64; g.nB = B; g.H = H; g.W = W;
+    g.Wt = f.w; g.M = B * H * W; g.N = 64; g.K = 25 * 64; g.dtype = SRK_FP16;
+    g.bias = f.b; g.act = SRK_ACT_NONE; g.res_scale = 1.f; g.win_shift = -1; g.ln_win_shift = -1;
+    g.img = y; g.img_s = s; g.img_scale = out_scale / f.w_scale; g.img_hc = hc; g.img_wc = wc;
+    if (int rc = srk_gemm(&g, stream)) return rc;
+    return srk_tail_border(feat, B, H, W, s, &f, out_scale, y, hc, wc, stream);
+}
+}  // namespace srk
+
+
 extern "C" size_t srk_swinir_workspace_bytes(const srk_swinir_plan* p, int B, int h, int w) {
     if (!p || B <= 0 || h <= 0 || w <= 0) return 0;
     SwinBufs b;
@@ -259,15 +279,19 @@ extern "C" int srk_swinir_forward(const srk_swinir_plan* p, const float* x, floa
             g.act = SRK_ACT_LRELU; g.out16 = b.U[0]; g.ld16 = 64;
             TRY(srk_gemm(&g, stream));
         }
-        int Hh = H, Ww = W;
-        for (int k = 0; k < p->n_upsample; ++k) {
-            srk_gemm_args g = conv_gemm(b.U[k], 64, Hh, Ww, p->upsample[k]);
-            g.out16 = b.U[k + 1]; g.ld16 = 64; g.out16_mode = SRK_O16_PIXSHUF2;
-            TRY(srk_gemm(&g, stream));
-            Hh *= 2; Ww *= 2;
+        if (p->tail_fold.w && H >= 3 && W >= 3 && fold_tail_enabled()) {
+            TRY(run_folded_tail(p->tail_fold, b.U[0], B, H, W, s_up, out_scale, y, h * s_up, w * s_up, stream));
+        } else {
+            int Hh = H, Ww = W;
+            for (int k = 0; k < p->n_upsample; ++k) {
+                srk_gemm_args g = conv_gemm(b.U[k], 64, Hh, Ww, p->upsample[k]);
+                g.out16 = b.U[k + 1]; g.ld16 = 64; g.out16_mode = SRK_O16_PIXSHUF2;
+                TRY(srk_gemm(&g, stream));
+                Hh *= 2; Ww *= 2;
+            }
+            TRY(srk_conv_out(b.U[p->n_upsample], 64, B, Hh, Ww, 64, p->conv_last_w, p->conv_last_b,
+                             out_scale, y, h * s_up, w * s_up, stream));
         }
-        TRY(srk_conv_out(b.U[p->n_upsample], 64, B, Hh, Ww, 64, p->conv_last_w, p->conv_last_b,
-                         out_scale, y, h * s_up, w * s_up, stream));
     } else {
         srk_gemm_args g = conv_gemm(y1, Cp, H, W, p->upsample[0]);
         g.img = y; g.img_s = s_up; g.img_scale = out_scale; g.img_hc = h * s_up; g.img_wc = w * s_up;
@@ -341,6 +365,8 @@ extern "C" int srk_edsr_forward(const srk_edsr_plan* p, const float* x, float* y
         g.res = b.HF; g.ld32 = Fp; g.out16 = b.U[0]; g.ld16 = Fp;
         TRY(srk_gemm(&g, stream));
     }
+    if (p->tail_fold.w && Fp == 64 && h >= 3 && w >= 3 && fold_tail_enabled())
+        return run_folded_tail(p->tail_fold, b.U[0], B, h, w, p->scale, 1.f, y, h * p->scale, w * p->scale, stream);
     int Hh = h, Ww = w;
     for (int k = 0; k < p->n_tail_up; ++k) {
         srk_gemm_args g = conv_gemm(b.U[k], Hh, Ww, p->tail_up[k]);

@@ -97,6 +97,11 @@ class EDSR(nn.Module):
         plan.n_tail_up = n_up
         plan.tail_w = k(P.pack_conv_out(self.tail[1].weight.detach()))
         plan.tail_b = float(self.tail[1].bias.detach().float().item())
+        if Fe == 64 and self.tail[1].weight.shape[0] == 1:
+            # the linear tail (Upsampler convs + PixelShuffles + output conv) as ONE 5x5 conv
+            ups = [(m.weight, m.bias) for m in self.tail[0] if isinstance(m, nn.Conv2d)]
+            fw, fb, bw, bb, wsc = P.fold_tail(ups, self.tail[1].weight, self.tail[1].bias, self.scale)
+            plan.tail_fold = L.TailFold(k(fw), k(fb), k(bw), k(bb), wsc)
         plan.conv_dtype = conv_dtype
         keep.append(body)
         self._plan, self._keep = plan, keep

@@ -245,6 +245,10 @@ class SwinIR(nn.Module):
             plan.n_upsample = n_up
             plan.conv_last_w = k(P.pack_conv_out(self.conv_last.weight.detach()))
             plan.conv_last_b = float(self.conv_last.bias.detach().float().item())
+            # the whole linear tail (upsample convs + PixelShuffles + conv_last) as ONE 5x5 conv
+            ups = [(m.weight, m.bias) for m in self.upsample if isinstance(m, nn.Conv2d)]
+            fw, fb, bw, bb, wsc = P.fold_tail(ups, self.conv_last.weight, self.conv_last.bias, self.upscale)
+            plan.tail_fold = L.TailFold(k(fw), k(fb), k(bw), k(bb), wsc)
         else:
             m = self.upsample[0]
             w, b = P.pack_conv3x3(m.weight.detach(), m.bias.detach(), Cp, 64, conv_dtype)

@@ -86,3 +86,60 @@ def pack_conv_in(w: torch.Tensor, b: torch.Tensor):
 def pack_conv_out(w: torch.Tensor):
     """(1, Cin, 3, 3) -> (9, Cin) fp16, tap major."""
     return w.float()[0].permute(1, 2, 0).reshape(9, w.shape[1]).to(torch.float16).contiguous()
+
+
+def fold_tail(up_convs, last_w: torch.Tensor, last_b: torch.Tensor, scale: int):
+    """Compose the linear reconstruction tail -- log2(s) x [Conv3x3(F->4F) + PixelShuffle(2)] then
+    Conv3x3(F->1) (network_swinir.py:661-680, 868; network_nlsn.py Upsampler + tail conv) -- into one
+    5x5 convolution F -> s*s per border variant (include/srk.h, srk_tail_fold).
+
+    up_convs: [(weight (4F,F,3,3), bias (4F))] in the reference layout (PixelShuffle channel order).
+    The kernels are measured, not derived: the tail is a linear map, so its response to unit
+    impulses on a 5x5 feature grid (fp64, plain torch ops on the parameter device, run once at
+    plan-build time) IS the composed kernel, including the effect of every intermediate zero
+    padding for a target pixel in the first / interior / last row and column.
+    Returns (w (64, 1600) fp16, b (64) fp32, border_w (9, 64, 1600) fp16, border_b (9, 64) fp32,
+    w_scale)."""
+    import torch.nn.functional as Fn
+    dev = last_w.device
+    F = last_w.shape[1]
+    if F != 64:
+        raise ValueError("fold_tail: built for 64 feature channels")
+    s2 = scale * scale
+    if s2 > 64:
+        raise ValueError("fold_tail: scale*scale must be <= 64")
+    ups = [(w.detach().double(), b.detach().double()) for w, b in up_convs]
+    lw, lb = last_w.detach().double(), last_b.detach().double()
+
+    def tail(x):
+        for w, b in ups:
+            x = Fn.pixel_shuffle(Fn.conv2d(x, w, b, padding=1), 2)
+        return Fn.conv2d(x, lw, lb, padding=1)
+
+    G = 5
+    # impulse k = (gy*5 + gx)*F + c at grid position (gy, gx), channel c; the last image is all zero
+    X = torch.zeros(G * G * F + 1, F, G, G, dtype=torch.float64, device=dev)
+    idx = torch.arange(G * G * F, device=dev)
+    X[idx, idx % F, (idx // F) // G, (idx // F) % G] = 1.0
+    out = tail(X)[:, 0]                                            # (1601, 5s, 5s)
+    W = torch.zeros(9, 64, 25 * F, dtype=torch.float64, device=dev)
+    Bv = torch.zeros(9, 64, dtype=torch.float64, device=dev)
+    for vy in range(3):
+        for vx in range(3):
+            ty, tx = 2 * vy, 2 * vx                               # target pixel: first / interior / last
+            blk = out[:, ty * scale:(ty + 1) * scale, tx * scale:(tx + 1) * scale].reshape(-1, s2)
+            bias = blk[-1]
+            resp = (blk[:-1] - bias).view(G, G, F, s2)             # [gy][gx][c][n]
+            v = vy * 3 + vx
+            Bv[v, :s2] = bias
+            for dy in range(-2, 3):
+                for dx in range(-2, 3):
+                    gy, gx = ty + dy, tx + dx
+                    if 0 <= gy < G and 0 <= gx < G:
+                        tap = (dy + 2) * 5 + (dx + 2)
+                        W[v, :s2, tap * F:(tap + 1) * F] = resp[gy, gx].t()
+    wmax = float(W.abs().max())
+    w_scale = 1.0 if wmax == 0.0 else 2.0 ** (13 - int(torch.floor(torch.log2(torch.tensor(wmax))).item()))
+    Wh = (W * w_scale).to(torch.float16)
+    Bs = (Bv * w_scale).float()
+    return (Wh[4].contiguous(), Bs[4].contiguous(), Wh.contiguous(), Bs.contiguous(), float(w_scale))

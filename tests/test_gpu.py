@@ -328,6 +328,82 @@ def test_gemm_conv3x3_pixelshuffle_and_image_epilogues(L, engine):
     assert float((img.cpu() - exp).abs().max()) < 3e-3 * max(1.0, float(exp.abs().max()))
 
 
+@pytest.mark.parametrize("engine", ENGINES)
+def test_gemm_conv5x5_image_epilogue(L, engine):
+    """conv_k = 5 (implicit GEMM over a 5x5 window, zero padding 2) with the image epilogue, s = 8."""
+    L.set_engine(engine)
+    g = torch.Generator().manual_seed(14)
+    B, H, W, Cin, s = 2, 11, 9, 64, 8
+    x = torch.randn(B, Cin, H, W, generator=g).half()
+    wt = (torch.randn(s * s, Cin, 5, 5, generator=g) * 0.03).half()
+    bias = torch.randn(s * s, generator=g)
+    wk = wt.float().permute(0, 2, 3, 1).reshape(s * s, 25 * Cin).half().contiguous()     # k = tap*Cin + c
+    hc, wc = H * s - 3, W * s - 6
+    img = torch.zeros(B, 1, hc, wc, device=DEV)
+    _gemm(L, A=x.permute(0, 2, 3, 1).contiguous().to(DEV), a_mode=L.A_CONV3X3, conv_k=5, lda=Cin, nB=B, H=H, W=W,
+          Wt=wk.to(DEV), M=B * H * W, N=64, K=25 * Cin, dtype=L.SRK_FP16, bias=bias.to(DEV), img=img, img_s=s,
+          img_scale=0.25, img_hc=hc, img_wc=wc)
+    exp = F.pixel_shuffle(F.conv2d(x.float(), wt.float(), bias, padding=2), s)[:, :, :hc, :wc] * 0.25
+    assert float((img.cpu() - exp).abs().max()) < 3e-3 * max(1.0, float(exp.abs().max()))
+
+
+@pytest.mark.parametrize("scale", [2, 4, 8])
+def test_folded_tail_equals_conv_chain(L, scale):
+    """packing.fold_tail + 5x5 conv GEMM + srk_tail_border vs the upsampler as the reference runs it:
+    [Conv3x3(64->256) + PixelShuffle(2)] x log2(s), Conv3x3(64->1), fp32 torch on the same fp16 features
+    (network_swinir.py:661-680, 868).  Every pixel, including the border ring, with a crop."""
+    if "tcgen05" not in ENGINES:
+        pytest.skip("tcgen05 engine not under test")
+    L.set_engine("tcgen05")
+    from sr_caco_2_b200 import packing as P
+    g = torch.Generator().manual_seed(15 + scale)
+    n = {2: 1, 4: 2, 8: 3}[scale]
+    ups = [((torch.randn(256, 64, 3, 3, generator=g) * 0.04).to(DEV), (torch.randn(256, generator=g) * 0.1).to(DEV))
+           for _ in range(n)]
+    lw, lb = (torch.randn(1, 64, 3, 3, generator=g) * 0.05).to(DEV), (torch.randn(1, generator=g) * 0.1).to(DEV)
+    for (B, H, W, ch, cw) in [(2, 24, 40, 0, 0), (3, 19, 17, 5, 3), (1, 3, 3, 0, 1)]:
+        x = torch.randn(B, 64, H, W, generator=g).half().to(DEV)
+        y = x.float()
+        for w_, b_ in ups:
+            y = F.pixel_shuffle(F.conv2d(y, w_, b_, padding=1), 2)
+        hc, wc = H * scale - ch, W * scale - cw
+        exp = F.conv2d(y, lw, lb, padding=1)[:, :, :hc, :wc] * 0.5
+        fw, fb, bw, bb, wsc = P.fold_tail(ups, lw, lb, scale)
+        feat = x.permute(0, 2, 3, 1).contiguous()
+        img = torch.full((B, 1, hc, wc), 7.0, device=DEV)
+        _gemm(L, A=feat, a_mode=L.A_CONV3X3, conv_k=5, lda=64, nB=B, H=H, W=W, Wt=fw, M=B * H * W, N=64, K=1600,
+              dtype=L.SRK_FP16, bias=fb, img=img, img_s=scale, img_scale=0.5 / wsc, img_hc=hc, img_wc=wc)
+        tf = L.TailFold(L.ptr(fw), L.ptr(fb), L.ptr(bw), L.ptr(bb), wsc)
+        L.check(L.load().srk_tail_border(L.ptr(feat), B, H, W, scale, C.byref(tf), 0.5, L.ptr(img), hc, wc,
+                                         L.stream_ptr()))
+        err = float((img - exp).abs().max())
+        assert err < 2e-3 * max(1.0, float(exp.abs().max())), (scale, B, H, W, err)
+
+
+def test_folded_tail_network_equals_unfolded(L):
+    """SRK_FOLD_TAIL=0 (upsampler convs one by one, fp16 intermediates) vs the folded tail, whole network."""
+    if "tcgen05" not in ENGINES:
+        pytest.skip("tcgen05 engine not under test")
+    L.set_engine("tcgen05")
+    cfg = O.SwinIRCfg(upscale=4, img_size=16, embed_dim=60, depths=[2, 2], num_heads=[6, 6], mlp_ratio=2.0,
+                      upsampler="pixelshuffle")
+    net = make_swinir(cfg, T.swinir_state_dict(cfg, 5))
+    x = T.synthetic_lr(2, 21, 27, 3).to(DEV)
+    prev = os.environ.get("SRK_FOLD_TAIL")
+    try:
+        os.environ["SRK_FOLD_TAIL"] = "1"
+        y1 = net(x).clone()
+        os.environ["SRK_FOLD_TAIL"] = "0"
+        y0 = net(x).clone()
+    finally:
+        if prev is None:
+            os.environ.pop("SRK_FOLD_TAIL", None)
+        else:
+            os.environ["SRK_FOLD_TAIL"] = prev
+    assert y1.shape == y0.shape == (2, 1, 84, 108)
+    assert float((y1 - y0).abs().max()) < 1.5e-3
+
+
 @pytest.mark.parametrize("geom", [(180, 6, 24, 16, 3), (128, 4, 16, 16, 1), (180, 6, 64, 64, 9), (180, 6, 40, 24, 5)])
 def test_fused_qkv_attention_equals_unfused(L, geom):
     """E_ATTN epilogue (qkv GEMM + window attention in one tcgen05 kernel) vs srk_gemm + srk_window_attention."""

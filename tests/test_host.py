@@ -43,12 +43,12 @@ def test_ctypes_struct_layouts_match_header_sizes(lib, tmp_path):
     src = tmp_path / "sz.c"
     src.write_text('#include "srk.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu\\n",'
                    'sizeof(srk_gemm_args),sizeof(srk_conv_params),sizeof(srk_stb_params),'
-                   'sizeof(srk_swinir_plan),sizeof(srk_edsr_plan));printf("%zu\\n",sizeof(srk_mlp_args));return 0;}\n')
+                   'sizeof(srk_swinir_plan),sizeof(srk_edsr_plan));printf("%zu %zu\\n",sizeof(srk_mlp_args),sizeof(srk_tail_fold));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     sizes = list(map(int, subprocess.check_output([str(exe)]).split()))
     from sr_caco_2_b200 import _lib as L
-    got = [ctypes.sizeof(c) for c in (L.GemmArgs, L.ConvParams, L.StbParams, L.SwinIRPlan, L.EDSRPlan, L.MlpArgs)]
+    got = [ctypes.sizeof(c) for c in (L.GemmArgs, L.ConvParams, L.StbParams, L.SwinIRPlan, L.EDSRPlan, L.MlpArgs, L.TailFold)]
     assert got == sizes
 
 
