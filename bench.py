@@ -295,16 +295,22 @@ def main():
     if swin_pad:
         hn, wn = (h // 8 + 1) * 8, (w // 8 + 1) * 8
     fl = CF.swinir_flops if kind == "swinir" else CF.edsr_flops
-    gflop_patch = fl(kw, hn, wn) / 1e9
+    gflop_patch = fl(kw, hn, wn) / 1e9                       # the network as the reference executes it
+    folded = (args.engine == "tcgen05" and os.environ.get("SRK_FOLD_TAIL", "1") != "0"
+              and kw.get("upsampler", "pixelshuffle") == "pixelshuffle")
+    gflop_exec = fl(kw, hn, wn, folded_tail=folded) / 1e9    # what this implementation executes
     peak = peaks["tensor_sustained"] or peaks["tensor_burst"]
-    step_tflops = value / world * gflop_patch / 1e3
+    step_tflops = value / world * gflop_exec / 1e3
     roofline = {"bound": "tensor", "achieved": None, "peak": peak, "unit": "TFLOP/s", "frac": None,
                 "traffic": None, "peak_source": peaks["source"] + ", sustained bf16",
                 "scope": "per GPU (rank 0)", "whole_step_achieved": step_tflops, "whole_step_frac": step_tflops / peak,
-                "gflop_per_patch": gflop_patch}
+                "gflop_per_patch": gflop_exec, "reference_gflop_per_patch": gflop_patch,
+                "flops_note": "executed FLOPs; the linear reconstruction tail is folded into one 5x5 conv "
+                              "(srk_tail_fold), the reference's layer-by-layer count is reference_gflop_per_patch"
+                              if folded else "executed == reference layer-by-layer count"}
     if prof_ms.get("gemm", 0) > 0:
         fused_attn = kind == "swinir" and prof_ms.get("attention", 0.0) == 0.0   # attention ran inside the qkv GEMM kernel
-        gf = fl(kw, hn, wn, gemm_only=True, attention_in_gemm=True) if fused_attn else fl(kw, hn, wn, gemm_only=True)
+        gf = fl(kw, hn, wn, gemm_only=True, attention_in_gemm=fused_attn, folded_tail=folded)
         ach = gf * B * K / (prof_ms["gemm"] * 1e-3) / 1e12
         roofline.update(achieved=ach, frac=ach / peak,
                         kernel="srk tcgen05 GEMM kernel family incl. the fused qkv+window-attention kernel (every launch of K steps, CUDA events on the launch stream)",

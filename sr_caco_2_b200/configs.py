@@ -26,10 +26,14 @@ WORKLOADS = {
 }
 
 
-def swinir_flops(kw: dict, h: int, w: int, gemm_only: bool = False, attention_in_gemm: bool = False) -> float:
+def swinir_flops(kw: dict, h: int, w: int, gemm_only: bool = False, attention_in_gemm: bool = False,
+                 folded_tail: bool = False) -> float:
     """FLOPs per patch at net-input size h x w (multiples of 8).  gemm_only: the part executed
     by the tensor-core GEMM kernel family (excludes the window-attention products and the
-    1-channel input / output convs, which run in their own kernels)."""
+    1-channel input / output convs, which run in their own kernels).
+    folded_tail = False counts the network as the reference executes it; True counts what this
+    implementation executes when the linear tail (upsample convs + PixelShuffles + conv_last) is
+    composed into one 5x5 conv 64 -> s*s (srk_tail_fold): the roofline uses the EXECUTED count."""
     T, C = h * w, kw["embed_dim"]
     hid, nblk, s, cin = int(C * kw["mlp_ratio"]), sum(kw["depths"]), kw["upscale"], kw["in_chans"]
     gemm = T * nblk * (4 * C * C + 2 * C * hid) + T * (len(kw["depths"]) + 1) * 9 * C * C
@@ -39,7 +43,9 @@ def swinir_flops(kw: dict, h: int, w: int, gemm_only: bool = False, attention_in
         gemm += attn
     else:
         other += attn
-    if kw["upsampler"] == "pixelshuffle":
+    if kw["upsampler"] == "pixelshuffle" and folded_tail:
+        gemm += T * 9 * C * 64 + T * 25 * 64 * 64          # conv_before_upsample + the folded 5x5 conv (N tile = 64)
+    elif kw["upsampler"] == "pixelshuffle":
         gemm += T * 9 * C * 64 + sum((4 ** k) * T * 9 * 64 * 256 for k in range(int(round(math.log2(s)))))
         other += s * s * T * 9 * 64 * cin
     else:
@@ -47,11 +53,16 @@ def swinir_flops(kw: dict, h: int, w: int, gemm_only: bool = False, attention_in
     return 2.0 * (gemm if gemm_only else gemm + other)
 
 
-def edsr_flops(kw: dict, h: int, w: int, gemm_only: bool = False) -> float:
+def edsr_flops(kw: dict, h: int, w: int, gemm_only: bool = False, attention_in_gemm: bool = False,
+               folded_tail: bool = False) -> float:
     T, Fe, s, cin = h * w, kw["n_feats"], kw["scale"], kw["in_chans"]
     gemm = T * (2 * kw["n_resblocks"] + 1) * 9 * Fe * Fe
-    gemm += sum((4 ** k) * T * 9 * Fe * 4 * Fe for k in range(int(round(math.log2(s)))))
-    other = T * 9 * cin * Fe + s * s * T * 9 * Fe * cin
+    other = T * 9 * cin * Fe
+    if folded_tail and Fe == 64:
+        gemm += T * 25 * 64 * 64
+    else:
+        gemm += sum((4 ** k) * T * 9 * Fe * 4 * Fe for k in range(int(round(math.log2(s)))))
+        other += s * s * T * 9 * Fe * cin
     return 2.0 * (gemm if gemm_only else gemm + other)
 
 
