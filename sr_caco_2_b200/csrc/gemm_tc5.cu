@@ -305,7 +305,8 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 int* srowm = reinterpret_cast<int*>(sbias + BN);
                 if (q == 0) {
 #pragma unroll
-                    for (int j = 0; j < BN / 32; ++j) sbias[lane + 32 * j] = __ldg(g.bias + n0 + lane + 32 * j);
+                    for (int j = 0; j < BN / 32; ++j)      // the packed GELU takes the halved bias
+                        sbias[lane + 32 * j] = __ldg(g.bias + n0 + lane + 32 * j) * (ACT == SRK_ACT_GELU ? 0.5f : 1.f);
                     int mm = tile_row_to_m(p, mt, lg * 32 + lane);
                     if (EPI == E_PIXSHUF && mm >= 0) {
                         // PixelShuffle(2): store the index of output pixel (b, 2y, 2x) instead of m, so the
@@ -339,10 +340,18 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const float4 bb = bp[j];
-                            pk[2 * j] = packf<DT>(actf<ACT>(__uint_as_float(v[4 * j]) + bb.x),
-                                                  actf<ACT>(__uint_as_float(v[4 * j + 1]) + bb.y));
-                            pk[2 * j + 1] = packf<DT>(actf<ACT>(__uint_as_float(v[4 * j + 2]) + bb.z),
-                                                      actf<ACT>(__uint_as_float(v[4 * j + 3]) + bb.w));
+                            if constexpr (ACT == SRK_ACT_GELU) {
+                                uint32_t a0, a1;
+                                unpack64(gelu2(pack64(v[4 * j], v[4 * j + 1]), pack64(__float_as_uint(bb.x), __float_as_uint(bb.y))), a0, a1);
+                                pk[2 * j] = packf<DT>(__uint_as_float(a0), __uint_as_float(a1));
+                                unpack64(gelu2(pack64(v[4 * j + 2], v[4 * j + 3]), pack64(__float_as_uint(bb.z), __float_as_uint(bb.w))), a0, a1);
+                                pk[2 * j + 1] = packf<DT>(__uint_as_float(a0), __uint_as_float(a1));
+                            } else {
+                                pk[2 * j] = packf<DT>(actf<ACT>(__uint_as_float(v[4 * j]) + bb.x),
+                                                      actf<ACT>(__uint_as_float(v[4 * j + 1]) + bb.y));
+                                pk[2 * j + 1] = packf<DT>(actf<ACT>(__uint_as_float(v[4 * j + 2]) + bb.z),
+                                                          actf<ACT>(__uint_as_float(v[4 * j + 3]) + bb.w));
+                            }
                         }
                         *reinterpret_cast<uint4*>(srow + c * 32) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                         *reinterpret_cast<uint4*>(srow + c * 32 + 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
