@@ -42,14 +42,19 @@ template <int BN, int EPI>
 struct TcCfg {
     static constexpr bool kStage16 = EPI == E_O16 || EPI == E_PIXSHUF || EPI == E_ATTN;   // 16-bit staging (math in phase T)
     static constexpr int EPI_WARPS = kStage16 ? 16 : 8;       // warps per TMEM lane group: 4 or 2
+    // 16-bit epilogues whose staging fits twice run as TWO warp groups that take alternate tiles, so
+    // the TMEM drain of one tile (64 B/clk port) overlaps the global stores of the other
+    static constexpr int kGroups = (EPI == E_ATTN || (EPI == E_O16 && BN <= 192)) ? 2 : 1;
     static constexpr int THREADS = 64 + 32 * EPI_WARPS;
     static constexpr int A_BYTES = TBM * TBK * 2;
     static constexpr int B_BYTES = BN * TBK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int SROW = BN + 4;                       // fp32 staging row stride (floats)
     static constexpr int SROW16 = BN * 2 + 16;                // 16-bit staging row stride (bytes)
-    static constexpr int STAGING_BYTES = EPI == E_ATTN ? 2 * TBM * SROW16 : (kStage16 ? TBM * SROW16 : TBM * SROW * 4);
-    static constexpr int AUX_BYTES = EPI == E_ATTN ? 4096 : 256 + 8 * (BN + 32) * 4;   // barriers + per-lane-group bias row / row map
+    static constexpr int STAGING_BYTES = kStage16 ? kGroups * TBM * SROW16 : TBM * SROW * 4;
+    // barriers + (16-bit epilogues) 2 slots per warp group of [bias row | row map of the 128 tile rows],
+    // (fp32 epilogues) per-lane-group scratch
+    static constexpr int AUX_BYTES = EPI == E_ATTN ? 4096 : (kStage16 ? 256 + kGroups * 2 * (BN + 128) * 4 : 256 + 8 * (BN + 32) * 4);
     static constexpr int AVAIL = TC_SMEM_TOTAL - STAGING_BYTES - 1024 - AUX_BYTES;   // operand bytes available
     static constexpr int MAX_STAGES = 8;
     static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
@@ -105,7 +110,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     if (threadIdx.x == 0) {
         for (int s = 0; s < Cfg::MAX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         mbar_init(bfull_bar, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI == E_ATTN ? Cfg::EPI_WARPS / 2 : Cfg::EPI_WARPS); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), Cfg::EPI_WARPS / Cfg::kGroups); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
@@ -288,25 +293,35 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         } else if constexpr (Cfg::kStage16) {
             // ---- 16-bit outputs: bias + activation + pack in phase T (thread = row), then a pure
             //      coalesced 16 B/lane copy of the staged rows in phase R ----
-            // four warps per TMEM lane group: quarter q drains 16-column sub-chunks q, q+4, ... in
-            // phase T and copies rows 8q .. 8q+7 of the lane group in phase R
-            const int ew = warp - 2, lg = warp & 3, q = ew >> 2;
-            unsigned char* stg16 = tc_smem_raw + (stg_base - raw) + (size_t)(lg * 32) * Cfg::SROW16;
-            // per-lane-group bias row + row map of the current tile (written by the q == 0 warp)
-            float* sbias0 = reinterpret_cast<float*>(tc_smem_raw + (bars + 256 - raw)) + lg * 2 * (BN + 32);
+            // G warp groups take alternate tiles (group g: TMEM stage g, staging buffer g).  Inside a
+            // group WPL warps share a TMEM lane group: warp q drains 16-column sub-chunks q, q+WPL, ...
+            // in phase T and copies rows q*RPW .. of the lane group in phase R.
+            constexpr int G = Cfg::kGroups;
+            constexpr int WPL = 4 / G;
+            constexpr int RPW = 32 / WPL;
+            const int ew = warp - 2, lg = warp & 3;
+            const int grp = G == 2 ? (ew >> 3) : 0;
+            const int q = (ew >> 2) & (WPL - 1);
+            unsigned char* stg16 = tc_smem_raw + (stg_base - raw) + (size_t)(grp * TBM + lg * 32) * Cfg::SROW16;
+            // [bias row | row map of the tile's 128 rows], two slots per group (late readers of the previous tile)
+            float* aux0 = reinterpret_cast<float*>(tc_smem_raw + (bars + 256 - raw)) + grp * 2 * (BN + 128);
             constexpr int SC = BN / 16;                            // 16-column sub-chunks
             constexpr int CPR = BN / 8;                            // 16 B chunks per row
-            int it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int bar_id = 1 + grp;
+            constexpr int bar_n = 32 * 4 * WPL;                    // the group's warps
+            static_assert(SC % WPL == 0 && (RPW * CPR) % 32 == 0, "tile shape does not split over the warps");
+            for (int tile = blockIdx.x + grp * gridDim.x, it = grp; tile < total_tiles; tile += G * gridDim.x, it += G) {
                 const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
                 const int as = it & 1, aphase = (it >> 1) & 1;
                 const int n0 = nt * BN;
-                float* sbias = sbias0 + (it & 1) * (BN + 32);      // double buffered: late readers of tile it-1
-                int* srowm = reinterpret_cast<int*>(sbias + BN);
+                float* sbias = aux0 + ((it / G) & 1) * (BN + 128);
+                int* srowm = reinterpret_cast<int*>(sbias + BN) + lg * 32;
                 if (q == 0) {
+                    if (lg == 0) {
 #pragma unroll
-                    for (int j = 0; j < BN / 32; ++j)      // the packed GELU takes the halved bias
-                        sbias[lane + 32 * j] = __ldg(g.bias + n0 + lane + 32 * j) * (ACT == SRK_ACT_GELU ? 0.5f : 1.f);
+                        for (int j = 0; j < BN / 32; ++j)      // the packed GELU takes the halved bias
+                            sbias[lane + 32 * j] = __ldg(g.bias + n0 + lane + 32 * j) * (ACT == SRK_ACT_GELU ? 0.5f : 1.f);
+                    }
                     int mm = tile_row_to_m(p, mt, lg * 32 + lane);
                     if (EPI == E_PIXSHUF && mm >= 0) {
                         // PixelShuffle(2): store the index of output pixel (b, 2y, 2x) instead of m, so the
@@ -317,16 +332,16 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     }
                     srowm[lane] = mm;
                 }
-                asm volatile("bar.sync %0, 128;" ::"r"(1 + lg) : "memory");
+                asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(bar_n) : "memory");
                 mbar_wait(tfull_bar(as), aphase);
                 tc_fence_after();
                 {
                     const uint32_t t_row = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN);
                     unsigned char* srow = stg16 + (size_t)lane * Cfg::SROW16;
 #pragma unroll
-                    for (int jj = 0; jj < SC / 4; ++jj) {
+                    for (int jj = 0; jj < SC / WPL; ++jj) {
                         if (p.dbg & 2) break;
-                        const int c = q + 4 * jj;
+                        const int c = q + WPL * jj;
                         uint32_t v[16];
                         asm volatile(
                             "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -360,30 +375,30 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty_bar(as));
-                asm volatile("bar.sync %0, 128;" ::"r"(1 + lg) : "memory");
-                // phase R: this warp's 8 rows, CPR 16 B chunks each
-                const unsigned char* sbase = stg16 + (size_t)(q * 8) * Cfg::SROW16;
+                asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(bar_n) : "memory");
+                // phase R: this warp's RPW rows, CPR 16 B chunks each
+                const unsigned char* sbase = stg16 + (size_t)(q * RPW) * Cfg::SROW16;
 #pragma unroll
-                for (int jj = 0; jj < (8 * CPR) / 32; ++jj) {
+                for (int jj = 0; jj < (RPW * CPR) / 32; ++jj) {
                     if (p.dbg & 1) break;
                     const int idx = lane + 32 * jj;
                     const int row = idx / CPR, col = idx - row * CPR;
-                    const int m = srowm[q * 8 + row];
+                    const int m = srowm[q * RPW + row];
                     const uint4 val = *reinterpret_cast<const uint4*>(sbase + (size_t)row * Cfg::SROW16 + col * 16);
                     if (m >= 0) {
                         uint16_t* dst;
                         if (EPI == E_PIXSHUF) {
                             // column n -> sub-pixel group n / (N/4), channel n % (N/4); N/4 is a multiple of 64
                             const int cq = g.N >> 2, n = n0 + col * 8;
-                            const int grp = n / cq, ch = n - grp * cq;
-                            dst = g.out16 + ((size_t)m + (grp >> 1) * (2 * g.W) + (grp & 1)) * g.ld16 + ch;
+                            const int grp4 = n / cq, ch = n - grp4 * cq;
+                            dst = g.out16 + ((size_t)m + (grp4 >> 1) * (2 * g.W) + (grp4 & 1)) * g.ld16 + ch;
                         } else {
                             dst = g.out16 + (size_t)m * g.ld16 + n0 + col * 8;
                         }
                         *reinterpret_cast<uint4*>(dst) = val;
                     }
                 }
-                // (the bar.sync at the top of the next iteration also protects the staging rows)
+                // (the bar.sync at the top of the group's next tile also protects the staging rows)
             }
         } else {
         const int ew = warp - 2;                               // 0..7
