@@ -166,7 +166,7 @@ gemm_mma_kernel(const GemmP p) {
 }
 
 int validate_gemm(const srk_gemm_args* g) {
-    SRK_REQUIRE(g && g->A && g->Wt && g->bias, "gemm: null operand");
+    SRK_REQUIRE(g && g->A && g->Wt && (g->bias || g->attn_table), "gemm: null operand");
     SRK_REQUIRE(g->M > 0 && g->N > 0 && g->K > 0, "gemm: bad M/N/K");
     SRK_REQUIRE(g->N % 16 == 0, "gemm: N=%d must be padded to a multiple of 16", g->N);
     SRK_REQUIRE(g->K % 64 == 0, "gemm: K=%d must be padded to a multiple of 64", g->K);

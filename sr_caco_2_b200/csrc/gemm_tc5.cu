@@ -220,9 +220,10 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             int* slab = reinterpret_cast<int*>(stab + 2 * 225) + (grp * 2 + window) * 64;  // [grp][window][64]
             const int pair = blockIdx.x % p.n_tiles;
             const int nH = g.attn_heads;
+            const bool has_bias = g.bias != nullptr;
             {
                 const int et = threadIdx.x - 64;                                          // 0..511
-                if (et < BN) sbias[et] = __ldg(g.bias + (et >> 6) * nH * 32 + pair * 64 + (et & 63));
+                if (et < BN && has_bias) sbias[et] = __ldg(g.bias + (et >> 6) * nH * 32 + pair * 64 + (et & 63));
                 if (et < 450) stab[et] = __ldg(g.attn_table + pair * 450 + et);
                 asm volatile("bar.sync 9, 512;" ::: "memory");
             }
@@ -254,13 +255,18 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                               "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                             : "r"(t_row + c * 16));
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                        const float4* bp = reinterpret_cast<const float4*>(sbias + c * 16);
                         uint32_t pk[8];
+                        if (has_bias) {
+                            const float4* bp = reinterpret_cast<const float4*>(sbias + c * 16);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float4 bb = bp[j];
-                            pk[2 * j] = packf<SRK_BF16>(__uint_as_float(v[4 * j]) + bb.x, __uint_as_float(v[4 * j + 1]) + bb.y);
-                            pk[2 * j + 1] = packf<SRK_BF16>(__uint_as_float(v[4 * j + 2]) + bb.z, __uint_as_float(v[4 * j + 3]) + bb.w);
+                            for (int j = 0; j < 4; ++j) {
+                                const float4 bb = bp[j];
+                                pk[2 * j] = packf<SRK_BF16>(__uint_as_float(v[4 * j]) + bb.x, __uint_as_float(v[4 * j + 1]) + bb.y);
+                                pk[2 * j + 1] = packf<SRK_BF16>(__uint_as_float(v[4 * j + 2]) + bb.z, __uint_as_float(v[4 * j + 3]) + bb.w);
+                            }
+                        } else {                                  // bias folded into the GEMM (pad columns of A hold 1)
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) pk[j] = packf<SRK_BF16>(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
                         }
                         *reinterpret_cast<uint4*>(srow + c * 32) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                         *reinterpret_cast<uint4*>(srow + c * 32 + 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
