@@ -327,25 +327,66 @@ def main():
                 "flops_note": "executed FLOPs; the linear reconstruction tail is folded into one 5x5 conv "
                               "(srk_tail_fold), the reference's layer-by-layer count is reference_gflop_per_patch"
                               if folded else "executed == reference layer-by-layer count"}
-    if prof_ms.get("gemm", 0) > 0:
+    gemm_ms = prof_ms.get("gemm", 0.0) + prof_ms.get("gemm_res_ln", 0.0)
+    gemm_calls = prof_calls.get("gemm", 0) + prof_calls.get("gemm_res_ln", 0)
+    family = None
+    if gemm_ms > 0:
         fused_attn = kind == "swinir" and prof_ms.get("attention", 0.0) == 0.0   # attention ran inside the qkv GEMM kernel
         gf = fl(kw, hn, wn, gemm_only=True, attention_in_gemm=fused_attn, folded_tail=folded)
-        ach = gf * B * K / (prof_ms["gemm"] * 1e-3) / 1e12
-        roofline.update(achieved=ach, frac=ach / peak,
-                        kernel="srk tcgen05 GEMM kernel family incl. the fused qkv+window-attention kernel (every launch of K steps, CUDA events on the launch stream)",
-                        algorithmic_gflop_per_patch_in_gemm=gf / 1e9,
-                        launches_per_step=prof_calls["gemm"] / K, ms_per_step=prof_ms["gemm"] / K,
-                        family_ms_per_step={k: v / K for k, v in prof_ms.items()})
+        ach = gf * B * K / (gemm_ms * 1e-3) / 1e12
+        family = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                  "kernel": "srk tcgen05 GEMM kernel family incl. the fused qkv+window-attention kernel (every launch of "
+                            "K steps, CUDA events on the launch stream)",
+                  "algorithmic_gflop_per_patch_in_gemm": gf / 1e9, "launches_per_step": gemm_calls / K,
+                  "ms_per_step": gemm_ms / K}
+        roofline.update(achieved=ach, frac=ach / peak, kernel=family["kernel"],
+                        algorithmic_gflop_per_patch_in_gemm=gf / 1e9, launches_per_step=gemm_calls / K,
+                        ms_per_step=gemm_ms / K, family_ms_per_step={k: v / K for k, v in prof_ms.items()})
     else:
         roofline.update(achieved=step_tflops, frac=step_tflops / peak,
                         kernel="whole step (per-kernel event timing unavailable)")
     tp = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
-    if os.path.exists(tp) and args.workload == "cfg3" and args.geometry == "direct" and B == 32:
-        tj = json.load(open(tp))["gemm_family"]
-        roofline["traffic"] = tj["dram_bytes"]
+    tj = json.load(open(tp)) if os.path.exists(tp) and args.workload == "cfg3" and args.geometry == "direct" and B == 32 else None
+    if tj:
+        roofline["traffic"] = tj["gemm_family"]["dram_bytes"]
         roofline["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum summed over the %d GEMM launches of one "
                                     "step (ncu launch list profiles/r01_launches_cfg3_step.csv); same per-step scope "
-                                    "as `achieved`" % tj["launches"])
+                                    "as `achieved`" % tj["gemm_family"]["launches"])
+    # The dominant single kernel of a SwinIR step is the row GEMM with residual + fused LayerNorm epilogue
+    # (proj and fc2 of every block: gemm_tc5_kernel<192, E_RES_LN>): it is HBM bound, so ITS roofline is the
+    # headline one and the tensor-pipe view of the whole GEMM family moves to `gemm_family`.
+    if kind == "swinir" and prof_ms.get("gemm_res_ln", 0.0) > 0 and peaks.get("hbm"):
+        Cp_, hid_p_ = (kw["embed_dim"] + 63) // 64 * 64, (int(kw["embed_dim"] * kw["mlp_ratio"]) + 63) // 64 * 64
+        nh_max = max(kw["num_heads"])
+        ao_p_ = ((-(-(kw["embed_dim"] // nh_max) // 16) * 16) * nh_max + 63) // 64 * 64
+        tok = B * hn * wn
+        # per token: A (16-bit) + residual in (fp32) + residual out (fp32) + LayerNorm output (16-bit)
+        b_proj, b_fc2 = 2 * ao_p_ + 10 * Cp_, 2 * hid_p_ + 10 * Cp_
+        n_l = prof_calls["gemm_res_ln"] / K
+        bytes_launch = tok * (b_proj + b_fc2) / 2.0
+        t_launch = prof_ms["gemm_res_ln"] / prof_calls["gemm_res_ln"] * 1e-3
+        ach_gbs = bytes_launch / t_launch / 1e9
+        hbm = {"bound": "hbm", "achieved": ach_gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach_gbs / peaks["hbm"],
+               "traffic": None, "peak_source": peaks["source"] + ", device copy",
+               "kernel": "gemm_tc5_kernel<192, E_RES_LN>: proj / fc2 row GEMM + bias + fp32 residual + fused LayerNorm, "
+                         "%.0f launches per step, %.1f %% of the step" % (n_l, 100.0 * prof_ms["gemm_res_ln"] / K / (ms / K)),
+               "algorithmic_bytes_per_launch": bytes_launch,
+               "algorithmic_bytes_per_token": {"proj": b_proj, "fc2": b_fc2},
+               "avg_launch_us": t_launch * 1e6, "launches_per_step": n_l,
+               "share_of_step": prof_ms["gemm_res_ln"] / K / (ms / K), "scope": "per GPU (rank 0)"}
+        if tj and "by_kernel" in tj:
+            for name, kinfo in tj["by_kernel"].items():
+                if name.startswith("gemm_tc5_kernel<192, 2, 0, 0>"):
+                    hbm["traffic"] = kinfo["dram_bytes"] / kinfo["launches"]
+                    hbm["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum per launch, average over the %d "
+                                           "launches of this kernel in profiles/r01_launches_cfg3_step.csv; below the "
+                                           "algorithmic bytes because part of the written rows is still dirty in the "
+                                           "126 MB L2 when the next kernel reads them" % kinfo["launches"])
+        hbm["gemm_family"] = family
+        hbm["whole_step"] = {k: roofline[k] for k in ("whole_step_achieved", "whole_step_frac", "gflop_per_patch",
+                                                       "reference_gflop_per_patch", "flops_note")}
+        hbm["whole_step"]["family_ms_per_step"] = {k: v / K for k, v in prof_ms.items()}
+        roofline = hbm
 
     line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -37,4 +37,5 @@ if len(sys.argv) > 2:
         if k.startswith("gemm_") or k.startswith("mlp_"):
             fam["gemm"][0] += n; fam["gemm"][1] += t; fam["gemm"][2] += b
     json.dump({"gemm_family": {"launches": fam["gemm"][0], "us": fam["gemm"][1], "dram_bytes": fam["gemm"][2]},
+               "by_kernel": {k: {"launches": n, "us": t, "dram_bytes": b} for k, (n, t, b) in agg.items()},
                "total_us": tot, "total_dram_bytes": totb}, open(sys.argv[2], "w"), indent=1)

@@ -118,7 +118,7 @@ extern "C" int srk_index_map(int kind, int H, int W, int shift, int a, int32_t* 
 
 extern "C" int srk_gemm(const srk_gemm_args* g, void* stream) {
     if (int rc = validate_gemm(g)) return rc;
-    ProfScope ps(SRK_PROF_GEMM, stream);
+    ProfScope ps(g->res && g->ln_g && g->a_mode == SRK_A_ROWS ? SRK_PROF_GEMM_RES_LN : SRK_PROF_GEMM, stream);
     if (g_engine == SRK_ENGINE_MMA_SYNC) return gemm_mma_sync(g, (cudaStream_t)stream);
     return gemm_tcgen05(g, (cudaStream_t)stream);
 }
