@@ -124,27 +124,29 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    // resident weight tile, loaded once: weights do not depend on the previous grid, so the load is
+    // issued before the programmatic-dependent-launch wait and overlaps the previous kernel's drain
+    if (warp == 0 && lane == 0 && p.bstat && (int)blockIdx.x < total_tiles) {
+        const int ntb = blockIdx.x % p.n_tiles;
+        mbar_expect_tx(bfull_bar, (uint32_t)p.bres_bytes);
+        for (int kb = 0; kb < p.nkb; ++kb) {
+            if (EPI == E_ATTN) {
+                // head pair ntb: rows [q | k | v] x (2 heads x 32) gathered from the [which][head][32] weight
+#pragma unroll
+                for (int w = 0; w < 3; ++w)
+                    tma_load_2d(base + kb * Cfg::B_BYTES + w * 8192, &map_b, bfull_bar, kb * TBK,
+                                w * g.attn_heads * 32 + ntb * 64);
+            } else {
+                tma_load_2d(base + kb * Cfg::B_BYTES, &map_b, bfull_bar, kb * TBK, ntb * BN);
+            }
+        }
+    }
     pdl_wait();                                                       // prologue done; now the previous grid's data
 
     if (warp == 0) {
         // ================================ TMA producer ================================
         if (lane == 0) {
             int stage = 0, phase = 0;
-            if (p.bstat && (int)blockIdx.x < total_tiles) {          // resident weight tile, loaded once
-                const int ntb = blockIdx.x % p.n_tiles;
-                mbar_expect_tx(bfull_bar, (uint32_t)p.bres_bytes);
-                for (int kb = 0; kb < p.nkb; ++kb) {
-                    if (EPI == E_ATTN) {
-                        // head pair ntb: rows [q | k | v] x (2 heads x 32) gathered from the [which][head][32] weight
-#pragma unroll
-                        for (int w = 0; w < 3; ++w)
-                            tma_load_2d(base + kb * Cfg::B_BYTES + w * 8192, &map_b, bfull_bar, kb * TBK,
-                                        w * g.attn_heads * 32 + ntb * 64);
-                    } else {
-                        tma_load_2d(base + kb * Cfg::B_BYTES, &map_b, bfull_bar, kb * TBK, ntb * BN);
-                    }
-                }
-            }
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
                 int cb_, cx = 0, cy = 0;
