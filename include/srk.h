@@ -209,7 +209,8 @@ int srk_conv_out(const void* a, int lda, int B, int H, int W, int Cin, const voi
 typedef struct {
     const void* w;            /* interior kernel (64, 25*64) fp16, row n = i*s + j, k = tap*64 + c; NULL: not folded */
     const float* b;           /* (64) fp32 */
-    const void* border_w;     /* (9, 64, 25*64) fp16 variant kernels */
+    const void* border_w;     /* (9, 64, 25*64) fp16 variant kernels; inside each 64-channel block k = ks*16 + 2t + 8w + h
+                               * is stored at [t][ks][w][h] (mma.sync B-fragment order of tail_border_kernel) */
     const float* border_b;    /* (9, 64) fp32 */
     float w_scale;
 } srk_tail_fold;

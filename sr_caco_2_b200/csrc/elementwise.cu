@@ -353,8 +353,13 @@ conv_out_mma_kernel(const __half* __restrict__ a, int B, int H, int W, const __h
 // as mma.sync B fragments straight from global / L2) on the tensor cores.
 constexpr int TB_K = 25 * 64;
 constexpr int TB_STRIDE = (TB_K + 8) * 2;            // bytes per staged pixel row (16 B skew: conflict-free ldmatrix)
+constexpr int TB_THREADS = 256;                      // 8 warps, one 8-output n-tile each
 
-__global__ void __launch_bounds__(128)
+// border_w layout (packing.fold_tail): [variant][n][tap][t][ks][w][2] fp16 -- inside every 64-channel
+// block the K order is permuted so that the B fragments of the 4 k-steps of a tap,
+//   b[ks][w] = W[n][tap*64 + ks*16 + 2t + 8w + {0,1}],
+// are 32 contiguous bytes for lane (g = n % 8, t): two 16 B loads per tap.
+__global__ void __launch_bounds__(TB_THREADS)
 tail_border_kernel(const __half* __restrict__ a, int H, int W, int s, const __half* __restrict__ bw,
                    const float* __restrict__ bb, float out_scale, float* __restrict__ y, int Hc, int Wc) {
     extern __shared__ __align__(16) unsigned char tb_smem[];
@@ -386,7 +391,7 @@ tail_border_kernel(const __half* __restrict__ a, int H, int W, int s, const __ha
     }
     const int variant = vy * 3 + vx;
     // stage the neighbourhoods: row i = pixel i of the stretch, column k = tap*64 + c
-    for (int idx = tid; idx < 16 * 25 * 8; idx += 128) {
+    for (int idx = tid; idx < 16 * 25 * 8; idx += TB_THREADS) {
         const int i = idx / 200, rem = idx - i * 200, tap = rem >> 3, chunk = rem & 7;
         uint4 v = make_uint4(0, 0, 0, 0);
         if (i < count) {
@@ -400,43 +405,38 @@ tail_border_kernel(const __half* __restrict__ a, int H, int W, int s, const __ha
     }
     __syncthreads();
     const int n_out = s * s;
-    if (warp * 16 >= n_out) return;                              // this warp's 16 outputs do not exist for this scale
+    if (warp * 8 >= n_out) return;                               // this warp's 8 outputs do not exist for this scale
     const int g = lane >> 2, t = lane & 3;
-    const __half* wv = bw + (size_t)variant * 64 * TB_K;
+    const uint4* wp = reinterpret_cast<const uint4*>(bw + ((size_t)variant * 64 + warp * 8 + g) * TB_K) + t * 2;
     const uint32_t a_addr = sm + ((lane & 7) + ((lane >> 3) & 1) * 8) * TB_STRIDE + (lane >> 4) * 16;
-    float acc[2][4];
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 5
+    for (int tap = 0; tap < 25; ++tap) {
+        const uint4 w0 = __ldg(wp + tap * 8), w1 = __ldg(wp + tap * 8 + 1);   // b[ks][w] for ks = 0,1 | 2,3
+        const uint32_t bf[4][2] = {{w0.x, w0.y}, {w0.z, w0.w}, {w1.x, w1.y}, {w1.z, w1.w}};
 #pragma unroll
-    for (int j = 0; j < 2; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-#pragma unroll 4
-    for (int ks = 0; ks < TB_K / 16; ++ks) {
-        uint32_t af[4];
-        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
-                     : "=r"(af[0]), "=r"(af[1]), "=r"(af[2]), "=r"(af[3]) : "r"(a_addr + ks * 32));
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const __half* wp = wv + (size_t)(warp * 16 + j * 8 + g) * TB_K + ks * 16 + 2 * t;
-            const uint32_t b0 = __ldg(reinterpret_cast<const uint32_t*>(wp));
-            const uint32_t b1 = __ldg(reinterpret_cast<const uint32_t*>(wp + 8));
+        for (int ks = 0; ks < 4; ++ks) {
+            uint32_t af[4];
+            asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                         : "=r"(af[0]), "=r"(af[1]), "=r"(af[2]), "=r"(af[3]) : "r"(a_addr + tap * 128 + ks * 32));
             asm volatile(
                 "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
-                : "+f"(acc[j][0]), "+f"(acc[j][1]), "+f"(acc[j][2]), "+f"(acc[j][3])
-                : "r"(af[0]), "r"(af[1]), "r"(af[2]), "r"(af[3]), "r"(b0), "r"(b1));
+                : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3])
+                : "r"(af[0]), "r"(af[1]), "r"(af[2]), "r"(af[3]), "r"(bf[ks][0]), "r"(bf[ks][1]));
         }
     }
-    // accumulator (row g / g+8, columns 2t, 2t+1 of n-tile j) -> image pixel (s*py + n/s, s*px + n%s)
+    // accumulator (row g / g+8, columns 2t, 2t+1 of the warp's n-tile) -> image pixel (s*py + n/s, s*px + n%s)
 #pragma unroll
-    for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int i = g + (e >> 1) * 8, n = warp * 16 + j * 8 + 2 * t + (e & 1);
-            if (i < count && n < n_out) {
-                int py, px;
-                pixel(i, py, px);
-                const int oy = py * s + n / s, ox = px * s + n % s;
-                if (oy < Hc && ox < Wc)
-                    y[((size_t)bi * Hc + oy) * Wc + ox] = (acc[j][e] + bb[variant * 64 + n]) * out_scale;
-            }
+    for (int e = 0; e < 4; ++e) {
+        const int i = g + (e >> 1) * 8, n = warp * 8 + 2 * t + (e & 1);
+        if (i < count && n < n_out) {
+            int py, px;
+            pixel(i, py, px);
+            const int oy = py * s + n / s, ox = px * s + n % s;
+            if (oy < Hc && ox < Wc)
+                y[((size_t)bi * Hc + oy) * Wc + ox] = (acc[e] + bb[variant * 64 + n]) * out_scale;
         }
+    }
 }
 
 }  // namespace srk
@@ -540,7 +540,7 @@ extern "C" int srk_tail_border(const void* a, int B, int H, int W, int s, const 
         attr = true;
     }
     dim3 grid(2 * ((W - 2 + 15) / 16) + 2 * ((H - 2 + 15) / 16) + 4, B);
-    tail_border_kernel<<<grid, 128, smem, st>>>((const __half*)a, H, W, s, (const __half*)f->border_w, f->border_b,
+    tail_border_kernel<<<grid, TB_THREADS, smem, st>>>((const __half*)a, H, W, s, (const __half*)f->border_w, f->border_b,
                                                 out_scale / f->w_scale, y, Hc, Wc);
     SRK_LAUNCH_CHECK("tail_border_kernel");
     return 0;

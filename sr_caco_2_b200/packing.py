@@ -98,8 +98,8 @@ def fold_tail(up_convs, last_w: torch.Tensor, last_b: torch.Tensor, scale: int):
     impulses on a 5x5 feature grid (fp64, plain torch ops on the parameter device, run once at
     plan-build time) IS the composed kernel, including the effect of every intermediate zero
     padding for a target pixel in the first / interior / last row and column.
-    Returns (w (64, 1600) fp16, b (64) fp32, border_w (9, 64, 1600) fp16, border_b (9, 64) fp32,
-    w_scale)."""
+    Returns (w (64, 1600) fp16, b (64) fp32, border_w (9, 64, 1600) fp16 in the ring-pass fragment
+    order, border_b (9, 64) fp32, w_scale)."""
     import torch.nn.functional as Fn
     dev = last_w.device
     F = last_w.shape[1]
@@ -142,4 +142,7 @@ def fold_tail(up_convs, last_w: torch.Tensor, last_b: torch.Tensor, scale: int):
     w_scale = 1.0 if wmax == 0.0 else 2.0 ** (13 - int(torch.floor(torch.log2(torch.tensor(wmax))).item()))
     Wh = (W * w_scale).to(torch.float16)
     Bs = (Bv * w_scale).float()
-    return (Wh[4].contiguous(), Bs[4].contiguous(), Wh.contiguous(), Bs.contiguous(), float(w_scale))
+    # ring-pass layout: inside every 64-channel block k = ks*16 + 2t + 8w + h is stored at [t][ks][w][h]
+    # (the mma.sync B fragments of a tap become 32 contiguous bytes per lane, elementwise.cu)
+    Wb = Wh.view(9, 64, 25, 4, 2, 4, 2).permute(0, 1, 2, 5, 3, 4, 6).reshape(9, 64, 25 * F).contiguous()
+    return (Wh[4].contiguous(), Bs[4].contiguous(), Wb, Bs.contiguous(), float(w_scale))
