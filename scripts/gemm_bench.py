@@ -7,7 +7,7 @@ L.load()
 dev = "cuda:0"
 eng = sys.argv[1] if len(sys.argv) > 1 else "tcgen05"
 L.set_engine(eng)
-B, H, W = 32, 64, 64
+B, H, W = int(os.environ.get("SRK_B", 32)), 64, 64
 M = B * H * W
 
 def run(name, **kw):

@@ -644,6 +644,7 @@ int num_sms() {
     if (dev < 64 && n[dev]) return n[dev];
     int v = 148;
     cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (const char* e = getenv("SRK_SM_CAP")) { const int cap = atoi(e); if (cap > 0 && cap < v) v = cap; }   // experiments
     if (dev < 64) n[dev] = v;
     return v;
 }
