@@ -153,8 +153,9 @@ conv_in_ln_kernel(const float* __restrict__ x, int B, int h, int w, int H, int W
     for (int i = threadIdx.x; i < ld32; i += blockDim.x) cws[9 * ld32 + i] = i < C ? bias[i] : 0.f;
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const long long npix = (long long)B * H * W;
-    const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+    const int npix = B * H * W;                                   // host checks B*H*W < 2^31: 32-bit index math
+    const int wstride = gridDim.x * (blockDim.x >> 5);
+    const int T = H * W;
     float2 G1[NP], B1[NP], G2[NP], B2[NP];
 #pragma unroll
     for (int k = 0; k < NP; ++k) {
@@ -166,8 +167,9 @@ conv_in_ln_kernel(const float* __restrict__ x, int B, int h, int w, int H, int W
         B2[k] = in ? *reinterpret_cast<const float2*>(b2 + c) : make_float2(0.f, 0.f);
     }
     const float inv_c = 1.f / (float)C;
-    for (long long pix = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pix < npix; pix += wstride) {
-        const int px = (int)(pix % W), py = (int)((pix / W) % H), bi = (int)(pix / ((long long)W * H));
+    for (int pix = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pix < npix; pix += wstride) {
+        const int bi = pix / T, tok = pix - bi * T;
+        const int py = tok / W, px = tok - py * W;
         float in[9];
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy)
@@ -218,8 +220,6 @@ conv_in_ln_kernel(const float* __restrict__ x, int B, int h, int w, int H, int W
         for (int k = 0; k < NP; ++k)
             if (64 * k + 2 * lane < C) { const float a0 = v[k].x - mean, a1 = v[k].y - mean; q += a0 * a0 + a1 * a1; }
         rstd = 1.f / sqrtf(warp_sum(q) * inv_c + 1e-5f);
-        const int T = H * W;
-        const int tok = py * W + px;
         const size_t row16 = (size_t)bi * T + (win_shift >= 0 ? token_to_win_pos(tok, H, W, win_shift) : tok);
 #pragma unroll
         for (int k = 0; k < NP; ++k) {
@@ -493,6 +493,7 @@ extern "C" int srk_conv_in_ln(const float* x, int B, int h, int w, int H, int W,
     SRK_REQUIRE(H % 8 == 0 && W % 8 == 0 && (win_shift == -1 || win_shift == 0 || win_shift == 4), "conv_in_ln: bad window geometry");
     SRK_REQUIRE(ld32 % 64 == 0 && ld32 == ld16 && ld32 >= C && ld32 <= 256 && C % 2 == 0, "conv_in_ln: channels must be padded to a multiple of 64 (<= 256)");
     const long long npix = (long long)B * H * W;
+    SRK_REQUIRE(npix < (1ll << 31), "conv_in_ln: B*H*W must be below 2^31");
     const long long blocks = (npix + 7) / 8;
     const int grid = (int)(blocks < 148 * 8 ? blocks : 148 * 8);
     const size_t smem = (size_t)10 * ld32 * sizeof(float);
