@@ -98,6 +98,14 @@ int srk_metrics(const float* E, const float* H, int B, int Hpx, int Wpx, int bor
                 void* scratch, void* stream);
 /* Variant with a caller-provided ROI mask (B,1,Hpx,Wpx) fp32 {0,1} (the `roi=` argument of
  * the reference's metric functions); out: (B, SRK_MET_N). */
+/* Same as srk_metrics with quantize = 1, the target given as the uint8 levels the loader holds
+ * (ship uint8 targets, convert on the device): H8: (B,1,Hpx,Wpx) uint8.  Identical
+ * results to srk_metrics(E, H8 / 255.f, ...): tensor2uint82float (utils_image.py:369-372) maps
+ * x / 255 back to x.  roi_ths must be ascending. */
+int srk_metrics_h8(const float* E, const unsigned char* H8, int B, int Hpx, int Wpx, int border,
+                   const int* roi_ths, int n_ths, double* out, int32_t* flags, void* scratch,
+                   void* stream);
+
 int srk_metrics_roi(const float* E, const float* H, const float* roi, int B, int Hpx, int Wpx,
                     int border, int quantize, double* out, int32_t* flags, void* scratch,
                     void* stream);
@@ -220,6 +228,11 @@ typedef struct {
  * y: (B,1,Hc,Wc), y = (conv5x5 + bias) * out_scale / w_scale.  H, W >= 3. */
 int srk_tail_border(const void* a, int B, int H, int W, int s, const srk_tail_fold* f,
                     float out_scale, float* y, int Hc, int Wc, void* stream);
+
+/* Bicubic baseline: Interpolate.forward (dlib/utils/utils_trainer.py:120-147),
+ * y = clamp(F.interpolate(x, scale_factor = s, mode = 'bicubic', antialias = True), 0, 1);
+ * x: (B,1,h,w) fp32, y: (B,1,h*s,w*s) fp32. */
+int srk_bicubic_upsample(const float* x, int B, int h, int w, int s, float* y, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Network drivers.  Replace SwinIR.forward (dlib/models/network_swinir.py:930-970) and the

@@ -51,6 +51,7 @@ import math
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
 
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -475,3 +476,42 @@ def edsr_flops(cfg: EDSRCfg, h: int, w: int) -> float:
         mac += (4 ** k) * T * 9 * Fe * 4 * Fe
     mac += cfg.scale ** 2 * T * 9 * Fe * cfg.in_chans
     return 2.0 * mac
+
+
+# ------------------------------------------------------------------------------------------
+# Bicubic baseline (SURVEY 8f-3): Interpolate.forward, dlib/utils/utils_trainer.py:120-147 --
+# F.interpolate(x, scale_factor=s, mode='bicubic', antialias=True) then clamp to [0, 1].
+# The anti-aliased bicubic of PyTorch is the separable PIL filter with a = -0.5: per output index o,
+# center = (o + 0.5) / s, taps xmin = max(0, int(center - 2 + 0.5)) .. min(n, int(center + 2 + 0.5)) - 1,
+# weight = cubic(j - center + 0.5), renormalised over the taps that exist (no edge replication).
+# ------------------------------------------------------------------------------------------
+def _cubic_aa(x, a=-0.5):
+    x = np.abs(x)
+    return np.where(x < 1.0, ((a + 2.0) * x - (a + 3.0)) * x * x + 1.0,
+                    np.where(x < 2.0, (((x - 5.0) * x + 8.0) * x - 4.0) * a, 0.0))
+
+
+def bicubic_aa_taps(n_in: int, scale: int):
+    """[(first tap, weights)] for every output index of a 1-D upsampling by `scale`."""
+    taps = []
+    for o in range(n_in * scale):
+        center = (o + 0.5) / scale
+        lo = max(0, int(center - 2.0 + 0.5))
+        hi = min(n_in, int(center + 2.0 + 0.5))
+        w = _cubic_aa(np.arange(lo, hi, dtype=np.float64) - center + 0.5)
+        taps.append((lo, w / w.sum()))
+    return taps
+
+
+def interpolate_baseline(x, scale: int):
+    """(B, C, h, w) in [0, 1] -> (B, C, h*s, w*s) float32, clamped to [0, 1]."""
+    x = np.asarray(x, dtype=np.float64)
+    B, C, h, w = x.shape
+    tx, ty = bicubic_aa_taps(w, scale), bicubic_aa_taps(h, scale)
+    tmp = np.empty((B, C, h, w * scale))
+    for o, (lo, wt) in enumerate(tx):
+        tmp[..., o] = (x[..., lo:lo + len(wt)] * wt).sum(-1)
+    out = np.empty((B, C, h * scale, w * scale))
+    for o, (lo, wt) in enumerate(ty):
+        out[..., o, :] = (tmp[..., lo:lo + len(wt), :] * wt[:, None]).sum(-2)
+    return np.clip(out, 0.0, 1.0).astype(np.float32)

@@ -92,6 +92,9 @@ PROTOTYPES = {
                               C.POINTER(C.c_int), C.c_int, vp, vp, vp, vp]),
     "srk_metrics_roi": (C.c_int, [fp, fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp,
                                   vp, vp]),
+    "srk_metrics_h8": (C.c_int, [fp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, vp, vp,
+                                 vp, vp]),
+    "srk_bicubic_upsample": (C.c_int, [fp, C.c_int, C.c_int, C.c_int, C.c_int, fp, vp]),
     "srk_gemm": (C.c_int, [C.POINTER(GemmArgs), vp]),
     "srk_mlp": (C.c_int, [C.POINTER(MlpArgs), vp]),
     "srk_layernorm": (C.c_int, [fp, C.c_int, C.c_int, C.c_int, fp, fp, C.c_float, vp, C.c_int,

@@ -439,6 +439,60 @@ tail_border_kernel(const __half* __restrict__ a, int H, int W, int s, const __ha
     }
 }
 
+// ---- bicubic baseline ---------------------------------------------------------------
+// Interpolate.forward (dlib/utils/utils_trainer.py:120-147): F.interpolate(scale_factor = s, mode =
+// 'bicubic', antialias = True) then clamp to [0, 1].  The anti-aliased bicubic is the separable PIL
+// filter with a = -0.5; for an up-scaling its support is 2 input pixels each side, and at the image
+// border the taps that do not exist are dropped and the rest renormalised (no edge replication).
+__device__ __forceinline__ float cubic_aa(float x) {
+    x = fabsf(x);
+    const float a = -0.5f;
+    if (x < 1.f) return ((a + 2.f) * x - (a + 3.f)) * x * x + 1.f;
+    if (x < 2.f) return (((x - 5.f) * x + 8.f) * x - 4.f) * a;
+    return 0.f;
+}
+// taps of output index o along an axis of n input pixels: first tap, count (<= 4), normalised weights
+__device__ __forceinline__ void bicubic_taps(int o, int n, float inv_s, int& lo, int& cnt, float (&wt)[4]) {
+    const float center = inv_s * ((float)o + 0.5f);
+    lo = max(0, (int)(center - 2.f + 0.5f));
+    const int hi = min(n, (int)(center + 2.f + 0.5f));
+    cnt = hi - lo;
+    float tot = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        wt[j] = j < cnt ? cubic_aa((float)(lo + j) - center + 0.5f) : 0.f;
+        tot += wt[j];
+    }
+    const float inv = 1.f / tot;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) wt[j] *= inv;
+}
+
+__global__ void __launch_bounds__(256)
+bicubic_up_kernel(const float* __restrict__ x, int h, int w, int s, float* __restrict__ y) {
+    const int W = w * s, Hh = h * s;
+    const int ox = blockIdx.x * 32 + (threadIdx.x & 31), oy = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (ox >= W || oy >= Hh) return;
+    const float inv_s = 1.f / (float)s;
+    int x0, nx, y0, ny;
+    float wx[4], wy[4];
+    bicubic_taps(ox, w, inv_s, x0, nx, wx);
+    bicubic_taps(oy, h, inv_s, y0, ny, wy);
+    const float* xb = x + (size_t)blockIdx.z * h * w;
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (j < ny) {
+            const float* row = xb + (size_t)(y0 + j) * w + x0;
+            float r = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) if (i < nx) r = fmaf(wx[i], __ldg(row + i), r);
+            acc = fmaf(wy[j], r, acc);
+        }
+    }
+    y[((size_t)blockIdx.z * Hh + oy) * W + ox] = fminf(fmaxf(acc, 0.f), 1.f);
+}
+
 }  // namespace srk
 
 using namespace srk;
@@ -544,5 +598,16 @@ extern "C" int srk_tail_border(const void* a, int B, int H, int W, int s, const 
     tail_border_kernel<<<grid, TB_THREADS, smem, st>>>((const __half*)a, H, W, s, (const __half*)f->border_w, f->border_b,
                                                 out_scale / f->w_scale, y, Hc, Wc);
     SRK_LAUNCH_CHECK("tail_border_kernel");
+    return 0;
+}
+
+extern "C" int srk_bicubic_upsample(const float* x, int B, int h, int w, int s, float* y, void* stream) {
+    SRK_REQUIRE(x && y, "bicubic_upsample: null pointer");
+    SRK_REQUIRE(B > 0 && B <= 65535 && h > 0 && w > 0 && s >= 1 && s <= 16, "bicubic_upsample: bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfScope ps(SRK_PROF_CONV_OUT, stream);
+    dim3 grid(ceil_div((long long)w * s, 32), ceil_div((long long)h * s, 8), B);
+    bicubic_up_kernel<<<grid, 256, 0, st>>>(x, h, w, s, y);
+    SRK_LAUNCH_CHECK("bicubic_up_kernel");
     return 0;
 }

@@ -315,6 +315,7 @@ __global__ void metrics_fast_init_kernel(BucketAcc* acc, int n) {
 
 struct FastParams {
     const float* E; const float* H;
+    const unsigned char* H8;      // optional: the target as stored uint8 levels (H is then unused)
     int B, Hpx, Wpx, border, n_ths;
     float ths[SRK_MAX_ROI_THS];
     BucketAcc* acc;
@@ -339,7 +340,8 @@ metrics_fast_kernel(const FastParams p) {
     const int Hc = p.Hpx - 2 * p.border, Wc = p.Wpx - 2 * p.border;
     const int r0 = blockIdx.y * MT, c0 = blockIdx.x * MT;
     const float* Eb = p.E + (size_t)b * p.Hpx * p.Wpx;
-    const float* Hb = p.H + (size_t)b * p.Hpx * p.Wpx;
+    const float* Hb = p.H8 ? nullptr : p.H + (size_t)b * p.Hpx * p.Wpx;
+    const unsigned char* H8b = p.H8 ? p.H8 + (size_t)b * p.Hpx * p.Wpx : nullptr;
     const int NB = p.n_ths + 1;
 
     lut[tid] = __fdiv_rn((float)tid, 255.f);                         // x / 255 exactly as the reference divides
@@ -357,7 +359,7 @@ metrics_fast_kernel(const FastParams p) {
         int e = 0, h = 0, kb = 0;
         if (r < Hc && c < Wc) {
             const size_t off = (size_t)(r + p.border) * p.Wpx + (c + p.border);
-            const float hf = quant255(__ldg(Hb + off));
+            const float hf = H8b ? (float)__ldg(H8b + off) : quant255(__ldg(Hb + off));
             e = (int)quant255(__ldg(Eb + off));
             h = (int)hf;
 #pragma unroll
@@ -575,8 +577,8 @@ static void launch_tile(int NV, dim3 grid, cudaStream_t st, const MetParams& p) 
 
 static int run_metrics(const float* E, const float* H, const float* roi, int B, int Hpx, int Wpx,
                        int border, int quantize, const int* roi_ths, int n_ths, double* out,
-                       int32_t* flags, void* scratch, cudaStream_t st) {
-    SRK_REQUIRE(E && H && out && flags && scratch, "metrics: null pointer");
+                       int32_t* flags, void* scratch, cudaStream_t st, const unsigned char* H8 = nullptr) {
+    SRK_REQUIRE(E && (H || H8) && out && flags && scratch, "metrics: null pointer");
     SRK_REQUIRE(B > 0 && Hpx > 0 && Wpx > 0 && border >= 0, "metrics: bad shape");
     SRK_REQUIRE(n_ths >= 0 && n_ths <= SRK_MAX_ROI_THS, "metrics: n_ths must be in [0,%d]",
                 SRK_MAX_ROI_THS);
@@ -591,7 +593,7 @@ static int run_metrics(const float* E, const float* H, const float* roi, int B, 
     if (quantize && !roi && sorted) {
         // hot path: integer / bucketed kernel
         FastParams fp{};
-        fp.E = E; fp.H = H; fp.B = B; fp.Hpx = Hpx; fp.Wpx = Wpx; fp.border = border; fp.n_ths = n_ths;
+        fp.E = E; fp.H = H; fp.H8 = H8; fp.B = B; fp.Hpx = Hpx; fp.Wpx = Wpx; fp.border = border; fp.n_ths = n_ths;
         for (int i = 0; i < n_ths; ++i) fp.ths[i] = (float)roi_ths[i];
         fp.acc = reinterpret_cast<BucketAcc*>(scratch);
         ProfScope ps(SRK_PROF_METRICS, st);
@@ -608,6 +610,7 @@ static int run_metrics(const float* E, const float* H, const float* roi, int B, 
         SRK_LAUNCH_CHECK("metrics_fast_finalize_kernel");
         return 0;
     }
+    if (H8) return fail(SRK_ERR_UNSUPPORTED, "metrics: uint8 targets need the quantised path with ascending thresholds");
     const int NV = roi ? 1 : 1 + n_ths;
     MetParams p{};
     p.E = E; p.H = H; p.roi = roi; p.B = B; p.Hpx = Hpx; p.Wpx = Wpx; p.border = border;
@@ -643,6 +646,14 @@ extern "C" int srk_metrics(const float* E, const float* H, int B, int Hpx, int W
                            int32_t* flags, void* scratch, void* stream) {
     return srk::run_metrics(E, H, nullptr, B, Hpx, Wpx, border, quantize, roi_ths, n_ths, out,
                             flags, scratch, (cudaStream_t)stream);
+}
+
+extern "C" int srk_metrics_h8(const float* E, const unsigned char* H8, int B, int Hpx, int Wpx, int border,
+                              const int* roi_ths, int n_ths, double* out, int32_t* flags, void* scratch,
+                              void* stream) {
+    if (!H8) return srk::fail(SRK_ERR_INVALID, "metrics_h8: null target");
+    return srk::run_metrics(E, nullptr, nullptr, B, Hpx, Wpx, border, 1, roi_ths, n_ths, out, flags, scratch,
+                            (cudaStream_t)stream, H8);
 }
 
 extern "C" int srk_metrics_roi(const float* E, const float* H, const float* roi, int B, int Hpx,

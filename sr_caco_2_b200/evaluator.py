@@ -90,6 +90,8 @@ def make_cuda_step(net, scale: int, swinir_padding: bool, border: Optional[int] 
         dev = next(net.parameters()).device
         cur = torch.cuda.current_stream(dev)
         lr_b = lr_b.to(dev, non_blocking=True)
+        if lr_b.dtype == torch.uint8:                   # uint8 shipping: uint2tensor on the device
+            lr_b = lr_b.float().div(255.0)
         if hr_b.device != dev:
             # the target image is 8^2 x larger than the input and only the metrics kernel reads it:
             # its host->device copy runs on a side stream underneath the network forward
@@ -110,6 +112,29 @@ def make_cuda_step(net, scale: int, swinir_padding: bool, border: Optional[int] 
             cols += [m["roi_" + k] for k in METRICS]
         else:
             cols += [torch.zeros_like(cols[0])] * 5
+        return torch.stack(cols, 1)
+
+    return step
+
+
+def make_bicubic_step(scale: int, border: Optional[int] = None,
+                      roi_ths: Sequence[int] = (4, 5, 6, 7, 8, 9, 10), check: bool = False, device=None):
+    """The model-free baseline sweep of `evaluate()` (utils_trainer.py:1263-1280): bicubic
+    up-scaling (Interpolate.forward :120-147) + the same single-pass metrics."""
+    from . import utils_image as UI
+    from .interpolate import bicubic_upsample
+
+    b = scale if border is None else border
+
+    def step(lr_b: torch.Tensor, hr_b: torch.Tensor) -> torch.Tensor:
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        lr_b = lr_b.to(dev, non_blocking=True)
+        if lr_b.dtype == torch.uint8:
+            lr_b = lr_b.float().div(255.0)
+        hr_b = hr_b.to(dev, non_blocking=True)
+        m = UI.compute_metrics(bicubic_upsample(lr_b, scale), hr_b, b, roi_ths, check=check)
+        cols = [m[k] for k in METRICS]
+        cols += [m["roi_" + k] for k in METRICS] if len(roi_ths) else [torch.zeros_like(cols[0])] * 5
         return torch.stack(cols, 1)
 
     return step

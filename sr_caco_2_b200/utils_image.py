@@ -49,7 +49,9 @@ def _run(a, b, border, roi, quantize, ths: Sequence[int] = ()):
     lib = L.load()
     _check_pair(a, b, roi)
     a = a.float().contiguous()
-    b = b.float().contiguous()
+    # uint8 target = the levels the loader holds: no float copy, the kernel reads the bytes
+    b_u8 = b.dtype == torch.uint8 and quantize and roi is None and list(ths) == sorted(set(int(t) for t in ths))
+    b = b.contiguous() if b_u8 else (b.float().div(255.0) if b.dtype == torch.uint8 else b.float()).contiguous()
     B, _, Hh, Ww = a.shape
     if Hh - 2 * border < 11 or Ww - 2 * border < 11:
         raise ValueError("Kernel size can't be greater than actual input size. "
@@ -67,9 +69,13 @@ def _run(a, b, border, roi, quantize, ths: Sequence[int] = ()):
                                         L.stream_ptr()))
         else:
             arr = (C.c_int * max(len(ths), 1))(*[int(t) for t in ths])
-            L.check(lib.srk_metrics(L.ptr(a), L.ptr(b), B, Hh, Ww, border, int(quantize), arr,
-                                    len(ths), L.ptr(out), L.ptr(flags), L.ptr(scratch),
-                                    L.stream_ptr()))
+            if b_u8:
+                L.check(lib.srk_metrics_h8(L.ptr(a), L.ptr(b), B, Hh, Ww, border, arr, len(ths), L.ptr(out),
+                                           L.ptr(flags), L.ptr(scratch), L.stream_ptr()))
+            else:
+                L.check(lib.srk_metrics(L.ptr(a), L.ptr(b), B, Hh, Ww, border, int(quantize), arr,
+                                        len(ths), L.ptr(out), L.ptr(flags), L.ptr(scratch),
+                                        L.stream_ptr()))
     return out, flags
 
 
@@ -98,7 +104,8 @@ def mbatch_gpu_calculate_ssim(x, y, border: int = 0, roi: Optional[torch.Tensor]
 
 def compute_metrics(E: torch.Tensor, H: torch.Tensor, border: int,
                     roi_ths: Sequence[int] = (), check: bool = True) -> Dict[str, torch.Tensor]:
-    """E, H in [0,1] (B,1,h,w) on CUDA.  Returns per-image fp64 tensors of shape (B,) for the
+    """E in [0,1] (B,1,h,w) on CUDA; H either float in [0,1] or the uint8 levels of the stored
+    target (same results, a quarter of the bytes).  Returns per-image fp64 tensors of shape (B,) for the
     five metrics of `_compute_metrics`, and when roi_ths is given, the same five averaged over
     the ROI thresholds under the keys 'roi_<metric>' (marginalize_roi_th_perf).
     One kernel pass; one optional host sync for the NaN/Inf/negative guard

@@ -545,6 +545,52 @@ def test_window_attention(L, geom):
             assert float(out.float().cpu()[:, nh * dp:].abs().max()) == 0.0
 
 
+def test_metrics_uint8_targets_equal_float_targets(L):
+    """srk_metrics_h8 (targets shipped as the stored uint8 levels) == srk_metrics on H8 / 255."""
+    from sr_caco_2_b200 import utils_image as UI
+    g = torch.Generator().manual_seed(21)
+    H8 = torch.randint(0, 256, (3, 1, 96, 80), generator=g, dtype=torch.uint8)
+    H8[0, 0, :40] = torch.randint(0, 12, (40, 80), generator=g, dtype=torch.uint8)      # exercise the ROI thresholds
+    E = (H8.float() / 255.0 + 0.05 * torch.randn(3, 1, 96, 80, generator=g)).clamp(0, 1)
+    ths = (4, 5, 6, 7, 8, 9, 10)
+    a = UI.compute_metrics(E.to(DEV), (H8.float() / 255.0).to(DEV), 4, ths)
+    b = UI.compute_metrics(E.to(DEV), H8.to(DEV), 4, ths)
+    assert torch.equal(a["raw"], b["raw"])
+    # the same through the evaluator: uint8 low-res input and uint8 target, converted on the device
+    from sr_caco_2_b200 import evaluator as EV
+    L8 = torch.randint(0, 256, (3, 1, 24, 20), generator=g, dtype=torch.uint8)
+    step = EV.make_bicubic_step(4, roi_ths=ths)
+    v8 = step(L8, H8)
+    vf = step(L8.float() / 255.0, H8.float() / 255.0)
+    assert v8.shape == (3, 10) and torch.equal(v8, vf)
+
+
+@pytest.mark.parametrize("scale", [2, 4, 8])
+def test_bicubic_baseline_against_reference_golden(L, scale):
+    """srk_bicubic_upsample vs the golden of Interpolate.forward (F.interpolate bicubic antialias + clamp)
+    and vs the oracle on a larger random batch; then its metrics through the shared kernel."""
+    import sr_caco_2_b200 as S
+    z = np.load(os.path.join(T.GOLDEN, "bicubic_baseline.npz"))
+    y = S.bicubic_upsample(torch.from_numpy(z[f"x{scale}"]).to(DEV), scale).cpu().numpy()
+    assert y.shape == z[f"y{scale}"].shape
+    assert float(np.abs(y - z[f"y{scale}"]).max()) < 2e-6
+    x = T.synthetic_lr(3, 37, 29, 5)
+    y = S.bicubic_upsample(x.to(DEV), scale)
+    ref = torch.from_numpy(O.interpolate_baseline(x.numpy(), scale))
+    assert float((y.cpu() - ref).abs().max()) < 2e-6
+    m = S.Interpolate("super-resolution", scale, "bicubic")
+    hr = ((ref + 0.04 * torch.randn(ref.shape, generator=torch.Generator().manual_seed(2))).clamp(0, 1) * 255).round() / 255
+    m.feed_data({"l_im": x, "h_im": hr})
+    m.test()
+    vis = m.current_visuals()
+    assert torch.equal(vis["E"], y)
+    from sr_caco_2_b200 import utils_image as UI
+    got = UI.compute_metrics(vis["E"], vis["H"], scale, (4, 6, 8))
+    exp = O.all_metrics(ref, hr, scale)
+    assert abs(float(got["psnr"][0]) - float(exp["psnr"][0])) < 0.01
+    assert abs(float(got["ssim"][0]) - float(exp["ssim"][0])) < 1e-4
+
+
 # ------------------------------------------------------------------------------------------
 # networks
 # ------------------------------------------------------------------------------------------

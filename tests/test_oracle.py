@@ -187,3 +187,15 @@ def test_state_dict_layout_and_forward_match_live_reference():
     with torch.no_grad():
         ref2 = net2(x)
     assert float((O.swinir_forward(sd2, cfg2, x) - ref2).abs().max()) < 2e-5
+
+
+def test_bicubic_baseline_oracle_matches_reference_golden():
+    """oracle.interpolate_baseline vs F.interpolate(bicubic, antialias=True) + clamp, the body of the
+    reference's Interpolate.forward (tests/golden/make_bicubic_golden.py)."""
+    import numpy as np
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "bicubic_baseline.npz"))
+    for s in (2, 4, 8):
+        got = O.interpolate_baseline(z[f"x{s}"], s)
+        assert got.shape == z[f"y{s}"].shape
+        assert float(np.abs(got - z[f"y{s}"]).max()) < 1e-6
+        assert got.min() >= 0.0 and got.max() <= 1.0
