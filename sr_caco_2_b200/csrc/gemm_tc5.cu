@@ -38,10 +38,14 @@ struct TcParams {
     int dbg;      // SRK_TC5_DBG (profiling experiments only): 1 skip phase R, 2 skip phase T body, 4 skip MMAs
 };
 
+#ifndef SRK_FP32_EPI_WARPS
+#define SRK_FP32_EPI_WARPS 8                               // epilogue warps of the fp32 (residual / LayerNorm) path: 8 or 16 (measured: 16 is 6 % slower, 96-register cap)
+#endif
+
 template <int BN, int EPI>
 struct TcCfg {
     static constexpr bool kStage16 = EPI == E_O16 || EPI == E_PIXSHUF || EPI == E_ATTN;   // 16-bit staging (math in phase T)
-    static constexpr int EPI_WARPS = kStage16 ? 16 : 8;       // warps per TMEM lane group: 4 or 2
+    static constexpr int EPI_WARPS = (kStage16 || SRK_FP32_EPI_WARPS == 16) ? 16 : 8;   // warps per TMEM lane group: 4 or 2
     // 16-bit epilogues whose staging fits twice run as TWO warp groups that take alternate tiles, so
     // the TMEM drain of one tile (64 B/clk port) overlaps the global stores of the other
     static constexpr int kGroups = (EPI == E_ATTN || (EPI == E_O16 && BN <= 192)) ? 2 : 1;
@@ -246,17 +250,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 {
                     const uint32_t t_row = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN);
                     unsigned char* srow = stg_all + (size_t)(lg * 32 + lane) * Cfg::SROW16;
-#pragma unroll
-                    for (int jj = 0; jj < SC / 2; ++jj) {
-                        const int c = hq + 2 * jj;
-                        uint32_t v[16];
-                        asm volatile(
-                            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-                            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-                            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                            : "r"(t_row + c * 16));
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    auto convert16 = [&](const uint32_t* v, int c) {      // 16 accumulator columns -> 32 B of the staged row
                         uint32_t pk[8];
                         if (has_bias) {
                             const float4* bp = reinterpret_cast<const float4*>(sbias + c * 16);
@@ -272,6 +266,14 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         }
                         *reinterpret_cast<uint4*>(srow + c * 32) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                         *reinterpret_cast<uint4*>(srow + c * 32 + 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    };
+#pragma unroll
+                    for (int jj = 0; jj < SC / 4; ++jj) {          // 32-column TMEM loads, interleaved between the two warps
+                        const int c2 = hq + 2 * jj;
+                        uint32_t v[32];
+                        tc_ld32(t_row + c2 * 32, v);
+                        convert16(v, 2 * c2);
+                        convert16(v + 16, 2 * c2 + 1);
                     }
                 }
                 tc_fence_before();
@@ -346,18 +348,8 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 {
                     const uint32_t t_row = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN);
                     unsigned char* srow = stg16 + (size_t)lane * Cfg::SROW16;
-#pragma unroll
-                    for (int jj = 0; jj < SC / WPL; ++jj) {
-                        if (p.dbg & 2) break;
-                        const int c = q + WPL * jj;
-                        uint32_t v[16];
-                        asm volatile(
-                            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-                            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-                            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                            : "r"(t_row + c * 16));
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    // convert 16 accumulator columns (+ bias, activation) and stage them as 32 B of the row
+                    auto convert16 = [&](const uint32_t* v, int c) {
                         const float4* bp = reinterpret_cast<const float4*>(sbias + c * 16);
                         uint32_t pk[8];
 #pragma unroll
@@ -378,6 +370,28 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         }
                         *reinterpret_cast<uint4*>(srow + c * 32) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                         *reinterpret_cast<uint4*>(srow + c * 32 + 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    };
+                    constexpr bool kX32 = (BN / 32) % WPL == 0;    // 32-column TMEM loads when they split evenly
+                    if constexpr (kX32) {
+#pragma unroll
+                        for (int jj = 0; jj < (BN / 32) / WPL; ++jj) {
+                            if (p.dbg & 2) break;
+                            const int c2 = q + WPL * jj;               // 32-column chunk
+                            uint32_t v[32];
+                            tc_ld32(t_row + c2 * 32, v);
+                            convert16(v, 2 * c2);
+                            convert16(v + 16, 2 * c2 + 1);
+                        }
+                    } else {
+#pragma unroll
+                        for (int jj = 0; jj < SC / WPL; ++jj) {
+                            if (p.dbg & 2) break;
+                            const int c = q + WPL * jj;
+                            uint32_t v[16];
+                            tc_ld16_nowait(t_row + c * 16, v);
+                            tc_wait_ld16(v);
+                            convert16(v, c);
+                        }
                     }
                 }
                 tc_fence_before();
@@ -409,9 +423,11 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 // (the bar.sync at the top of the group's next tile also protects the staging rows)
             }
         } else {
-        const int ew = warp - 2;                               // 0..7
+        constexpr int WPL = Cfg::EPI_WARPS / 4;                // warps per TMEM lane group (2 or 4)
+        constexpr int RPW = 32 / WPL;                          // rows per warp in phase R (16 or 8)
+        const int ew = warp - 2;                               // 0 .. EPI_WARPS-1
         const int lg = warp & 3;                               // TMEM lane group this warp may access
-        const int half = ew >> 2;                              // column half in phase T, row half in phase R
+        const int half = ew >> 2;                              // which column chunks in phase T, which rows in phase R
         float* stg = reinterpret_cast<float*>(tc_smem_raw + (stg_base - raw)) + (size_t)(lg * 32) * Cfg::SROW;
         constexpr int NP = BN / 64;                            // column pairs per lane
         constexpr bool kRes = EPI == E_RES_LN || EPI == E_RES;
@@ -430,12 +446,12 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 lnb[k] = n < g.ln_C ? __ldg(reinterpret_cast<const float2*>(g.ln_b + n)) : make_float2(0.f, 0.f);
             }
         }
-        // row bookkeeping of one tile: lane i (< 16) describes row i of this warp's phase-R rows
+        // row bookkeeping of one tile: lane i (< RPW) describes row i of this warp's phase-R rows
         auto rows_of = [&](int tile_, int& m_, int& r32_, int& r16_) {
             m_ = -1; r32_ = 0; r16_ = 0;
             if (tile_ >= total_tiles) return;
             const int mt_ = tile_ / p.n_tiles;
-            m_ = lane < 16 ? tile_row_to_m(p, mt_, lg * 32 + half * 16 + lane) : -1;
+            m_ = lane < RPW ? tile_row_to_m(p, mt_, lg * 32 + half * RPW + lane) : -1;
             if (m_ >= 0) {
                 r32_ = (has_res || g.out32 || has_ln) ? row32_of(g, m_) : m_;
                 r16_ = m_;
@@ -451,13 +467,13 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         // residual rows live in registers and are software-pipelined one tile ahead: as soon as
         // row i of the current tile is finished, row i of the NEXT tile is requested into the
         // same registers, so the HBM latency hides behind the rest of phase R + the next phase T
-        float2 resv[kPrefetch ? 16 : 1][NP];
+        float2 resv[kPrefetch ? RPW : 1][NP];
         int my_m, my_r32, my_r16;
         rows_of(blockIdx.x, my_m, my_r32, my_r16);
         if (kPrefetch) {
             const int n0f = (blockIdx.x % p.n_tiles) * BN;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
+            for (int i = 0; i < RPW; ++i) {
                 const int m = __shfl_sync(0xffffffffu, my_m, i);
                 const int r32 = __shfl_sync(0xffffffffu, my_r32, i);
                 const float* rr = g.res + (size_t)r32 * g.ld32 + n0f + 2 * lane;
@@ -483,20 +499,33 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             {
                 const uint32_t t_row = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN);
                 float* srow = stg + (size_t)lane * Cfg::SROW;
-                constexpr int CH = BN / 32;                    // 32-column chunks in the tile
+                constexpr int SC = BN / 16;                    // 16-column sub-chunks, interleaved between the WPL warps
+                if constexpr (WPL == 2) {
+                    constexpr int CH = BN / 32;                // 32-column chunks, interleaved between the two warps
 #pragma unroll 1
-                for (int c = half; c < CH; c += 2) {           // chunks interleaved between the two warps
-                    uint32_t v[32];
-                    tc_ld32(t_row + c * 32, v);
+                    for (int c = half; c < CH; c += 2) {       // (measured: x32 loads beat pipelined x16 loads here)
+                        uint32_t v[32];
+                        tc_ld32(t_row + c * 32, v);
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<uint4*>(srow + c * 32 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<uint4*>(srow + c * 32 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    }
+                } else {
+#pragma unroll 1
+                    for (int c = half; c < SC; c += WPL) {
+                        uint32_t v[16];
+                        tc_ld16_nowait(t_row + c * 16, v);
+                        tc_wait_ld16(v);
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4)
+                            *reinterpret_cast<uint4*>(srow + c * 16 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    }
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(as));        // accumulator stage drained
-            asm volatile("bar.sync %0, 64;" ::"r"(1 + lg) : "memory");   // both halves staged
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + lg), "n"(32 * WPL) : "memory");   // the lane group is staged
 
             // ---- phase R: staged rows -> global (lane = column pair) ----
             auto process_row = [&](const int i, float2 (&rslot)[NP]) {
@@ -504,7 +533,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 const int r32 = __shfl_sync(0xffffffffu, my_r32, i);
                 const int r16 = __shfl_sync(0xffffffffu, my_r16, i);
                 const bool valid = m >= 0;                     // predicate the stores, keep one basic block
-                const float* srow = stg + (size_t)(half * 16 + i) * Cfg::SROW;
+                const float* srow = stg + (size_t)(half * RPW + i) * Cfg::SROW;
                 float2 v[NP];
 #pragma unroll
                 for (int k = 0; k < NP; ++k) {
@@ -588,12 +617,12 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             };
             if constexpr (kPrefetch) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) process_row(i, resv[i]);
+                for (int i = 0; i < RPW; ++i) process_row(i, resv[i]);
             } else {
 #pragma unroll 2
-                for (int i = 0; i < 16; ++i) process_row(i, resv[0]);
+                for (int i = 0; i < RPW; ++i) process_row(i, resv[0]);
             }
-            asm volatile("bar.sync %0, 64;" ::"r"(1 + lg) : "memory");   // staging free for the next tile
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + lg), "n"(32 * WPL) : "memory");   // staging free for the next tile
             my_m = nx_m; my_r32 = nx_r32; my_r16 = nx_r16;
         }
         }  // !kStage16
