@@ -38,6 +38,9 @@ struct TcParams {
     int dbg;      // SRK_TC5_DBG (profiling experiments only): 1 skip phase R, 2 skip phase T body, 4 skip MMAs
 };
 
+#ifndef SRK_LN_ROW_BATCH
+#define SRK_LN_ROW_BATCH 2                                 // E_RES_LN epilogue: rows processed together (measured: 2 is best, 4 spills)
+#endif
 #ifndef SRK_FP32_EPI_WARPS
 #define SRK_FP32_EPI_WARPS 8                               // epilogue warps of the fp32 (residual / LayerNorm) path: 8 or 16 (measured: 16 is 6 % slower, 96-register cap)
 #endif
@@ -615,7 +618,81 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     }
                 }
             };
-            if constexpr (kPrefetch) {
+            // E_RES_LN: RB rows per step, their LayerNorm butterflies interleaved stage by stage (the
+            // 2 x 5 dependent shuffles of one row are the longest latency chain of phase R)
+            constexpr int RB = SRK_LN_ROW_BATCH;                   // rows whose butterflies are interleaved
+            auto process_rows = [&](const int i0) {
+                int m[RB], r32[RB], r16[RB];
+                float2 v[RB][NP];
+#pragma unroll
+                for (int r = 0; r < RB; ++r) {
+                    m[r] = __shfl_sync(0xffffffffu, my_m, i0 + r);
+                    r32[r] = __shfl_sync(0xffffffffu, my_r32, i0 + r);
+                    r16[r] = __shfl_sync(0xffffffffu, my_r16, i0 + r);
+                    const float* srow = stg + (size_t)(half * RPW + i0 + r) * Cfg::SROW;
+                    float2 (&rs)[NP] = resv[kPrefetch ? i0 + r : 0];
+#pragma unroll
+                    for (int k = 0; k < NP; ++k) {
+                        v[r][k] = *reinterpret_cast<const float2*>(srow + 64 * k + 2 * lane);
+                        v[r][k].x = actf<ACT>(v[r][k].x + bia[k].x) * g.res_scale + rs[k].x;
+                        v[r][k].y = actf<ACT>(v[r][k].y + bia[k].y) * g.res_scale + rs[k].y;
+                    }
+                    // request row i of the next tile into the same registers
+                    const int mx = __shfl_sync(0xffffffffu, nx_m, i0 + r);
+                    const int rx = __shfl_sync(0xffffffffu, nx_r32, i0 + r);
+                    const float* rn = g.res + (size_t)rx * g.ld32 + n0x + 2 * lane;
+#pragma unroll
+                    for (int k = 0; k < NP; ++k)
+                        rs[k] = mx >= 0 ? __ldg(reinterpret_cast<const float2*>(rn + 64 * k)) : make_float2(0.f, 0.f);
+                    if (m[r] >= 0) {
+                        float* oo = g.out32 + (size_t)r32[r] * g.ld32 + n0 + 2 * lane;
+#pragma unroll
+                        for (int k = 0; k < NP; ++k) *reinterpret_cast<float2*>(oo + 64 * k) = v[r][k];
+                    }
+                }
+                float sm[RB], mean[RB], q[RB];
+#pragma unroll
+                for (int r = 0; r < RB; ++r) {
+                    sm[r] = 0.f;
+#pragma unroll
+                    for (int k = 0; k < NP; ++k) sm[r] += v[r][k].x + v[r][k].y;     // pad columns are exactly 0
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                    for (int r = 0; r < RB; ++r) sm[r] += __shfl_xor_sync(0xffffffffu, sm[r], o);
+#pragma unroll
+                for (int r = 0; r < RB; ++r) {
+                    mean[r] = sm[r] * inv_c; q[r] = 0.f;
+#pragma unroll
+                    for (int k = 0; k < NP; ++k) {
+                        if (64 * k + 2 * lane < g.ln_C) {
+                            const float a0 = v[r][k].x - mean[r], a1 = v[r][k].y - mean[r];
+                            q[r] += a0 * a0 + a1 * a1;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                    for (int r = 0; r < RB; ++r) q[r] += __shfl_xor_sync(0xffffffffu, q[r], o);
+#pragma unroll
+                for (int r = 0; r < RB; ++r) {
+                    const float rstd = rsqrtf(q[r] * inv_c + 1e-5f);
+                    uint16_t* oo = g.out16 + (size_t)r16[r] * g.ld16 + 2 * lane;
+#pragma unroll
+                    for (int k = 0; k < NP; ++k) {
+                        const bool in = 64 * k + 2 * lane < g.ln_C;
+                        const float y0 = in ? (v[r][k].x - mean[r]) * rstd * lng[k].x + lnb[k].x : 0.f;
+                        const float y1 = in ? (v[r][k].y - mean[r]) * rstd * lng[k].y + lnb[k].y : 0.f;
+                        if (m[r] >= 0) *reinterpret_cast<uint32_t*>(oo + 64 * k) = packf<DT>(y0, y1);
+                    }
+                }
+            };
+            if constexpr (kPrefetch && EPI == E_RES_LN) {
+#pragma unroll
+                for (int i = 0; i < RPW; i += RB) process_rows(i);
+            } else if constexpr (kPrefetch) {
 #pragma unroll
                 for (int i = 0; i < RPW; ++i) process_row(i, resv[i]);
             } else {
