@@ -40,7 +40,8 @@ typedef enum {
 /* 16-bit operand formats of the tensor-core GEMMs */
 enum { SRK_BF16 = 0, SRK_FP16 = 1 };
 /* epilogue activations */
-enum { SRK_ACT_NONE = 0, SRK_ACT_GELU = 1, SRK_ACT_LRELU = 2, SRK_ACT_RELU = 3 };
+enum { SRK_ACT_NONE = 0, SRK_ACT_GELU = 1, SRK_ACT_LRELU = 2 /* slope 0.01 */, SRK_ACT_RELU = 3,
+       SRK_ACT_LRELU02 = 4 /* slope 0.2 */ };
 /* A-operand addressing of srk_gemm */
 enum { SRK_A_ROWS = 0, SRK_A_CONV3X3 = 1 };
 /* 16-bit output addressing of srk_gemm */
@@ -48,7 +49,7 @@ enum { SRK_O16_ROWS = 0, SRK_O16_PIXSHUF2 = 1 };
 /* GEMM engines: tcgen05/TMEM/TMA (product path) and the legacy mma.sync kernel that is kept
  * as the in-library cross-check of the former (tests only) */
 enum { SRK_ENGINE_TCGEN05 = 0, SRK_ENGINE_MMA_SYNC = 1 };
-enum { SRK_UPSAMPLER_PIXELSHUFFLE = 0, SRK_UPSAMPLER_PIXELSHUFFLEDIRECT = 1 };
+enum { SRK_UPSAMPLER_PIXELSHUFFLE = 0, SRK_UPSAMPLER_PIXELSHUFFLEDIRECT = 1, SRK_UPSAMPLER_NEAREST_CONV = 2 };
 
 const char* srk_last_error(void);
 int srk_version(void);
@@ -272,6 +273,17 @@ typedef struct {
     const void* conv_last_w; float conv_last_b;      /* (9,64) fp16 */
     int linear_dtype, conv_dtype;                    /* SRK_BF16 / SRK_FP16 */
     srk_tail_fold tail_fold;                         /* pixelshuffle only; w == NULL: run the convs one by one */
+    /* resi_connection '3conv' (network_swinir.py:545-552, 874-884): the RSTB conv / conv_after_body is
+     * Conv3x3(C -> C/4) + LeakyReLU(0.2) + Conv1x1(C/4 -> C/4) + LeakyReLU(0.2) + Conv3x3(C/4 -> C).
+     * resi_3conv != 0: rstb_c0[l] / rstb_c1[l] (cab_c0 / cab_c1) hold the first two convs (C/4 padded to
+     * 64: n_p = 64; c1 is a (64, 64) row-GEMM weight) and rstb_convs[l] (conv_after_body) the third. */
+    int resi_3conv;
+    const srk_conv_params* rstb_c0; const srk_conv_params* rstb_c1;
+    srk_conv_params cab_c0, cab_c1;
+    /* upsampler 'nearest+conv' (X4, :875-886, 948-961): upsample[0..1] hold conv_up1 / conv_up2 composed
+     * with the nearest x2 interpolation in front of them (a 3x3 conv on the LOW-res grid, 64 -> 4*64 in
+     * PixelShuffle order, packing.pack_conv_nearest2x), conv_hr the 64 -> 64 conv before conv_last. */
+    srk_conv_params conv_hr;
 } srk_swinir_plan;
 
 size_t srk_swinir_workspace_bytes(const srk_swinir_plan* p, int B, int h, int w);

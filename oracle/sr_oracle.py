@@ -231,10 +231,18 @@ def _swin_block(x: Tensor, H: int, W: int, p: Dict[str, Tensor], pre: str, nh: i
 def swinir_forward(sd: Dict[str, Tensor], cfg: SwinIRCfg, x: Tensor,
                    emulate_bf16: bool = False) -> Tensor:
     """SwinIR forward, (B,C,h,w) fp32 in [0,1] -> (B,C,h*s,w*s).  network_swinir.py:930-970.
-    Supported: upsampler in {'pixelshuffle','pixelshuffledirect'}, resi_connection '1conv'."""
+    Supported: upsampler in {'pixelshuffle','pixelshuffledirect','nearest_conv'}, resi_connection
+    '1conv' / '3conv'."""
     emu = emulate_bf16
     p = {k: v.float() if v.is_floating_point() else v for k, v in sd.items()}
-    assert cfg.resi_connection == "1conv"
+    assert cfg.resi_connection in ("1conv", "3conv")
+
+    def resi_conv(img, name):                                           # :543-552, 870-884
+        if cfg.resi_connection == "1conv":
+            return _conv3(img, p[name + ".weight"], p[name + ".bias"], emu)
+        t1 = F.leaky_relu(_conv3(img, p[name + ".0.weight"], p[name + ".0.bias"], emu), 0.2)
+        t2 = F.leaky_relu(F.conv2d(_h(t1, emu), _h(p[name + ".2.weight"], emu), p[name + ".2.bias"]), 0.2)
+        return _conv3(t2, p[name + ".4.weight"], p[name + ".4.bias"], emu)
     B, Cin, h0, w0 = x.shape
     wsz = cfg.window_size
     ph, pw = (wsz - h0 % wsz) % wsz, (wsz - w0 % wsz) % wsz
@@ -256,11 +264,11 @@ def swinir_forward(sd: Dict[str, Tensor], cfg: SwinIRCfg, x: Tensor,
             t = _swin_block(t, H, W, p, f"layers.{li}.residual_group.blocks.{bi}.",
                             cfg.num_heads[li], ws, shift, emu)
         img = t.transpose(1, 2).reshape(B, C, H, W)                     # unembed :651-655
-        img = _conv3(img, p[f"layers.{li}.conv.weight"], p[f"layers.{li}.conv.bias"], emu)
+        img = resi_conv(img, f"layers.{li}.conv")
         t = img.flatten(2).transpose(1, 2) + t_in                       # :563-565
     t = F.layer_norm(t, (C,), p["norm.weight"], p["norm.bias"], 1e-5)
     img = t.transpose(1, 2).reshape(B, C, H, W)
-    y = _conv3(img, p["conv_after_body.weight"], p["conv_after_body.bias"], emu) + f0
+    y = resi_conv(img, "conv_after_body") + f0
 
     s = cfg.upscale
     if cfg.upsampler == "pixelshuffle":                                 # :941-942
@@ -277,6 +285,15 @@ def swinir_forward(sd: Dict[str, Tensor], cfg: SwinIRCfg, x: Tensor,
         y = _conv3(y, p["conv_last.weight"], p["conv_last.bias"], emu, "out")
     elif cfg.upsampler == "pixelshuffledirect":                         # :947
         y = F.pixel_shuffle(_conv3(y, p["upsample.0.weight"], p["upsample.0.bias"], emu), s)
+    elif cfg.upsampler == "nearest_conv":                               # :948-961 (X4)
+        assert s == 4
+        y = F.leaky_relu(_conv3(y, p["conv_before_upsample.0.weight"],
+                                p["conv_before_upsample.0.bias"], emu), 0.01)
+        for name in ("conv_up1", "conv_up2"):
+            y = F.interpolate(y, scale_factor=2, mode="nearest")
+            y = F.leaky_relu(_conv3(y, p[name + ".weight"], p[name + ".bias"], emu), 0.2)
+        y = F.leaky_relu(_conv3(y, p["conv_hr.weight"], p["conv_hr.bias"], emu), 0.2)
+        y = _conv3(y, p["conv_last.weight"], p["conv_last.bias"], emu, "out")
     else:
         raise NotImplementedError(cfg.upsampler)
     y = y / cfg.img_range + mean

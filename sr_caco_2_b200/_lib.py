@@ -9,11 +9,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsrk.so")
 
 SRK_BF16, SRK_FP16 = 0, 1
-ACT_NONE, ACT_GELU, ACT_LRELU, ACT_RELU = 0, 1, 2, 3
+ACT_NONE, ACT_GELU, ACT_LRELU, ACT_RELU, ACT_LRELU02 = 0, 1, 2, 3, 4
 A_ROWS, A_CONV3X3 = 0, 1
 O16_ROWS, O16_PIXSHUF2 = 0, 1
 ENGINE_TCGEN05, ENGINE_MMA_SYNC = 0, 1
-UPSAMPLER_PIXELSHUFFLE, UPSAMPLER_PIXELSHUFFLEDIRECT = 0, 1
+UPSAMPLER_PIXELSHUFFLE, UPSAMPLER_PIXELSHUFFLEDIRECT, UPSAMPLER_NEAREST_CONV = 0, 1, 2
 MET_PSNR, MET_MSE, MET_NRMSE, MET_SSIM, MET_PSNR_Y, MET_N = 0, 1, 2, 3, 4, 5
 MAX_ROI_THS = 8
 
@@ -67,7 +67,9 @@ class SwinIRPlan(C.Structure):
                 ("conv_after_body", ConvParams), ("conv_before_upsample", ConvParams),
                 ("upsample", ConvParams * 4), ("n_upsample", C.c_int),
                 ("conv_last_w", fp), ("conv_last_b", C.c_float),
-                ("linear_dtype", C.c_int), ("conv_dtype", C.c_int), ("tail_fold", TailFold)]
+                ("linear_dtype", C.c_int), ("conv_dtype", C.c_int), ("tail_fold", TailFold),
+                ("resi_3conv", C.c_int), ("rstb_c0", C.POINTER(ConvParams)), ("rstb_c1", C.POINTER(ConvParams)),
+                ("cab_c0", ConvParams), ("cab_c1", ConvParams), ("conv_hr", ConvParams)]
 
 
 class EDSRPlan(C.Structure):

@@ -182,6 +182,7 @@ __device__ __forceinline__ float gelu_erf(float x) {
 __device__ __forceinline__ float apply_act(float v, int act) {
     if (act == SRK_ACT_GELU) return gelu_erf(v);
     if (act == SRK_ACT_LRELU) return v > 0.f ? v : 0.01f * v;
+    if (act == SRK_ACT_LRELU02) return v > 0.f ? v : 0.2f * v;
     if (act == SRK_ACT_RELU) return fmaxf(v, 0.f);
     return v;
 }

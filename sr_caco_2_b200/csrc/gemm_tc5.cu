@@ -804,6 +804,7 @@ static int dispatch_tc5(const srk_gemm_args* a, const CUtensorMap& ma, const CUt
         if (act == SRK_ACT_GELU && dt == SRK_BF16) return launch_tc5<BN, E_O16, SRK_ACT_GELU, SRK_BF16>(ma, mb, p, st);
         if (act == SRK_ACT_LRELU && dt == SRK_FP16) return launch_tc5<BN, E_O16, SRK_ACT_LRELU, SRK_FP16>(ma, mb, p, st);
         if (act == SRK_ACT_RELU && dt == SRK_FP16) return launch_tc5<BN, E_O16, SRK_ACT_RELU, SRK_FP16>(ma, mb, p, st);
+        if (act == SRK_ACT_LRELU02 && dt == SRK_FP16) return launch_tc5<BN, E_O16, SRK_ACT_LRELU02, SRK_FP16>(ma, mb, p, st);
     }
     if (!img && res && ln && act == SRK_ACT_NONE && dt == SRK_BF16)
         return launch_tc5<BN, E_RES_LN, SRK_ACT_NONE, SRK_BF16>(ma, mb, p, st);
@@ -813,6 +814,8 @@ static int dispatch_tc5(const srk_gemm_args* a, const CUtensorMap& ma, const CUt
         return launch_tc5<BN, E_RES, SRK_ACT_NONE, SRK_FP16>(ma, mb, p, st);
     if (!img && !res && !o32 && ps && act == SRK_ACT_NONE && dt == SRK_FP16)
         return launch_tc5<BN, E_PIXSHUF, SRK_ACT_NONE, SRK_FP16>(ma, mb, p, st);
+    if (!img && !res && !o32 && ps && act == SRK_ACT_LRELU02 && dt == SRK_FP16)
+        return launch_tc5<BN, E_PIXSHUF, SRK_ACT_LRELU02, SRK_FP16>(ma, mb, p, st);
     return launch_tc5<BN, E_GENERIC, 0, 0>(ma, mb, p, st);
 }
 
@@ -832,7 +835,7 @@ int gemm_tcgen05(const srk_gemm_args* a, cudaStream_t st) {
     TcParams p{};
     p.g = make_gemm_params(a);
     const bool ps256 = a->out16 && a->out16_mode == SRK_O16_PIXSHUF2 && !a->res && !a->out32 && !a->img && !a->ln_g &&
-                       a->act == SRK_ACT_NONE && a->out16_dtype == SRK_FP16 && a->N % 256 == 0;
+                       (a->act == SRK_ACT_NONE || a->act == SRK_ACT_LRELU02) && a->out16_dtype == SRK_FP16 && a->N % 256 == 0;
     const int BN = ps256 ? 256 : (a->N % 192 == 0 ? 192 : (a->N % 128 == 0 ? 128 : 64));
     if (a->ln_g) {
         SRK_REQUIRE(a->N == BN, "gemm(tcgen05): fused LayerNorm needs the whole row in one tile (N=%d)", a->N);
@@ -878,7 +881,8 @@ int gemm_tcgen05(const srk_gemm_args* a, cudaStream_t st) {
     }
     if (attn) return launch_tc5<192, E_ATTN, SRK_ACT_NONE, SRK_BF16>(ma, mb, p, st);
     switch (BN) {
-        case 256: return launch_tc5<256, E_PIXSHUF, SRK_ACT_NONE, SRK_FP16>(ma, mb, p, st);
+        case 256: return a->act == SRK_ACT_LRELU02 ? launch_tc5<256, E_PIXSHUF, SRK_ACT_LRELU02, SRK_FP16>(ma, mb, p, st)
+                                                   : launch_tc5<256, E_PIXSHUF, SRK_ACT_NONE, SRK_FP16>(ma, mb, p, st);
         case 192: return dispatch_tc5<192>(a, ma, mb, p, st);
         case 128: return dispatch_tc5<128>(a, ma, mb, p, st);
         default: return dispatch_tc5<64>(a, ma, mb, p, st);

@@ -22,6 +22,7 @@ static inline int pad8(int v) { return (v + 7) / 8 * 8; }
 struct SwinBufs {
     float *F0, *XA, *XB;
     void *A16, *QKV, *AO, *HID, *Y1, *U[5];
+    void *T1, *T2;                    // '3conv': the two C/4-channel (padded to 64) intermediates
     int nq_p;
 };
 
@@ -45,7 +46,12 @@ static size_t swin_layout(const srk_swinir_plan* p, int B, int H, int W, char* b
     if (p->upsampler == SRK_UPSAMPLER_PIXELSHUFFLE) {
         size_t m = M;
         for (int k = 0; k <= p->n_upsample; ++k) { b->U[k] = a.take(m * 64 * 2); m *= 4; }
+    } else if (p->upsampler == SRK_UPSAMPLER_NEAREST_CONV) {
+        b->U[0] = a.take(M * 64 * 2); b->U[1] = a.take(M * 4 * 64 * 2);
+        b->U[2] = a.take(M * 16 * 64 * 2); b->U[3] = a.take(M * 16 * 64 * 2);
     }
+    b->T1 = b->T2 = nullptr;
+    if (p->resi_3conv) { b->T1 = a.take(M * 64 * 2); b->T2 = a.take(M * 64 * 2); }
     return align_up(a.off, 256);
 }
 
@@ -56,11 +62,16 @@ static int check_swin_plan(const srk_swinir_plan* p) {
     if (p->upsampler == SRK_UPSAMPLER_PIXELSHUFFLE) {
         SRK_REQUIRE(p->n_upsample >= 0 && p->n_upsample <= 4 && (1 << p->n_upsample) == p->upscale,
                     "swinir: pixelshuffle needs upscale = 2^n (n <= 4)");
+    } else if (p->upsampler == SRK_UPSAMPLER_NEAREST_CONV) {
+        SRK_REQUIRE(p->upscale == 4 && p->n_upsample == 2 && p->conv_hr.w && p->conv_last_w, "swinir: nearest+conv is built for X4");
     } else if (p->upsampler == SRK_UPSAMPLER_PIXELSHUFFLEDIRECT) {
         SRK_REQUIRE(p->n_upsample == 1 && p->upscale * p->upscale <= 64, "swinir: direct upsampler needs scale <= 8");
     } else {
         return fail(SRK_ERR_UNSUPPORTED, "swinir: upsampler %d not built", p->upsampler);
     }
+    if (p->resi_3conv)
+        SRK_REQUIRE(p->rstb_c0 && p->rstb_c1 && p->cab_c0.w && p->cab_c1.w && p->embed_dim / 4 <= 64,
+                    "swinir: '3conv' needs the two extra convs per RSTB and embed_dim / 4 <= 64");
     SRK_REQUIRE(p->Cp % 64 == 0 && p->Cp >= p->embed_dim && p->hid_p % 64 == 0 && p->hid_p >= p->hidden_dim &&
                 p->dp % 16 == 0 && p->ao_p % 64 == 0 && p->embed_dim % 4 == 0, "swinir: bad padded dims");
     return 0;
@@ -127,6 +138,19 @@ extern "C" int srk_swinir_forward(const srk_swinir_plan* p, const float* x, floa
         g.Wt = Wt; g.M = M; g.N = N; g.K = K; g.dtype = ldt; g.bias = bias; g.act = SRK_ACT_NONE;
         g.res_scale = 1.f; g.win_shift = -1; g.ln_win_shift = -1; g.out16_dtype = ldt;
         return g;
+    };
+
+    // resi_connection '3conv': Conv3x3(C -> C/4) + LeakyReLU(0.2) + Conv1x1 + LeakyReLU(0.2) in front of the
+    // last conv; both intermediates are (M, 64) fp16 (C/4 zero-padded to 64)
+    auto three_conv_head = [&](const void* A, const srk_conv_params& c0, const srk_conv_params& c1) -> int {
+        srk_gemm_args g0 = conv_gemm(A, Cp, H, W, c0);
+        g0.act = SRK_ACT_LRELU02; g0.out16 = b.T1; g0.ld16 = 64;
+        if (int rc = srk_gemm(&g0, stream)) return rc;
+        srk_gemm_args g1{};
+        g1.A = b.T1; g1.a_mode = SRK_A_ROWS; g1.lda = 64; g1.nB = B; g1.H = H; g1.W = W;
+        g1.Wt = c1.w; g1.M = M; g1.N = 64; g1.K = 64; g1.dtype = cdt; g1.bias = c1.b; g1.act = SRK_ACT_LRELU02;
+        g1.res_scale = 1.f; g1.win_shift = -1; g1.ln_win_shift = -1; g1.out16 = b.T2; g1.ld16 = 64; g1.out16_dtype = cdt;
+        return srk_gemm(&g1, stream);
     };
 
     // conv_first (+ reflect pad + input scaling), patch_embed.norm
@@ -242,7 +266,9 @@ extern "C" int srk_swinir_forward(const srk_swinir_plan* p, const float* x, floa
         // RSTB tail conv + residual with the RSTB input  [+ fused LN: norm1 of the next RSTB's
         // first block (window order), or the final `norm` after the last RSTB (token order)]
         {
-            srk_gemm_args g = conv_gemm(a16, Cp, H, W, p->rstb_convs[l]);
+            if (p->resi_3conv) TRY(three_conv_head(a16, p->rstb_c0[l], p->rstb_c1[l]));
+            srk_gemm_args g = p->resi_3conv ? conv_gemm(b.T2, 64, H, W, p->rstb_convs[l])
+                                            : conv_gemm(a16, Cp, H, W, p->rstb_convs[l]);
             g.res = b.XA; g.out32 = b.XA; g.ld32 = Cp;
             bool swap_after = false;
             if (fuse_ln) {
@@ -269,7 +295,9 @@ extern "C" int srk_swinir_forward(const srk_swinir_plan* p, const float* x, floa
     const float out_scale = 1.f / p->img_range;
     const int s_up = p->upscale;
     {
-        srk_gemm_args g = conv_gemm(normed, Cp, H, W, p->conv_after_body);
+        if (p->resi_3conv) TRY(three_conv_head(normed, p->cab_c0, p->cab_c1));
+        srk_gemm_args g = p->resi_3conv ? conv_gemm(b.T2, 64, H, W, p->conv_after_body)
+                                        : conv_gemm(normed, Cp, H, W, p->conv_after_body);
         g.res = b.F0; g.ld32 = Cp; g.out16 = y1; g.ld16 = Cp;
         TRY(srk_gemm(&g, stream));
     }
@@ -292,6 +320,27 @@ extern "C" int srk_swinir_forward(const srk_swinir_plan* p, const float* x, floa
             TRY(srk_conv_out(b.U[p->n_upsample], 64, B, Hh, Ww, 64, p->conv_last_w, p->conv_last_b,
                              out_scale, y, h * s_up, w * s_up, stream));
         }
+    } else if (p->upsampler == SRK_UPSAMPLER_NEAREST_CONV) {
+        // conv_before_upsample + LeakyReLU; 2 x [nearest x2 + conv + LeakyReLU(0.2)] as composed low-res convs
+        // with the PixelShuffle epilogue; conv_hr + LeakyReLU(0.2); conv_last   (network_swinir.py:948-961)
+        {
+            srk_gemm_args g = conv_gemm(y1, Cp, H, W, p->conv_before_upsample);
+            g.act = SRK_ACT_LRELU; g.out16 = b.U[0]; g.ld16 = 64;
+            TRY(srk_gemm(&g, stream));
+        }
+        int Hh = H, Ww = W;
+        for (int k = 0; k < 2; ++k) {
+            srk_gemm_args g = conv_gemm(b.U[k], 64, Hh, Ww, p->upsample[k]);
+            g.act = SRK_ACT_LRELU02; g.out16 = b.U[k + 1]; g.ld16 = 64; g.out16_mode = SRK_O16_PIXSHUF2;
+            TRY(srk_gemm(&g, stream));
+            Hh *= 2; Ww *= 2;
+        }
+        {
+            srk_gemm_args g = conv_gemm(b.U[2], 64, Hh, Ww, p->conv_hr);
+            g.act = SRK_ACT_LRELU02; g.out16 = b.U[3]; g.ld16 = 64;
+            TRY(srk_gemm(&g, stream));
+        }
+        TRY(srk_conv_out(b.U[3], 64, B, Hh, Ww, 64, p->conv_last_w, p->conv_last_b, out_scale, y, h * s_up, w * s_up, stream));
     } else {
         srk_gemm_args g = conv_gemm(y1, Cp, H, W, p->upsample[0]);
         g.img = y; g.img_s = s_up; g.img_scale = out_scale; g.img_hc = h * s_up; g.img_wc = w * s_up;

@@ -162,6 +162,7 @@ template <int ACT>
 __device__ __forceinline__ float actf(float v) {
     if (ACT == SRK_ACT_GELU) return gelu_erf(v);
     if (ACT == SRK_ACT_LRELU) return v > 0.f ? v : 0.01f * v;
+    if (ACT == SRK_ACT_LRELU02) return v > 0.f ? v : 0.2f * v;
     if (ACT == SRK_ACT_RELU) return fmaxf(v, 0.f);
     return v;
 }

@@ -10,8 +10,11 @@ forward of its own.  `SwinIR.forward` repacks the weights once (padded 16-bit GE
 and issues one `srk_swinir_forward` call: hand-written sm_100a kernels, no PyTorch ops on the
 hot path, no CPU / eager fallback (a CPU tensor raises).
 
-Built: in_chans == 1, window_size == 8, upsampler in {'pixelshuffle', 'pixelshuffledirect'},
-resi_connection '1conv', eval mode.  Anything else raises NotImplementedError at construction.
+Built: in_chans == 1, window_size == 8, upsampler in {'pixelshuffle', 'pixelshuffledirect',
+'nearest_conv' (X4)}, resi_connection '1conv' / '3conv', eval mode.  Anything else raises
+NotImplementedError at construction.  'nearest_conv' runs each nearest x2 + Conv3x3 pair as one
+3x3 conv on the low-res grid with the PixelShuffle epilogue (packing.pack_conv_nearest2x); '3conv'
+adds a C -> C/4 conv, a 1x1 row GEMM and LeakyReLU(0.2) epilogues in front of the RSTB conv.
 """
 from __future__ import annotations
 
@@ -27,7 +30,9 @@ from . import packing as P
 
 US_PIXEL_SHUFFLE = "pixelshuffle"              # dlib/utils/constants.py:91-93
 US_PIXEL_SHUFFLE_DIRECT = "pixelshuffledirect"
+US_NEAREST_CONV = "nearest_conv"               # dlib/utils/constants.py:93
 R_CONNECTION_1CONV = "1conv"
+R_CONNECTION_3CONV = "3conv"                   # dlib/utils/constants.py:96
 
 
 def _to_2tuple(v):
@@ -82,10 +87,14 @@ class SwinIR(nn.Module):
                                       "microscopy patches) is built")
         if window_size != 8:
             raise NotImplementedError("sr_caco_2_b200.SwinIR: only window_size == 8 is built")
-        if upsampler not in (US_PIXEL_SHUFFLE, US_PIXEL_SHUFFLE_DIRECT):
+        if upsampler not in (US_PIXEL_SHUFFLE, US_PIXEL_SHUFFLE_DIRECT, US_NEAREST_CONV):
             raise NotImplementedError(f"sr_caco_2_b200.SwinIR: upsampler {upsampler!r} not built")
-        if resi_connection != R_CONNECTION_1CONV:
-            raise NotImplementedError("sr_caco_2_b200.SwinIR: only resi_connection '1conv' is built")
+        if upsampler == US_NEAREST_CONV:
+            assert upscale == 4, 'only support x4 now.'            # network_swinir.py:877
+        if resi_connection not in (R_CONNECTION_1CONV, R_CONNECTION_3CONV):
+            raise NotImplementedError(f"sr_caco_2_b200.SwinIR: resi_connection {resi_connection!r} not built")
+        if resi_connection == R_CONNECTION_3CONV and embed_dim // 4 > 64:
+            raise NotImplementedError("sr_caco_2_b200.SwinIR: '3conv' is built for embed_dim <= 256")
         if patch_size != 1 or ape or not patch_norm or not qkv_bias or qk_scale is not None \
                 or norm_layer is not nn.LayerNorm:
             raise NotImplementedError("sr_caco_2_b200.SwinIR: non-default patch/ape/norm options")
@@ -99,6 +108,7 @@ class SwinIR(nn.Module):
         self.img_range = float(img_range)
         self.mean = torch.zeros(1, 1, 1, 1)
         self.upscale, self.upsampler, self.window_size = upscale, upsampler, window_size
+        self.resi_connection = resi_connection
         self.in_chans, self.embed_dim, self.mlp_ratio = in_chans, embed_dim, mlp_ratio
         self.depths, self.num_heads = list(depths), list(num_heads)
         self.num_layers = len(depths)
@@ -134,11 +144,19 @@ class SwinIR(nn.Module):
                 blk.mlp.fc2 = nn.Linear(hidden, embed_dim)
                 blk.register_buffer("attn_mask", _shift_mask(res, ws, shift) if shift > 0 else None)
                 rstb.residual_group.blocks.append(blk)
-            rstb.conv = nn.Conv2d(embed_dim, embed_dim, 3, 1, 1)
+            rstb.conv = self._resi_conv(embed_dim, resi_connection)
             self.layers.append(rstb)
         self.norm = nn.LayerNorm(embed_dim)
-        self.conv_after_body = nn.Conv2d(embed_dim, embed_dim, 3, 1, 1)
-        if upsampler == US_PIXEL_SHUFFLE:
+        self.conv_after_body = self._resi_conv(embed_dim, resi_connection)
+        if upsampler == US_NEAREST_CONV:                          # network_swinir.py:875-886
+            self.conv_before_upsample = nn.Sequential(nn.Conv2d(embed_dim, num_feat, 3, 1, 1),
+                                                      nn.LeakyReLU(inplace=True))
+            self.conv_up1 = nn.Conv2d(num_feat, num_feat, 3, 1, 1)
+            self.conv_up2 = nn.Conv2d(num_feat, num_feat, 3, 1, 1)
+            self.conv_hr = nn.Conv2d(num_feat, num_feat, 3, 1, 1)
+            self.conv_last = nn.Conv2d(num_feat, in_chans, 3, 1, 1)
+            self.lrelu = nn.LeakyReLU(negative_slope=0.2, inplace=True)
+        elif upsampler == US_PIXEL_SHUFFLE:
             self.conv_before_upsample = nn.Sequential(nn.Conv2d(embed_dim, num_feat, 3, 1, 1),
                                                       nn.LeakyReLU(inplace=True))
             ups = []
@@ -160,6 +178,14 @@ class SwinIR(nn.Module):
         self._keep = None
         self._ws = None
         self.register_load_state_dict_post_hook(lambda mod, keys: mod._invalidate())
+
+    @staticmethod
+    def _resi_conv(dim, resi_connection):                          # network_swinir.py:543-552, 870-884
+        if resi_connection == R_CONNECTION_1CONV:
+            return nn.Conv2d(dim, dim, 3, 1, 1)
+        return nn.Sequential(nn.Conv2d(dim, dim // 4, 3, 1, 1), nn.LeakyReLU(negative_slope=0.2, inplace=True),
+                             nn.Conv2d(dim // 4, dim // 4, 1, 1, 0), nn.LeakyReLU(negative_slope=0.2, inplace=True),
+                             nn.Conv2d(dim // 4, dim, 3, 1, 1))
 
     # ---- packed-weight cache --------------------------------------------------------------
     def _invalidate(self):
@@ -191,6 +217,9 @@ class SwinIR(nn.Module):
         nblk = sum(self.depths)
         stbs = (L.StbParams * max(nblk, 1))()
         convs = (L.ConvParams * max(self.num_layers, 1))()
+        three = self.resi_connection == R_CONNECTION_3CONV
+        convs0 = (L.ConvParams * max(self.num_layers, 1))()
+        convs1 = (L.ConvParams * max(self.num_layers, 1))()
         depths = (C.c_int * max(self.num_layers, 1))(*self.depths)
         bi_flat = 0
         for li, rstb in enumerate(self.layers):
@@ -214,13 +243,22 @@ class SwinIR(nn.Module):
                 s.shift = self._block_geometry[bi_flat][1]
                 s.num_heads = nh
                 bi_flat += 1
-            w, b = P.pack_conv3x3(rstb.conv.weight.detach(), rstb.conv.bias.detach(), Cp, Cp, conv_dtype)
-            convs[li].w, convs[li].b, convs[li].cin_p, convs[li].n_p = k(w), k(b), Cp, Cp
+            if three:
+                c0, c1, c2 = rstb.conv[0], rstb.conv[2], rstb.conv[4]
+                w, b = P.pack_conv3x3(c0.weight.detach(), c0.bias.detach(), Cp, 64, conv_dtype)
+                convs0[li].w, convs0[li].b, convs0[li].cin_p, convs0[li].n_p = k(w), k(b), Cp, 64
+                convs1[li].w = k(P.pack_linear(c1.weight.detach()[:, :, 0, 0], 64, 64, conv_dtype))
+                convs1[li].b, convs1[li].cin_p, convs1[li].n_p = k(P.pad_bias(c1.bias.detach(), 64)), 64, 64
+                w, b = P.pack_conv3x3(c2.weight.detach(), c2.bias.detach(), 64, Cp, conv_dtype)
+                convs[li].w, convs[li].b, convs[li].cin_p, convs[li].n_p = k(w), k(b), 64, Cp
+            else:
+                w, b = P.pack_conv3x3(rstb.conv.weight.detach(), rstb.conv.bias.detach(), Cp, Cp, conv_dtype)
+                convs[li].w, convs[li].b, convs[li].cin_p, convs[li].n_p = k(w), k(b), Cp, Cp
         plan = L.SwinIRPlan()
         plan.upscale, plan.in_chans, plan.window_size = self.upscale, self.in_chans, self.window_size
         plan.embed_dim, plan.hidden_dim, plan.n_layers = Cdim, hid, self.num_layers
-        plan.upsampler = (L.UPSAMPLER_PIXELSHUFFLE if self.upsampler == US_PIXEL_SHUFFLE
-                          else L.UPSAMPLER_PIXELSHUFFLEDIRECT)
+        plan.upsampler = {US_PIXEL_SHUFFLE: L.UPSAMPLER_PIXELSHUFFLE, US_NEAREST_CONV: L.UPSAMPLER_NEAREST_CONV,
+                          US_PIXEL_SHUFFLE_DIRECT: L.UPSAMPLER_PIXELSHUFFLEDIRECT}[self.upsampler]
         plan.img_range = self.img_range
         plan.Cp, plan.hid_p, plan.dp, plan.ao_p = Cp, hid_p, dp, ao_p
         plan.depths, plan.stbs, plan.rstb_convs = depths, stbs, convs
@@ -230,9 +268,31 @@ class SwinIR(nn.Module):
         plan.pe_norm_b = k(self.patch_embed.norm.bias.detach().float().contiguous())
         plan.norm_g = k(self.norm.weight.detach().float().contiguous())
         plan.norm_b = k(self.norm.bias.detach().float().contiguous())
-        w, b = P.pack_conv3x3(self.conv_after_body.weight.detach(), self.conv_after_body.bias.detach(), Cp, Cp, conv_dtype)
-        plan.conv_after_body = L.ConvParams(k(w), k(b), Cp, Cp)
-        if self.upsampler == US_PIXEL_SHUFFLE:
+        if three:
+            c0, c1, c2 = self.conv_after_body[0], self.conv_after_body[2], self.conv_after_body[4]
+            w, b = P.pack_conv3x3(c0.weight.detach(), c0.bias.detach(), Cp, 64, conv_dtype)
+            plan.cab_c0 = L.ConvParams(k(w), k(b), Cp, 64)
+            plan.cab_c1 = L.ConvParams(k(P.pack_linear(c1.weight.detach()[:, :, 0, 0], 64, 64, conv_dtype)),
+                                       k(P.pad_bias(c1.bias.detach(), 64)), 64, 64)
+            w, b = P.pack_conv3x3(c2.weight.detach(), c2.bias.detach(), 64, Cp, conv_dtype)
+            plan.conv_after_body = L.ConvParams(k(w), k(b), 64, Cp)
+            plan.resi_3conv, plan.rstb_c0, plan.rstb_c1 = 1, convs0, convs1
+        else:
+            w, b = P.pack_conv3x3(self.conv_after_body.weight.detach(), self.conv_after_body.bias.detach(), Cp, Cp, conv_dtype)
+            plan.conv_after_body = L.ConvParams(k(w), k(b), Cp, Cp)
+        if self.upsampler == US_NEAREST_CONV:
+            c0 = self.conv_before_upsample[0]
+            w, b = P.pack_conv3x3(c0.weight.detach(), c0.bias.detach(), Cp, 64, conv_dtype)
+            plan.conv_before_upsample = L.ConvParams(k(w), k(b), Cp, 64)
+            for i, m in enumerate((self.conv_up1, self.conv_up2)):
+                w, b = P.pack_conv_nearest2x(m.weight.detach(), m.bias.detach(), 64, conv_dtype)
+                plan.upsample[i] = L.ConvParams(k(w), k(b), 64, 256)
+            plan.n_upsample = 2
+            w, b = P.pack_conv3x3(self.conv_hr.weight.detach(), self.conv_hr.bias.detach(), 64, 64, conv_dtype)
+            plan.conv_hr = L.ConvParams(k(w), k(b), 64, 64)
+            plan.conv_last_w = k(P.pack_conv_out(self.conv_last.weight.detach()))
+            plan.conv_last_b = float(self.conv_last.bias.detach().float().item())
+        elif self.upsampler == US_PIXEL_SHUFFLE:
             c0 = self.conv_before_upsample[0]
             w, b = P.pack_conv3x3(c0.weight.detach(), c0.bias.detach(), Cp, 64, conv_dtype)
             plan.conv_before_upsample = L.ConvParams(k(w), k(b), Cp, 64)
@@ -255,7 +315,7 @@ class SwinIR(nn.Module):
             plan.upsample[0] = L.ConvParams(k(w), k(b), Cp, 64)
             plan.n_upsample = 1
         plan.linear_dtype, plan.conv_dtype = linear_dtype, conv_dtype
-        keep += [stbs, convs, depths]
+        keep += [stbs, convs, convs0, convs1, depths]
         self._plan, self._keep = plan, keep
         assert all(t.device == dev for t in keep if isinstance(t, torch.Tensor))
 

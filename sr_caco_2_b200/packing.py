@@ -146,3 +146,24 @@ def fold_tail(up_convs, last_w: torch.Tensor, last_b: torch.Tensor, scale: int):
     # (the mma.sync B fragments of a tap become 32 contiguous bytes per lane, elementwise.cu)
     Wb = Wh.view(9, 64, 25, 4, 2, 4, 2).permute(0, 1, 2, 5, 3, 4, 6).reshape(9, 64, 25 * F).contiguous()
     return (Wh[4].contiguous(), Bs[4].contiguous(), Wb, Bs.contiguous(), float(w_scale))
+
+
+def pack_conv_nearest2x(w: torch.Tensor, b: torch.Tensor, cin_p: int, dtype_code: int):
+    """Conv3x3 applied to a nearest x2 up-sampled image (network_swinir.py:953-960) as ONE 3x3 conv on the
+    LOW-res grid with 4*Cout outputs in PixelShuffle order (i, j, c): output pixel (2y+i, 2x+j) reads
+    up-sampled pixel (2y+i+dy, 2x+j+dx) = low-res pixel (y + (i+dy)//2, x + (j+dx)//2), so the taps that
+    land on the same low-res pixel are summed.  The zero padding of the up-sampled image coincides with
+    the zero padding of the low-res one (row -1 <-> row -1, row 2H <-> row H).
+    w: (Cout, Cin, 3, 3) -> ((4*Cout, 9*cin_p) 16-bit, (4*Cout) fp32 bias)."""
+    cout, cin = w.shape[:2]
+    wf = w.float()
+    comp = torch.zeros(2, 2, cout, 3, 3, cin_p, dtype=torch.float32, device=w.device)   # [i][j][c][oy+1][ox+1][cin]
+    for i in range(2):
+        for j in range(2):
+            for dy in (-1, 0, 1):
+                for dx in (-1, 0, 1):
+                    oy, ox = (i + dy) // 2, (j + dx) // 2
+                    comp[i, j, :, oy + 1, ox + 1, :cin] += wf[:, :, dy + 1, dx + 1]
+    out = comp.reshape(4 * cout, 9 * cin_p)
+    bias = b.float().repeat(4)
+    return out.to(_dt(dtype_code)).contiguous(), bias.contiguous()

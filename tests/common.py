@@ -47,6 +47,21 @@ def _lin(g, sd, name, cout, cin):
     sd[name + ".bias"] = 0.02 * torch.randn(cout, generator=g)
 
 
+def _conv1(g, sd, name, cout, cin):
+    k = 1.0 / math.sqrt(cin)
+    sd[name + ".weight"] = (torch.rand(cout, cin, 1, 1, generator=g) * 2 - 1) * k
+    sd[name + ".bias"] = (torch.rand(cout, generator=g) * 2 - 1) * k
+
+
+def _resi(g, sd, name, C, kind):
+    if kind == "1conv":
+        _conv(g, sd, name, C, C)
+    else:                                       # '3conv', network_swinir.py:545-552
+        _conv(g, sd, name + ".0", C // 4, C)
+        _conv1(g, sd, name + ".2", C // 4, C // 4)
+        _conv(g, sd, name + ".4", C, C // 4)
+
+
 def swinir_state_dict(cfg: O.SwinIRCfg, seed: int = 0) -> Dict[str, torch.Tensor]:
     g = torch.Generator().manual_seed(seed)
     C, sd = cfg.embed_dim, {}
@@ -70,9 +85,9 @@ def swinir_state_dict(cfg: O.SwinIRCfg, seed: int = 0) -> Dict[str, torch.Tensor
             _ln(g, sd, pre + "norm2", C)
             _lin(g, sd, pre + "mlp.fc1", hid, C)
             _lin(g, sd, pre + "mlp.fc2", C, hid)
-        _conv(g, sd, f"layers.{li}.conv", C, C)
+        _resi(g, sd, f"layers.{li}.conv", C, cfg.resi_connection)
     _ln(g, sd, "norm", C)
-    _conv(g, sd, "conv_after_body", C, C)
+    _resi(g, sd, "conv_after_body", C, cfg.resi_connection)
     s = cfg.upscale
     if cfg.upsampler == "pixelshuffle":
         _conv(g, sd, "conv_before_upsample.0", 64, C)
@@ -84,6 +99,11 @@ def swinir_state_dict(cfg: O.SwinIRCfg, seed: int = 0) -> Dict[str, torch.Tensor
         _conv(g, sd, "conv_last", cfg.in_chans, 64)
     elif cfg.upsampler == "pixelshuffledirect":
         _conv(g, sd, "upsample.0", s * s * cfg.in_chans, C)
+    elif cfg.upsampler == "nearest_conv":
+        _conv(g, sd, "conv_before_upsample.0", 64, C)
+        for name in ("conv_up1", "conv_up2", "conv_hr"):
+            _conv(g, sd, name, 64, 64)
+        _conv(g, sd, "conv_last", cfg.in_chans, 64)
     else:
         raise NotImplementedError(cfg.upsampler)
     return sd

@@ -595,7 +595,7 @@ def test_bicubic_baseline_against_reference_golden(L, scale):
 # networks
 # ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("engine", ENGINES)
-@pytest.mark.parametrize("name", ["swinir_tiny_direct", "swinir_tiny_ps"])
+@pytest.mark.parametrize("name", ["swinir_tiny_direct", "swinir_tiny_ps", "swinir_tiny_3conv", "swinir_tiny_nearest"])
 def test_swinir_tiny_against_reference_golden(L, engine, name):
     L.set_engine(engine)
     z, sd, cfgd = load_npz(name)

@@ -67,16 +67,21 @@ def test_unsupported_variants_raise_at_construction():
     with pytest.raises(NotImplementedError):
         SwinIR(in_chans=3, window_size=8, upsampler="pixelshuffle")
     with pytest.raises(NotImplementedError):
-        SwinIR(in_chans=1, window_size=8, upsampler="nearest+conv", upscale=4)
+        SwinIR(in_chans=1, window_size=8, upsampler="nearest+conv", upscale=4)       # not a reference constant
     with pytest.raises(NotImplementedError):
-        SwinIR(in_chans=1, window_size=8, upsampler="pixelshuffle", resi_connection="3conv")
+        SwinIR(in_chans=1, window_size=8, upsampler="", upscale=1)                   # denoising branch: out of scope
+    with pytest.raises(AssertionError):                                              # network_swinir.py:877
+        SwinIR(in_chans=1, window_size=8, upsampler="nearest_conv", upscale=2)
     with pytest.raises(NotImplementedError):   # img_size 4 would shrink the window to 4
         SwinIR(in_chans=1, window_size=8, img_size=4, upsampler="pixelshuffle", upscale=2)
 
 
 @pytest.mark.parametrize("cfg", [T.cfg_light_x2(), T.cfg_classical(8), T.cfg_classical(2),
                                  O.SwinIRCfg(upscale=8, in_chans=1, img_size=8, depths=[2], embed_dim=60,
-                                             num_heads=[6], mlp_ratio=2, upsampler="pixelshuffledirect")])
+                                             num_heads=[6], mlp_ratio=2, upsampler="pixelshuffledirect"),
+                                 O.SwinIRCfg(upscale=4, in_chans=1, img_size=16, depths=[2, 2], embed_dim=60,
+                                             num_heads=[6, 6], mlp_ratio=2, upsampler="nearest_conv",
+                                             resi_connection="3conv")])
 def test_swinir_state_dict_contract(cfg):
     """Key names / shapes / dtypes equal the reference layout (tests/common.py enumerates it and
     test_oracle checks that enumeration against the live reference with strict=True)."""

@@ -111,7 +111,7 @@ def test_metric_known_answers_appendix_b():
     assert abs(float(g[0, 0]) - 1.057566123563447e-06) < 1e-11
 
 
-@pytest.mark.parametrize("name", ["swinir_tiny_direct", "swinir_tiny_ps"])
+@pytest.mark.parametrize("name", ["swinir_tiny_direct", "swinir_tiny_ps", "swinir_tiny_3conv", "swinir_tiny_nearest"])
 def test_swinir_tiny_against_reference_golden(name):
     z, sd, cfgd = load_npz(name)
     cfg = O.SwinIRCfg(**cfgd)
