@@ -429,11 +429,8 @@ int qkv_attention_tcgen05(const srk_gemm_args* a, cudaStream_t st) {
         cuuint32_t box[2] = {64, 64};
         if (int rc = encode_map(&mb, SRK_BF16, 2, a->Wt, dims, strides, box)) return rc;
     }
-    static bool attr = false;
-    if (!attr) {
-        SRK_CUDA(cudaFuncSetAttribute(qkv_attn_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QA_SMEM));
-        attr = true;
-    }
+    static bool attr[64] = {};
+    if (first_use_on_device(attr)) SRK_CUDA(cudaFuncSetAttribute(qkv_attn_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QA_SMEM));
     int grid = (num_sms() / p.n_pairs) * p.n_pairs;
     if (grid > p.m_tiles * p.n_pairs) grid = p.m_tiles * p.n_pairs;
     static int trace = -1;

@@ -47,6 +47,16 @@ struct ProfScope {
     ~ProfScope() { if (on) prof_end(st); }
 };
 
+// per-device one-shot flag for cudaFuncSetAttribute (function attributes are per device): returns true the
+// first time `flags` is asked about the current device
+static inline bool first_use_on_device(bool (&flags)[64]) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return true;
+    if (flags[dev]) return false;
+    flags[dev] = true;
+    return true;
+}
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 

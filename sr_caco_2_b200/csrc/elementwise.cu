@@ -569,11 +569,8 @@ extern "C" int srk_conv_out(const void* a, int lda, int B, int H, int W, int Cin
     cudaStream_t st = (cudaStream_t)stream;
     ProfScope ps(SRK_PROF_CONV_OUT, stream);
     const size_t smem = 2 * (size_t)CO_TILE_BYTES + 8 * 3 * 48 * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
-        SRK_CUDA(cudaFuncSetAttribute(conv_out_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-    }
+    static bool attr[64] = {};
+    if (first_use_on_device(attr)) SRK_CUDA(cudaFuncSetAttribute(conv_out_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long tiles = (long long)B * ((Hc + CO_TH - 1) / CO_TH) * ((Wc + CO_TW - 1) / CO_TW);
     const int grid = (int)(tiles < 2 * 148 ? tiles : 2 * 148);
     conv_out_mma_kernel<<<grid, CO_THREADS, smem, st>>>((const __half*)a, B, H, W, (const __half*)wgt, bias, out_scale, y, Hc, Wc);
@@ -589,11 +586,8 @@ extern "C" int srk_tail_border(const void* a, int B, int H, int W, int s, const 
     cudaStream_t st = (cudaStream_t)stream;
     ProfScope ps(SRK_PROF_CONV_OUT, stream);
     const size_t smem = 16 * (size_t)TB_STRIDE;
-    static bool attr = false;
-    if (!attr) {
-        SRK_CUDA(cudaFuncSetAttribute(tail_border_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-    }
+    static bool attr[64] = {};
+    if (first_use_on_device(attr)) SRK_CUDA(cudaFuncSetAttribute(tail_border_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(2 * ((W - 2 + 15) / 16) + 2 * ((H - 2 + 15) / 16) + 4, B);
     tail_border_kernel<<<grid, TB_THREADS, smem, st>>>((const __half*)a, H, W, s, (const __half*)f->border_w, f->border_b,
                                                 out_scale / f->w_scale, y, Hc, Wc);

@@ -758,12 +758,9 @@ int num_sms() {
 template <int BN, int EPI, int ACT, int DT>
 static int launch_tc5(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p_in, cudaStream_t st) {
     using Cfg = TcCfg<BN, EPI>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        SRK_CUDA(cudaFuncSetAttribute(gemm_tc5_kernel<BN, EPI, ACT, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    static bool attr_set[64] = {};
+    if (first_use_on_device(attr_set)) SRK_CUDA(cudaFuncSetAttribute(gemm_tc5_kernel<BN, EPI, ACT, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       TC_SMEM_TOTAL));
-        attr_set = true;
-    }
     TcParams p = p_in;
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("SRK_TC5_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
     const int total = p.m_tiles * p.n_tiles;

@@ -601,8 +601,8 @@ static int run_metrics(const float* E, const float* H, const float* roi, int B, 
         metrics_fast_init_kernel<<<ceil_div((long long)B * MAXV, 128), 128, 0, st>>>(fp.acc, B * MAXV);
         SRK_LAUNCH_CHECK("metrics_fast_init_kernel");
         const size_t smem = sizeof(float) * (2 * MH * (MH + 2) + 5 * MH * (MT + 1)) + MH * MH;
-        static bool attr = false;
-        if (!attr) { SRK_CUDA(cudaFuncSetAttribute(metrics_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+        static bool attr[64] = {};
+        if (first_use_on_device(attr)) SRK_CUDA(cudaFuncSetAttribute(metrics_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid(ceil_div(Wc, MT), ceil_div(Hc, MT), B);
         metrics_fast_kernel<<<grid, NTHREADS, smem, st>>>(fp);
         SRK_LAUNCH_CHECK("metrics_fast_kernel");

@@ -386,11 +386,8 @@ static int launch_mlp(const srk_mlp_args* a, cudaStream_t st) {
     }
     const size_t smem = (size_t)Cfg::A_BYTES + Cfg::H_BYTES + Cfg::W_BYTES + Cfg::AUX + (size_t)(a->hid_p + 3 * CP) * 4 + 1024;
     SRK_REQUIRE(smem <= (size_t)ML_SMEM_TOTAL, "mlp: hidden dim %d needs too much shared memory", a->hid_p);
-    static bool attr = false;
-    if (!attr) {
-        SRK_CUDA(cudaFuncSetAttribute(mlp_tc5_kernel<CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, ML_SMEM_TOTAL));
-        attr = true;
-    }
+    static bool attr[64] = {};
+    if (first_use_on_device(attr)) SRK_CUDA(cudaFuncSetAttribute(mlp_tc5_kernel<CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, ML_SMEM_TOTAL));
     const int grid = p.m_tiles < num_sms() ? p.m_tiles : num_sms();
     mlp_tc5_kernel<CP><<<grid, ML_THREADS, smem, st>>>(ma, mw1, mw2, p);
     SRK_LAUNCH_CHECK("mlp_tc5_kernel");
