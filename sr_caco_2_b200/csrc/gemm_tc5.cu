@@ -42,7 +42,8 @@ struct TcParams {
 #define SRK_LN_ROW_BATCH 2                                 // E_RES_LN epilogue: rows processed together (measured: 2 is best, 4 spills)
 #endif
 #ifndef SRK_FP32_EPI_WARPS
-#define SRK_FP32_EPI_WARPS 8                               // epilogue warps of the fp32 (residual / LayerNorm) path: 8 or 16 (measured: 16 is 6 % slower, 96-register cap)
+#define SRK_FP32_EPI_WARPS 8                               // epilogue warps of the fp32 (residual / LayerNorm) path: 8 or 16.  Measured: 16 is 6 % slower -- warps are
+                                                           // allocated in groups of 4, so 18 warps count as 20 and cap the kernel at 96 registers (spills)
 #endif
 
 template <int BN, int EPI>
