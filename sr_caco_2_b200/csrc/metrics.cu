@@ -313,6 +313,14 @@ __global__ void metrics_fast_init_kernel(BucketAcc* acc, int n) {
     if (i < n) { acc[i].sse = 0ull; acc[i].cnt = 0ull; acc[i].scnt = 0ull; acc[i].ssim = 0.0; acc[i].mn = 255; acc[i].mx = -1; }
 }
 
+// v / 255 for an integer level v in [0, 255], rounded exactly like the reference's division
+// (one Newton step on v * (1/255): checked against __fdiv_rn for all 256 levels, tests/test_gpu.py)
+__device__ __forceinline__ float div255(float v) {
+    const float r = 1.f / 255.f;
+    const float q = v * r;
+    return fmaf(fmaf(-q, 255.f, v), r, q);
+}
+
 struct FastParams {
     const float* E; const float* H;
     const unsigned char* H8;      // optional: the target as stored uint8 levels (H is then unused)
@@ -321,7 +329,7 @@ struct FastParams {
     BucketAcc* acc;
 };
 
-__global__ void __launch_bounds__(NTHREADS)
+__global__ void __launch_bounds__(NTHREADS, 3)
 metrics_fast_kernel(const FastParams p) {
     extern __shared__ __align__(16) unsigned char met_smem[];
     typedef float TileRow[MH + 2];
@@ -330,7 +338,6 @@ metrics_fast_kernel(const FastParams p) {
     TileRow* sy = sx + MH;                                           // H8/255
     HbRow (*hb)[MH] = reinterpret_cast<HbRow (*)[MH]>(sy + MH);      // [5][MH][MT+1]
     unsigned char* sk = reinterpret_cast<unsigned char*>(&hb[5][0][0]);   // bucket of every halo pixel [MH][MH]
-    __shared__ float lut[256];
     __shared__ unsigned long long r_sse[MAXV], r_cnt[MAXV], r_scnt[MAXV];
     __shared__ double r_ssim[MAXV];
     __shared__ int r_mn[MAXV], r_mx[MAXV];
@@ -344,7 +351,6 @@ metrics_fast_kernel(const FastParams p) {
     const unsigned char* H8b = p.H8 ? p.H8 + (size_t)b * p.Hpx * p.Wpx : nullptr;
     const int NB = p.n_ths + 1;
 
-    lut[tid] = __fdiv_rn((float)tid, 255.f);                         // x / 255 exactly as the reference divides
     if (tid < MAXV) { r_sse[tid] = 0ull; r_cnt[tid] = 0ull; r_scnt[tid] = 0ull; r_ssim[tid] = 0.0; r_mn[tid] = 255; r_mx[tid] = -1; }
     __syncthreads();
 
@@ -353,14 +359,31 @@ metrics_fast_kernel(const FastParams p) {
 #pragma unroll
     for (int k = 0; k < MAXV; ++k) { cnt[k] = 0; sse[k] = 0; mn[k] = 255; mx[k] = -1; }
 
-    for (int i = tid; i < MH * MH; i += NTHREADS) {
+    // all global loads of the thread first (7 halo pixels x 2 images in flight), then the arithmetic
+    constexpr int NPIX = (MH * MH + NTHREADS - 1) / NTHREADS;
+    float ev[NPIX], hv[NPIX];
+#pragma unroll
+    for (int u = 0; u < NPIX; ++u) {
+        const int i = tid + u * NTHREADS;
+        const int lr = i / MH, lc = i - lr * MH;
+        const int r = r0 + lr, c = c0 + lc;
+        ev[u] = 0.f; hv[u] = 0.f;
+        if (i < MH * MH && r < Hc && c < Wc) {
+            const size_t off = (size_t)(r + p.border) * p.Wpx + (c + p.border);
+            ev[u] = __ldg(Eb + off);
+            hv[u] = H8b ? (float)__ldg(H8b + off) : __ldg(Hb + off);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < NPIX; ++u) {
+        const int i = tid + u * NTHREADS;
+        if (i >= MH * MH) break;
         const int lr = i / MH, lc = i - lr * MH;
         const int r = r0 + lr, c = c0 + lc;
         int e = 0, h = 0, kb = 0;
         if (r < Hc && c < Wc) {
-            const size_t off = (size_t)(r + p.border) * p.Wpx + (c + p.border);
-            const float hf = H8b ? (float)__ldg(H8b + off) : quant255(__ldg(Hb + off));
-            e = (int)quant255(__ldg(Eb + off));
+            const float hf = H8b ? hv[u] : quant255(hv[u]);
+            e = (int)quant255(ev[u]);
             h = (int)hf;
 #pragma unroll
             for (int t = 0; t < SRK_MAX_ROI_THS; ++t) kb += (t < p.n_ths && hf >= p.ths[t]) ? 1 : 0;
@@ -377,8 +400,8 @@ metrics_fast_kernel(const FastParams p) {
                 }
             }
         }
-        sx[lr][lc] = lut[e];
-        sy[lr][lc] = lut[h];
+        sx[lr][lc] = div255((float)e);
+        sy[lr][lc] = div255((float)h);
         sk[lr * MH + lc] = (unsigned char)kb;
     }
     __syncthreads();
@@ -602,7 +625,10 @@ static int run_metrics(const float* E, const float* H, const float* roi, int B, 
         SRK_LAUNCH_CHECK("metrics_fast_init_kernel");
         const size_t smem = sizeof(float) * (2 * MH * (MH + 2) + 5 * MH * (MT + 1)) + MH * MH;
         static bool attr[64] = {};
-        if (first_use_on_device(attr)) SRK_CUDA(cudaFuncSetAttribute(metrics_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (first_use_on_device(attr)) {
+            SRK_CUDA(cudaFuncSetAttribute(metrics_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            SRK_CUDA(cudaFuncSetAttribute(metrics_fast_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        }
         dim3 grid(ceil_div(Wc, MT), ceil_div(Hc, MT), B);
         metrics_fast_kernel<<<grid, NTHREADS, smem, st>>>(fp);
         SRK_LAUNCH_CHECK("metrics_fast_kernel");
