@@ -491,18 +491,15 @@ metrics_fast_kernel(const FastParams p) {
 #pragma unroll
     for (int k = 0; k < MAXV; ++k) {
         if (k < NB) {
-            unsigned int c_ = cnt[k], s_ = sse[k], sc_ = scnt[k];
+            // integer quantities: one REDUX instruction each (sm_80+); only the fp32 SSIM sum needs the butterfly
+            const unsigned int c_ = __reduce_add_sync(0xffffffffu, cnt[k]);
+            const unsigned int s_ = __reduce_add_sync(0xffffffffu, sse[k]);      // <= 32 * 4 * 65025 fits 32 bits
+            const unsigned int sc_ = __reduce_add_sync(0xffffffffu, scnt[k]);
+            const int mn_ = __reduce_min_sync(0xffffffffu, mn[k]);
+            const int mx_ = __reduce_max_sync(0xffffffffu, mx[k]);
             float f_ = ssum[k];
-            int mn_ = mn[k], mx_ = mx[k];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                c_ += __shfl_xor_sync(0xffffffffu, c_, o);
-                s_ += __shfl_xor_sync(0xffffffffu, s_, o);     // <= 32 * 4 * 65025 fits 32 bits
-                sc_ += __shfl_xor_sync(0xffffffffu, sc_, o);
-                f_ += __shfl_xor_sync(0xffffffffu, f_, o);
-                mn_ = min(mn_, __shfl_xor_sync(0xffffffffu, mn_, o));
-                mx_ = max(mx_, __shfl_xor_sync(0xffffffffu, mx_, o));
-            }
+            for (int o = 16; o > 0; o >>= 1) f_ += __shfl_xor_sync(0xffffffffu, f_, o);
             if (lane == 0) {
                 if (c_) { atomicAdd(&r_cnt[k], (unsigned long long)c_); atomicAdd(&r_sse[k], (unsigned long long)s_);
                           atomicMin(&r_mn[k], mn_); atomicMax(&r_mx[k], mx_); }

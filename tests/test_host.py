@@ -218,3 +218,50 @@ def test_two_rank_gloo_metric_exchange_equals_single_process():
         for k in ("psnr", "mse", "nrmse", "ssim", "psnr_y"):
             assert abs(results[r][k] - float(a[k].double().mean())) < 1e-9 * max(1, abs(results[r][k]))
             assert abs(results[r]["roi_" + k] - float(b[k].double().mean())) < 1e-9 * max(1, abs(results[r][k]))
+
+
+def test_fold_tail_equals_layer_chain_on_cpu():
+    """packing.fold_tail: the composed 5x5 kernels (interior + 8 border variants, fragment-ordered for the
+    ring pass) reproduce [Conv3x3 + PixelShuffle(2)] x n + Conv3x3 at every pixel (fp64 evaluation)."""
+    import torch.nn.functional as F
+    from sr_caco_2_b200 import packing as P
+    g = torch.Generator().manual_seed(3)
+    for s, n in ((2, 1), (4, 2), (8, 3)):
+        ups = [(torch.randn(256, 64, 3, 3, generator=g) * 0.05, torch.randn(256, generator=g) * 0.1) for _ in range(n)]
+        lw, lb = torch.randn(1, 64, 3, 3, generator=g) * 0.05, torch.randn(1, generator=g) * 0.1
+        fw, fb, bw, bb, wsc = P.fold_tail(ups, lw, lb, s)
+        assert fw.shape == (64, 1600) and bw.shape == (9, 64, 1600) and fw.dtype == torch.float16
+        # undo the ring-pass fragment order: [t][ks][w][h] -> k = ks*16 + 8w + 2t + h
+        bn = bw.view(9, 64, 25, 4, 4, 2, 2).permute(0, 1, 2, 4, 5, 3, 6).reshape(9, 64, 1600)
+        assert torch.equal(bn[4], fw)
+        H, W = 6, 7
+        x = torch.randn(2, 64, H, W, generator=g).double()
+        y = x
+        for w_, b_ in ups:
+            y = F.pixel_shuffle(F.conv2d(y, w_.double(), b_.double(), padding=1), 2)
+        y = F.conv2d(y, lw.double(), lb.double(), padding=1)[:, 0]
+        xp = F.pad(x, (2, 2, 2, 2))
+        out = torch.zeros_like(y)
+        for yy in range(H):
+            for xx in range(W):
+                v = (0 if yy == 0 else 2 if yy == H - 1 else 1) * 3 + (0 if xx == 0 else 2 if xx == W - 1 else 1)
+                patch = xp[:, :, yy:yy + 5, xx:xx + 5].permute(0, 2, 3, 1).reshape(2, 1600)
+                o = (patch @ bn[v].double().t() + bb[v].double()) / wsc
+                out[:, yy * s:(yy + 1) * s, xx * s:(xx + 1) * s] = o[:, :s * s].view(2, s, s)
+        assert float((out - y).abs().max()) < 3e-3 * max(1.0, float(y.abs().max()))     # fp16 weight rounding only
+
+
+def test_pack_conv_nearest2x_equals_interpolate_then_conv_on_cpu():
+    """packing.pack_conv_nearest2x: nearest x2 + Conv3x3 == 3x3 conv on the low-res grid + PixelShuffle(2)."""
+    import torch.nn.functional as F
+    from sr_caco_2_b200 import _lib as L, packing as P
+    g = torch.Generator().manual_seed(4)
+    w, b = torch.randn(64, 64, 3, 3, generator=g) * 0.05, torch.randn(64, generator=g) * 0.1
+    x = torch.randn(2, 64, 5, 7, generator=g)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w, b, padding=1)
+    wk, bk = P.pack_conv_nearest2x(w, b, 64, L.SRK_FP16)
+    assert wk.shape == (256, 576) and bk.shape == (256,)
+    wc = wk.float().view(2, 2, 64, 3, 3, 64).permute(0, 1, 2, 5, 3, 4).reshape(256, 64, 3, 3)   # rows (i, j, c)
+    low = F.conv2d(x, wc, bk, padding=1).view(2, 2, 2, 64, 5, 7)                                # [b][i][j][c][y][x]
+    got = low.permute(0, 3, 4, 1, 5, 2).reshape(2, 64, 10, 14)
+    assert float((got - ref).abs().max()) < 2e-3
