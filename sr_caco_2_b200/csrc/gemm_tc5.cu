@@ -744,16 +744,19 @@ int encode_map(CUtensorMap* map, int dtype, int rank, const void* ptr, const cuu
     return 0;
 }
 
+thread_local int g_sm_cap = 0;            // > 0: persistent grids are sized for this many SMs (two-stream mode of net.cu)
 int num_sms() {
     static int n[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 64 && n[dev]) return n[dev];
-    int v = 148;
-    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-    if (const char* e = getenv("SRK_SM_CAP")) { const int cap = atoi(e); if (cap > 0 && cap < v) v = cap; }   // experiments
-    if (dev < 64) n[dev] = v;
-    return v;
+    int v = dev < 64 ? n[dev] : 0;
+    if (!v) {
+        v = 148;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        if (const char* e = getenv("SRK_SM_CAP")) { const int cap = atoi(e); if (cap > 0 && cap < v) v = cap; }   // experiments
+        if (dev < 64) n[dev] = v;
+    }
+    return g_sm_cap > 0 && g_sm_cap < v ? g_sm_cap : v;
 }
 
 template <int BN, int EPI, int ACT, int DT>

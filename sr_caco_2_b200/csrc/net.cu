@@ -104,13 +104,65 @@ int run_folded_tail(const srk_tail_fold& f, const void* feat, int B, int H, int 
 extern "C" size_t srk_swinir_workspace_bytes(const srk_swinir_plan* p, int B, int h, int w) {
     if (!p || B <= 0 || h <= 0 || w <= 0) return 0;
     SwinBufs b;
-    return swin_layout(p, B, pad8(h), pad8(w), nullptr, &b);
+    const size_t whole = swin_layout(p, B, pad8(h), pad8(w), nullptr, &b);
+    if (B < 2) return whole;
+    // the two-stream mode lays the two half batches out one after the other
+    const size_t halves = swin_layout(p, B / 2, pad8(h), pad8(w), nullptr, &b) + swin_layout(p, B - B / 2, pad8(h), pad8(w), nullptr, &b);
+    return whole > halves ? whole : halves;
 }
 
 #define TRY(expr) do { int rc__ = (expr); if (rc__) return rc__; } while (0)
 
+namespace srk {
+extern thread_local int g_sm_cap;
+int num_sms();
+// SRK_STREAMS=2 (experiment): the batch is split in two halves that run on two streams, each with persistent
+// grids sized for half of the SMs, so the HBM-bound kernels of one half overlap the compute-bound ones of the other
+static int n_streams() {
+    const char* e = getenv("SRK_STREAMS");
+    return e && atoi(e) == 2 ? 2 : 1;
+}
+}  // namespace srk
+static int swinir_forward_one(const srk_swinir_plan* p, const float* x, float* y, int B, int h, int w, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
 extern "C" int srk_swinir_forward(const srk_swinir_plan* p, const float* x, float* y, int B, int h,
                                   int w, void* workspace, size_t workspace_bytes, void* stream) {
+    if (n_streams() == 1 || B < 2 || !p || !workspace)
+        return swinir_forward_one(p, x, y, B, h, w, workspace, workspace_bytes, stream);
+    TRY(check_swin_plan(p));
+    const int B0 = B / 2, B1 = B - B0, H = pad8(h), W = pad8(w);
+    SwinBufs bb;
+    const size_t need0 = swin_layout(p, B0, H, W, nullptr, &bb), need1 = swin_layout(p, B1, H, W, nullptr, &bb);
+    if (need0 + need1 > workspace_bytes)
+        return fail(SRK_ERR_WORKSPACE, "swinir: workspace %zu < %zu bytes", workspace_bytes, need0 + need1);
+    static cudaStream_t side[64] = {};
+    static cudaEvent_t ev_fork[64] = {}, ev_join[64] = {};
+    int dev = 0;
+    SRK_CUDA(cudaGetDevice(&dev));
+    SRK_REQUIRE(dev >= 0 && dev < 64, "swinir: device index out of range");
+    if (!side[dev]) {
+        SRK_CUDA(cudaStreamCreateWithFlags(&side[dev], cudaStreamNonBlocking));
+        SRK_CUDA(cudaEventCreateWithFlags(&ev_fork[dev], cudaEventDisableTiming));
+        SRK_CUDA(cudaEventCreateWithFlags(&ev_join[dev], cudaEventDisableTiming));
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    SRK_CUDA(cudaEventRecord(ev_fork[dev], st));
+    SRK_CUDA(cudaStreamWaitEvent(side[dev], ev_fork[dev], 0));
+    const int s = p->upscale;
+    g_sm_cap = 0;
+    g_sm_cap = num_sms() / 2;
+    int rc = swinir_forward_one(p, x, y, B0, h, w, workspace, need0, stream);
+    if (!rc) rc = swinir_forward_one(p, x + (size_t)B0 * h * w, y + (size_t)B0 * h * s * w * s, B1, h, w,
+                                     (char*)workspace + need0, need1, (void*)side[dev]);
+    g_sm_cap = 0;
+    SRK_CUDA(cudaEventRecord(ev_join[dev], side[dev]));
+    SRK_CUDA(cudaStreamWaitEvent(st, ev_join[dev], 0));
+    return rc;
+}
+
+static int swinir_forward_one(const srk_swinir_plan* p, const float* x, float* y, int B, int h,
+                              int w, void* workspace, size_t workspace_bytes, void* stream) {
     TRY(check_swin_plan(p));
     SRK_REQUIRE(x && y && workspace, "swinir: null pointer");
     SRK_REQUIRE(B > 0 && h > 0 && w > 0, "swinir: bad input shape");
