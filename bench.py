@@ -401,9 +401,10 @@ def main():
 
     if not args.no_cpu_baseline and world >= 1:
         sample_b = 4 if kind == "swinir" else 8
-        v, spt, thr = cpu_reference_run(kind, kw, sd_cpu, h, w, seed, 2, 1, sample_b)
+        cpu_steps = 6 if kind == "swinir" else 8                 # ~10 s of host work for cfg3
+        v, spt, thr = cpu_reference_run(kind, kw, sd_cpu, h, w, seed, cpu_steps, 1, sample_b)
         line["cpu_baseline"] = {"value": v, "unit": unit, "cores": thr, "kind": "port",
-                                "sample": f"2 steps x batch {sample_b} (1 warm-up) of the same workload through "
+                                "sample": f"{cpu_steps} steps x batch {sample_b} (1 warm-up) of the same workload through "
                                           "oracle/sr_oracle.py on the host CPU, fp32"}
     print(json.dumps(line))
     if world > 1:
