@@ -138,6 +138,18 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
+// same with an explicit stride between the 8-row core groups (the swizzle is a function of the absolute
+// shared-memory address, so the start may be any 128 B row of a larger swizzled tile and the groups need
+// not be 1024 B apart: measured with csrc/dbg_umma.cu)
+__device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
 // kind::f16 instruction descriptor: D fp32, A/B both `fmt` (0 = F16, 1 = BF16), K-major A and B
 __host__ __device__ constexpr uint32_t umma_idesc(int fmt, int M, int N) {
     return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) |
