@@ -2,8 +2,19 @@
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+import subprocess
 from sr_caco_2_b200 import _lib as L
-lib = L.load()
+L.load()                                  # libsrk.so provides encode_map / fail / the error string
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "sr_caco_2_b200")
+SO = os.path.join(ROOT, "gpurun_out", "libdbg_umma.so")
+os.makedirs(os.path.dirname(SO), exist_ok=True)
+# the experiment kernel is NOT part of libsrk.so: built here, linked against it
+subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
+                       "-shared", "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(PKG, "csrc"),
+                       os.path.join(PKG, "csrc", "dbg_umma.cu"), "-o", SO, "-L", PKG, "-l:libsrk.so",
+                       "-Xlinker", "-rpath," + PKG])
+lib = C.CDLL(SO)
 lib.srk_dbg_umma_shift.restype = C.c_int
 lib.srk_dbg_umma_shift.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
 torch.manual_seed(0)

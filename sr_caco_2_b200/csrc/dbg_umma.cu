@@ -1,4 +1,4 @@
-// Experiment (not on any product path): can a tcgen05.mma A operand be a SHIFTED window of a larger
+// Experiment (not part of libsrk.so: scripts/dbg_umma.py builds and runs it): can a tcgen05.mma A operand be a SHIFTED window of a larger
 // 128B-swizzled tile?  A: (R, 64) fp16 rows loaded by ONE TMA box into a 1024 B aligned buffer; the MMA reads
 // 128 rows as 16 core groups of 8 rows: group g starts at row  shift + g * pitch  (SBO = pitch * 128 B).
 // D[r][n] = sum_k A[shift + (r / 8) * pitch + r % 8][k] * Bm[n][k]   is compared on the host.
@@ -62,7 +62,7 @@ dbg_umma_shift_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 
 using namespace srk;
 
-// experiment entry (exported for scripts/dbg_umma.py only; not declared in include/srk.h)
+// experiment entry (scripts/dbg_umma.py)
 extern "C" int srk_dbg_umma_shift(const void* A, int R, const void* Bm, int shift, int pitch, int base_offset, float* D,
                                   void* stream) {
     SRK_REQUIRE(A && Bm && D && R > 0 && R <= 256, "dbg_umma: bad arguments");
