@@ -149,6 +149,9 @@ typedef struct {
      * only the attention output to out16 (M, ld16 = attn_heads*32): q, k, v never reach HBM. */
     const float* attn_table; int attn_heads; float attn_scale; int attn_shift;
     int conv_k;                          /* SRK_A_CONV3X3 window: 0 or 3 -> 3x3, 5 -> 5x5 */
+    /* fused LayerNorm: also write 1.0 into the two pad columns ln_C, ln_C + 1 of out16 (ln_C even, N >= ln_C + 2):
+     * the consumer is a qkv GEMM whose weight holds the bias (hi, lo bf16) in those two K columns */
+    int ln_pad_one;
 } srk_gemm_args;
 int srk_gemm(const srk_gemm_args* g, void* stream);
 
@@ -252,6 +255,9 @@ typedef struct {
     const float* rel_table;             /* (nH, 225) */
     int shift;                          /* 0 or window_size/2, decided at construction */
     int num_heads;
+    /* optional: w_qkv with the bias folded into K columns embed_dim (bf16 hi part) and embed_dim + 1 (bf16 of the
+     * remainder); used with a NULL bias when the producer of the A rows wrote 1.0 there (ln_pad_one). NULL: not built */
+    const void* w_qkv_fb;
 } srk_stb_params;
 
 typedef struct {

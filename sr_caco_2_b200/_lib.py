@@ -29,7 +29,7 @@ class GemmArgs(C.Structure):
                 ("ln_g", fp), ("ln_b", fp), ("ln_C", C.c_int), ("ln_win_shift", C.c_int),
                 ("img", fp), ("img_s", C.c_int), ("img_scale", C.c_float), ("img_hc", C.c_int),
                 ("img_wc", C.c_int), ("attn_table", fp), ("attn_heads", C.c_int),
-                ("attn_scale", C.c_float), ("attn_shift", C.c_int), ("conv_k", C.c_int)]
+                ("attn_scale", C.c_float), ("attn_shift", C.c_int), ("conv_k", C.c_int), ("ln_pad_one", C.c_int)]
 
 
 class MlpArgs(C.Structure):
@@ -52,7 +52,7 @@ class StbParams(C.Structure):
     _fields_ = [("ln1_g", fp), ("ln1_b", fp), ("ln2_g", fp), ("ln2_b", fp),
                 ("w_qkv", vp), ("w_proj", vp), ("w_fc1", vp), ("w_fc2", vp),
                 ("b_qkv", fp), ("b_proj", fp), ("b_fc1", fp), ("b_fc2", fp),
-                ("rel_table", fp), ("shift", C.c_int), ("num_heads", C.c_int)]
+                ("rel_table", fp), ("shift", C.c_int), ("num_heads", C.c_int), ("w_qkv_fb", vp)]
 
 
 class SwinIRPlan(C.Structure):

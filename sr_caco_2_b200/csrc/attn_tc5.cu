@@ -99,7 +99,7 @@ qkv_attn_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < 192; i += QA_THREADS) sbias[i] = p.bias[(i >> 6) * p.nH * 32 + pair * 64 + (i & 63)];
+    for (int i = threadIdx.x; i < 192; i += QA_THREADS) sbias[i] = p.bias ? p.bias[(i >> 6) * p.nH * 32 + pair * 64 + (i & 63)] : 0.f;
     for (int i = threadIdx.x; i < 450; i += QA_THREADS) stab[i] = p.table[pair * 450 + i] * LOG2E;
     tc_fence_before();
     __syncthreads();

@@ -17,6 +17,7 @@ struct GemmP {
     int T;            // H*W (tokens per image) when H, W are set, else 0
     int cpb;          // channel blocks of 64 per conv tap (lda / 64)
     int kt;           // conv window (3 or 5)
+    int ln_pad_one;   // fused LayerNorm writes 1.0 into pad columns ln_C, ln_C + 1
 };
 
 inline GemmP make_gemm_params(const srk_gemm_args* g) {
@@ -36,6 +37,7 @@ inline GemmP make_gemm_params(const srk_gemm_args* g) {
     p.T = (g->H > 0 && g->W > 0) ? g->H * g->W : 0;
     p.cpb = g->lda / 64;
     p.kt = g->conv_k == 5 ? 5 : 3;
+    p.ln_pad_one = g->ln_pad_one;
     return p;
 }
 

@@ -508,7 +508,9 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             for (int k = 0; k < NP; ++k) {
                 const int n = 64 * k + 2 * lane;
                 lng[k] = n < g.ln_C ? __ldg(reinterpret_cast<const float2*>(g.ln_g + n)) : make_float2(0.f, 0.f);
-                lnb[k] = n < g.ln_C ? __ldg(reinterpret_cast<const float2*>(g.ln_b + n)) : make_float2(0.f, 0.f);
+                // pad columns: beta doubles as the constant written there (1.0 in ln_C, ln_C + 1 when ln_pad_one)
+                lnb[k] = n < g.ln_C ? __ldg(reinterpret_cast<const float2*>(g.ln_b + n))
+                                    : ((g.ln_pad_one && n == g.ln_C) ? make_float2(1.f, 1.f) : make_float2(0.f, 0.f));
             }
         }
         // row bookkeeping of one tile: lane i (< RPW) describes row i of this warp's phase-R rows
@@ -651,8 +653,8 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
                     for (int k = 0; k < NP; ++k) {
                         const bool in = 64 * k + 2 * lane < g.ln_C;
-                        const float y0 = in ? (v[k].x - mean) * rstd * lng[k].x + lnb[k].x : 0.f;
-                        const float y1 = in ? (v[k].y - mean) * rstd * lng[k].y + lnb[k].y : 0.f;
+                        const float y0 = in ? (v[k].x - mean) * rstd * lng[k].x + lnb[k].x : lnb[k].x;
+                        const float y1 = in ? (v[k].y - mean) * rstd * lng[k].y + lnb[k].y : lnb[k].y;
                         if (valid)
                             *reinterpret_cast<uint32_t*>(oo + 64 * k) =
                                 EPI == E_GENERIC ? pack2(y0, y1, g.out16_dtype) : packf<DT>(y0, y1);
@@ -745,8 +747,8 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
                     for (int k = 0; k < NP; ++k) {
                         const bool in = 64 * k + 2 * lane < g.ln_C;
-                        const float y0 = in ? (v[r][k].x - mean[r]) * rstd * lng[k].x + lnb[k].x : 0.f;
-                        const float y1 = in ? (v[r][k].y - mean[r]) * rstd * lng[k].y + lnb[k].y : 0.f;
+                        const float y0 = in ? (v[r][k].x - mean[r]) * rstd * lng[k].x + lnb[k].x : lnb[k].x;
+                        const float y1 = in ? (v[r][k].y - mean[r]) * rstd * lng[k].y + lnb[k].y : lnb[k].y;
                         if (m[r] >= 0) *reinterpret_cast<uint32_t*>(oo + 64 * k) = packf<DT>(y0, y1);
                     }
                 }
@@ -932,6 +934,7 @@ int gemm_tcgen05(const srk_gemm_args* a, cudaStream_t st) {
     const int BN = ps256 ? 256 : (a->N % 192 == 0 ? 192 : (a->N % 128 == 0 ? 128 : 64));
     if (a->ln_g) {
         SRK_REQUIRE(a->N == BN, "gemm(tcgen05): fused LayerNorm needs the whole row in one tile (N=%d)", a->N);
+        SRK_REQUIRE(!a->ln_pad_one || (a->ln_C % 2 == 0 && a->ln_C + 2 <= a->N), "gemm(tcgen05): ln_pad_one needs two pad columns");
         SRK_REQUIRE(a->out16 && a->out16_mode == SRK_O16_ROWS && a->ln_b && a->ln_C > 0 && a->ln_C <= a->N,
                     "gemm(tcgen05): bad fused LayerNorm arguments");
     }

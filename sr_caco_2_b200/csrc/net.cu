@@ -223,6 +223,11 @@ static int swinir_forward_one(const srk_swinir_plan* p, const float* x, float* y
     void* a16 = b.A16;           // 16-bit operand buffer in use; `alt` is its ping-pong partner (the conv
     void* alt = b.Y1;            // epilogue may not overwrite the image it is convolving)
     bool a16_ready = first_fused; // A16 already holds LN1 of the next block (fused producer)
+    // qkv bias folded into the GEMM: the LayerNorm epilogue that produces a block's A rows writes 1.0 into the pad
+    // columns C, C + 1 and the block's folded weight (w_qkv_fb) carries the bias there -> no bias add in the epilogue
+    static const bool fold_env = !(getenv("SRK_FOLD_QKV_BIAS") && atoi(getenv("SRK_FOLD_QKV_BIAS")) == 0);
+    const bool fold_ok = fold_env && Cp - C >= 2 && C % 2 == 0;
+    bool a16_ones = false;
     bool final_norm_done = false;
     for (int l = 0; l < p->n_layers; ++l) {
         const float* cur = b.XA;
@@ -232,15 +237,18 @@ static int swinir_forward_one(const srk_swinir_plan* p, const float* x, float* y
             SRK_REQUIRE(nH * p->dp <= p->ao_p && 3 * nH * p->dp <= b.nq_p, "swinir: head layout overflow");
             SRK_REQUIRE(s.shift == 0 || s.shift == 4, "swinir: shift must be 0 or window_size/2");
             const int hd = C / nH;
-            if (!a16_ready)
+            if (!a16_ready) {
                 TRY(srk_layernorm(cur, Cp, M, C, s.ln1_g, s.ln1_b, eps, a16, Cp, ldt, nullptr, H, W, s.shift, stream));
+                a16_ones = false;
+            }
             a16_ready = false;
             static const bool attn_env = !(getenv("SRK_FUSED_ATTN") && atoi(getenv("SRK_FUSED_ATTN")) == 0);
             const bool fused_attn = attn_env && fuse_ln && p->dp == 32 && nH % 2 == 0 && p->ao_p == nH * 32 &&
                                     b.nq_p == 3 * nH * 32;
             if (fused_attn) {
                 // qkv projection + window attention in one kernel: q, k, v stay in shared memory
-                srk_gemm_args g = lin_gemm(a16, Cp, s.w_qkv, s.b_qkv, b.nq_p, Cp);
+                const bool fb = a16_ones && s.w_qkv_fb != nullptr;
+                srk_gemm_args g = lin_gemm(a16, Cp, fb ? s.w_qkv_fb : s.w_qkv, fb ? nullptr : s.b_qkv, b.nq_p, Cp);
                 g.out16 = b.AO; g.ld16 = p->ao_p;
                 g.attn_table = s.rel_table; g.attn_heads = nH; g.attn_scale = 1.0f / sqrtf((float)hd); g.attn_shift = s.shift;
                 TRY(srk_gemm(&g, stream));
@@ -282,7 +290,7 @@ static int swinir_forward_one(const srk_swinir_plan* p, const float* x, float* y
                 } else {
                     const srk_stb_params& nx = p->stbs[blk + 1];
                     m.ln_g = nx.ln1_g; m.ln_b = nx.ln1_b; m.ln_C = C; m.ln_win_shift = nx.shift; m.out16_dtype = ldt;
-                    a16_ready = true;
+                    a16_ready = true; a16_ones = false;
                 }
                 // the kernel reads A (a16) by TMA tile-by-tile and writes out16 rows of OTHER tiles when the
                 // next block is shifted, so the 16-bit output must not alias the operand: ping-pong
@@ -306,6 +314,7 @@ static int swinir_forward_one(const srk_swinir_plan* p, const float* x, float* y
                     const srk_stb_params& nx = p->stbs[blk + 1];
                     g.ln_g = nx.ln1_g; g.ln_b = nx.ln1_b; g.ln_C = C; g.ln_win_shift = nx.shift;
                     g.out16 = a16; g.ld16 = Cp;
+                    g.ln_pad_one = fold_ok && nx.w_qkv_fb != nullptr; a16_ones = g.ln_pad_one != 0;
                     a16_ready = true;
                 }
                 TRY(srk_gemm(&g, stream));
@@ -328,6 +337,7 @@ static int swinir_forward_one(const srk_swinir_plan* p, const float* x, float* y
                     const srk_stb_params& nx = p->stbs[blk];
                     g.ln_g = nx.ln1_g; g.ln_b = nx.ln1_b; g.ln_C = C; g.ln_win_shift = nx.shift;
                     g.out16 = alt; g.ld16 = Cp; g.out16_dtype = ldt;
+                    g.ln_pad_one = fold_ok && nx.w_qkv_fb != nullptr; a16_ones = g.ln_pad_one != 0;
                     a16_ready = true; swap_after = true;
                 } else if (l + 1 == p->n_layers) {
                     g.ln_g = p->norm_g; g.ln_b = p->norm_b; g.ln_C = C; g.ln_win_shift = -1;

@@ -233,6 +233,8 @@ class SwinIR(nn.Module):
                 s.ln2_g, s.ln2_b = k(blk.norm2.weight.detach().float().contiguous()), k(blk.norm2.bias.detach().float().contiguous())
                 wq, bq = P.pack_qkv(blk.attn.qkv.weight.detach(), blk.attn.qkv.bias.detach(), nh, d, dp, nq_p, Cp, linear_dtype)
                 s.w_qkv, s.b_qkv = k(wq), k(bq)
+                if Cp - Cdim >= 2 and Cdim % 2 == 0:
+                    s.w_qkv_fb = k(P.fold_qkv_bias(wq, bq, Cdim))
                 s.w_proj = k(P.pack_proj(blk.attn.proj.weight.detach(), nh, d, dp, Cp, ao_p, linear_dtype))
                 s.b_proj = k(P.pad_bias(blk.attn.proj.bias.detach(), Cp))
                 s.w_fc1 = k(P.pack_linear(blk.mlp.fc1.weight.detach(), hid_p, Cp, linear_dtype))

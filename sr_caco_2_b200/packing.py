@@ -46,6 +46,17 @@ def pack_qkv(w: torch.Tensor, b: torch.Tensor, nh: int, d: int, dp: int, n_p: in
     return out.to(_dt(dtype_code)).contiguous(), bias.contiguous()
 
 
+def fold_qkv_bias(w_packed: torch.Tensor, bias_packed: torch.Tensor, c: int) -> torch.Tensor:
+    """Packed qkv weight (n_p, k_p) with the bias folded into the pad K columns c (bf16 of the bias) and
+    c + 1 (bf16 of the remainder): with A[:, c] = A[:, c + 1] = 1 the GEMM adds bias to 2^-17 relative."""
+    assert w_packed.shape[1] - c >= 2
+    out = w_packed.clone()
+    hi = bias_packed.to(w_packed.dtype)
+    lo = (bias_packed - hi.float()).to(w_packed.dtype)
+    out[:, c], out[:, c + 1] = hi, lo
+    return out.contiguous()
+
+
 def pack_proj(w: torch.Tensor, nh: int, d: int, dp: int, n_p: int, k_p: int, dtype_code: int):
     """proj Linear (C, C): input column (head, e) = head*d + e -> column head*dp + e."""
     C = w.shape[0]
