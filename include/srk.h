@@ -50,6 +50,14 @@ enum { SRK_O16_ROWS = 0, SRK_O16_PIXSHUF2 = 1 };
  * as the in-library cross-check of the former (tests only) */
 enum { SRK_ENGINE_TCGEN05 = 0, SRK_ENGINE_MMA_SYNC = 1 };
 enum { SRK_UPSAMPLER_PIXELSHUFFLE = 0, SRK_UPSAMPLER_PIXELSHUFFLEDIRECT = 1, SRK_UPSAMPLER_NEAREST_CONV = 2 };
+/* `options` of the network plans: 0 is the product launch sequence; each bit switches ONE fusion off so
+ * that the parity tests can compare a fused kernel with the unfused sequence it replaces */
+enum { SRK_OPT_NO_FUSED_MLP = 1,       /* fc1 + GELU and fc2 + residual + LN as two GEMM launches */
+       SRK_OPT_NO_FUSED_ATTN = 2,      /* qkv GEMM, window attention and proj as separate launches */
+       SRK_OPT_NO_FOLD_TAIL = 4,       /* run the upsampler convs one by one */
+       SRK_OPT_NO_FOLD_QKV_BIAS = 8,   /* add the qkv bias in the epilogue */
+       SRK_OPT_NO_FUSED_BLOCK = 16,    /* qkv + attention fused, proj + residual + LN as its own GEMM launch */
+       SRK_OPT_NO_GRAPH = 32 };        /* (host layer) do not replay the forward from a CUDA graph */
 
 const char* srk_last_error(void);
 int srk_version(void);
@@ -158,7 +166,8 @@ int srk_gemm(const srk_gemm_args* g, void* stream);
 /* Fused Swin MLP (tcgen05 engine):  v = res + fc2(GELU(fc1(A) + b1)) + b2 ; out32 = v ;
  * out16 = LayerNorm(v; ln_g, ln_b) written at the token's row (ln_win_shift = -1) or at its
  * window-major row for the next block's cyclic shift, or a plain 16-bit cast when ln_g == NULL.
- * A: (M, lda) bf16 rows in token order; W1: (hid_p, Cp) bf16; W2: (Cp, hid_p) bf16; hid_p %% 128 == 0.
+ * A: (M, lda) bf16 rows in token order; W1: (hid_p, Cp) bf16; W2: (Cp, hid_p) bf16; hid_p %% 64 == 0.
+ * ln_pad_one: the fused LayerNorm also writes 1.0 into pad columns ln_C, ln_C + 1 (see srk_gemm_args).
  * Replaces Mlp.forward network_swinir.py:39-45 + the residual / norm of :335, :293. */
 typedef struct {
     const void* A; int lda; int M; int C; int Cp; int hid_p;
@@ -166,6 +175,7 @@ typedef struct {
     const float* res; float* out32; int ld32;
     void* out16; int ld16; int out16_dtype;
     const float* ln_g; const float* ln_b; int ln_C; int ln_win_shift; int H, W;
+    int ln_pad_one;
 } srk_mlp_args;
 int srk_mlp(const srk_mlp_args* a, void* stream);
 
@@ -290,6 +300,7 @@ typedef struct {
      * with the nearest x2 interpolation in front of them (a 3x3 conv on the LOW-res grid, 64 -> 4*64 in
      * PixelShuffle order, packing.pack_conv_nearest2x), conv_hr the 64 -> 64 conv before conv_last. */
     srk_conv_params conv_hr;
+    int options;                         /* SRK_OPT_* bits, 0 = default */
 } srk_swinir_plan;
 
 size_t srk_swinir_workspace_bytes(const srk_swinir_plan* p, int B, int h, int w);
@@ -306,6 +317,7 @@ typedef struct {
     const void* tail_w; float tail_b;    /* (9,F) fp16 */
     int conv_dtype;
     srk_tail_fold tail_fold;             /* w == NULL: run the tail convs one by one */
+    int options;                         /* SRK_OPT_* bits, 0 = default */
 } srk_edsr_plan;
 
 size_t srk_edsr_workspace_bytes(const srk_edsr_plan* p, int B, int h, int w);

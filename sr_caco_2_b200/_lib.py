@@ -16,6 +16,7 @@ ENGINE_TCGEN05, ENGINE_MMA_SYNC = 0, 1
 UPSAMPLER_PIXELSHUFFLE, UPSAMPLER_PIXELSHUFFLEDIRECT, UPSAMPLER_NEAREST_CONV = 0, 1, 2
 MET_PSNR, MET_MSE, MET_NRMSE, MET_SSIM, MET_PSNR_Y, MET_N = 0, 1, 2, 3, 4, 5
 MAX_ROI_THS = 8
+OPT_NO_FUSED_MLP, OPT_NO_FUSED_ATTN, OPT_NO_FOLD_TAIL, OPT_NO_FOLD_QKV_BIAS, OPT_NO_FUSED_BLOCK, OPT_NO_GRAPH = 1, 2, 4, 8, 16, 32
 
 vp, fp, ip = C.c_void_p, C.c_void_p, C.c_void_p   # all device pointers travel as void*
 
@@ -37,7 +38,7 @@ class MlpArgs(C.Structure):
                 ("hid_p", C.c_int), ("W1", vp), ("b1", fp), ("W2", vp), ("b2", fp), ("res", fp),
                 ("out32", fp), ("ld32", C.c_int), ("out16", vp), ("ld16", C.c_int),
                 ("out16_dtype", C.c_int), ("ln_g", fp), ("ln_b", fp), ("ln_C", C.c_int),
-                ("ln_win_shift", C.c_int), ("H", C.c_int), ("W", C.c_int)]
+                ("ln_win_shift", C.c_int), ("H", C.c_int), ("W", C.c_int), ("ln_pad_one", C.c_int)]
 
 
 class ConvParams(C.Structure):
@@ -69,7 +70,7 @@ class SwinIRPlan(C.Structure):
                 ("conv_last_w", fp), ("conv_last_b", C.c_float),
                 ("linear_dtype", C.c_int), ("conv_dtype", C.c_int), ("tail_fold", TailFold),
                 ("resi_3conv", C.c_int), ("rstb_c0", C.POINTER(ConvParams)), ("rstb_c1", C.POINTER(ConvParams)),
-                ("cab_c0", ConvParams), ("cab_c1", ConvParams), ("conv_hr", ConvParams)]
+                ("cab_c0", ConvParams), ("cab_c1", ConvParams), ("conv_hr", ConvParams), ("options", C.c_int)]
 
 
 class EDSRPlan(C.Structure):
@@ -78,7 +79,7 @@ class EDSRPlan(C.Structure):
                 ("Fp", C.c_int), ("head_w", fp), ("head_b", fp),
                 ("body", C.POINTER(ConvParams)), ("tail_up", ConvParams * 4),
                 ("n_tail_up", C.c_int), ("tail_w", fp), ("tail_b", C.c_float),
-                ("conv_dtype", C.c_int), ("tail_fold", TailFold)]
+                ("conv_dtype", C.c_int), ("tail_fold", TailFold), ("options", C.c_int)]
 
 
 # every symbol include/srk.h declares: (restype, argtypes)

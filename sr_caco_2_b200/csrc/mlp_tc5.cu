@@ -3,28 +3,36 @@
 // the SM.  Restates Mlp.forward (dlib/models/network_swinir.py:39-45) + the residual add and the
 // next norm1 (:335, :293) of SwinTransformerBlock.forward.
 //
-// Per 128-token tile (hidden processed in chunks of 128 columns, c = 0 .. NC-1):
-//   TMA        : A tile (LN2 output, bf16) once; W1 / W2 tiles stream through a 4-slot ring in
-//                exactly the order the MMA warp consumes them.
-//   MMA warp   : fc1(c):  D1[c&1] (TMEM, 128 cols)  = A . W1[128c.., :]^T
-//                fc2(c):  D2      (TMEM, CP cols)  += H[c&1] . W2[:, 128c..]^T
-//                issued as fc1(0), fc1(1), fc2(0), fc1(2), fc2(1), ... so the GELU of chunk c
-//                overlaps the fc1 MMAs of chunk c+1.
-//   16 epilogue warps: GELU stage: tcgen05.ld D1 -> + b1 -> GELU -> bf16 -> written into shared
-//                memory in the 128B-swizzled K-major operand layout (H[c&1]) that fc2 reads;
-//                final stage: D2 -> padded fp32 staging (aliases the H buffers, 64 rows at a
-//                time) -> + b2 + residual (fp32 stream, register-prefetched one tile ahead) ->
-//                x' store + LayerNorm / cast store, all as coalesced row segments.
+// Per 128-token tile the hidden dimension is processed in chunks of 64 columns, c = 0 .. NC-1:
+//   warp 0       TMA: the A tile (LN2 output, bf16) once per tile; W1 / W2 chunk tiles stream
+//                through a 3-slot ring in exactly the order the MMA warp consumes them.
+//   warp 1       MMA: fc1(c):  D1[c&1] (TMEM, 64 cols)   = A . W1[64c.., :]^T
+//                     fc2(c):  D2[t&1] (TMEM, CP cols)  += H[c%3] . W2[:, 64c..]^T
+//                issued as fc1(0) fc1(1) | fc1(2) fc2(0) | fc1(3) fc2(1) | ... so the tensor pipe
+//                always has the fc1 of a later chunk queued while a chunk is in the GELU warps.
+//   warps 4..11  GELU warps (2 per TMEM lane group, 32 chunk columns each): tcgen05.ld D1 ->
+//                + b1 -> exact-erf GELU (packed fp32x2, one MUFU per element) -> bf16 -> written
+//                into shared memory in the 128B-swizzled K-major operand layout fc2 reads.
+//   warps 12..19 final warps: D2 -> padded fp32 staging (64 rows at a time) -> + b2 + residual
+//                (fp32 stream, register-prefetched half a tile ahead) -> x' store + LayerNorm /
+//                cast store, all as coalesced row segments.  D2 is double buffered, so the final
+//                stage of tile t runs under the GELU / MMA work of tile t+1.
 #include "tc5_ptx.cuh"
-#include <stdlib.h>
 
 namespace srk {
 
-constexpr int ML_EPI_WARPS = 8;            // 2 warps per TMEM lane group
-constexpr int ML_QN = ML_EPI_WARPS / 4;    // warps per lane group
-constexpr int ML_RPW = 64 / ML_EPI_WARPS;  // rows per warp in each 64-row half of the final stage
-constexpr int ML_THREADS = 64 + 32 * ML_EPI_WARPS;
-constexpr int ML_WSLOT = 24576, ML_WSLOTS = 4;
+constexpr int ML_CH = 64;                  // hidden columns per chunk
+constexpr int ML_G_WARPS = 8;              // GELU warps
+#ifndef SRK_ML_F_WARPS
+#define SRK_ML_F_WARPS 8
+#endif
+constexpr int ML_F_WARPS = SRK_ML_F_WARPS;  // final-stage warps (1 or 2 per TMEM lane group)
+constexpr int ML_THREADS = 128 + 32 * (ML_G_WARPS + ML_F_WARPS);
+constexpr int ML_NH = 3;                   // H (GELU output) operand stages
+constexpr int ML_NW = 3;                   // weight ring slots
+constexpr int ML_RPW = 64 / ML_F_WARPS;    // rows per final warp in each 64-row half
+constexpr int ML_RB = 2;                   // row PAIRS per final-stage step (a warp finishes two rows at a time)
+constexpr int ML_NBK = 2;                  // residual banks of RB row pairs in flight (prefetch distance 2 * NBK * RB rows)
 constexpr int ML_SMEM_TOTAL = 227 * 1024;
 
 struct MlpP {
@@ -33,22 +41,24 @@ struct MlpP {
     const float* b1; const float* b2;
     const float* res; float* out32; int ld32;
     uint16_t* out16; int ld16; int out16_dtype;
-    const float* ln_g; const float* ln_b; int ln_C; int ln_win_shift;
+    const float* ln_g; const float* ln_b; int ln_C; int ln_win_shift; int ln_pad_one;
 };
 
 template <int CP>
 struct MlCfg {
     static constexpr int KB1 = CP / 64;
     static constexpr int A_BYTES = KB1 * 16384;
-    static constexpr int H_BYTES = 2 * 32768;
+    static constexpr int H_BYTES = ML_NH * 16384;
+    static constexpr int WSLOT = CP * 128;                       // one W1 chunk (KB1 boxes of 64 x 64) or one W2 chunk (CP x 64)
+    static constexpr int W_BYTES = ML_NW * WSLOT;
     static constexpr int SROW = CP + 4;                          // fp32 staging row stride (floats)
-    static constexpr int W_BYTES = ML_WSLOTS * ML_WSLOT;
-    static constexpr int AUX = 512;                              // barriers + tmem slot
-    static_assert(64 * SROW * 4 <= H_BYTES, "staging must fit in the H buffers");
-    static_assert(CP * 128 <= ML_WSLOT, "W2 tile must fit a ring slot");
+    static constexpr int STG_BYTES = 64 * SROW * 4;
+    static constexpr int AUX = 256;                              // barriers + tmem slot
+    static constexpr int TMEM_D2 = 128;                          // D1: 2 x 64 columns, D2: 2 x CP columns
+    static_assert(128 + 2 * CP <= 512, "TMEM budget");
 };
 
-template <int CP>
+template <int CP, bool LN>
 __global__ void __launch_bounds__(ML_THREADS, 1)
 mlp_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w1,
                const __grid_constant__ CUtensorMap map_w2, const MlpP p) {
@@ -57,32 +67,35 @@ mlp_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     extern __shared__ unsigned char ml_smem_raw[];
     const uint32_t raw = smem_u32(ml_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
-    const uint32_t sA = base, sH = sA + Cfg::A_BYTES, sW = sH + Cfg::H_BYTES, bars = sW + Cfg::W_BYTES;
+    const uint32_t sA = base, sH = sA + Cfg::A_BYTES, sW = sH + Cfg::H_BYTES, sStg = sW + Cfg::W_BYTES,
+                   bars = sStg + Cfg::STG_BYTES;
     // barrier map
     const uint32_t a_full = bars, a_empty = bars + 8;
     auto w_full = [&](int s) { return bars + 16 + 8u * s; };
-    auto w_empty = [&](int s) { return bars + 48 + 8u * s; };
-    auto d1_full = [&](int b) { return bars + 80 + 8u * b; };
-    auto d1_empty = [&](int b) { return bars + 96 + 8u * b; };
-    auto h_full = [&](int b) { return bars + 112 + 8u * b; };
-    auto h_empty = [&](int b) { return bars + 128 + 8u * b; };
-    const uint32_t d2_full = bars + 144, d2_empty = bars + 152, tmem_slot = bars + 160;
-    float* sb1 = reinterpret_cast<float*>(ml_smem_raw + (bars + Cfg::AUX - raw));   // [hid_p]
+    auto w_empty = [&](int s) { return bars + 40 + 8u * s; };
+    auto d1_full = [&](int b) { return bars + 64 + 8u * b; };
+    auto d1_empty = [&](int b) { return bars + 80 + 8u * b; };
+    auto h_full = [&](int b) { return bars + 96 + 8u * b; };
+    auto h_empty = [&](int b) { return bars + 120 + 8u * b; };
+    auto d2_full = [&](int b) { return bars + 144 + 8u * b; };
+    auto d2_empty = [&](int b) { return bars + 160 + 8u * b; };
+    const uint32_t tmem_slot = bars + 176;
+    float* sb1 = reinterpret_cast<float*>(ml_smem_raw + (bars + Cfg::AUX - raw));   // [hid_p] fc1 bias, HALVED (gelu2)
     float* sb2 = sb1 + p.hid_p;                                                     // [CP]
     float* sg = sb2 + CP;                                                            // [CP] LayerNorm gamma (0 beyond ln_C)
-    float* sbt = sg + CP;                                                            // [CP] LayerNorm beta
+    float* sbt = sg + CP;                                                            // [CP] LayerNorm beta (pad: 0, or 1 in ln_C, ln_C+1)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NC = p.NC;
 
     if (threadIdx.x == 0) {
         mbar_init(a_full, 1); mbar_init(a_empty, 1);
-        for (int s = 0; s < ML_WSLOTS; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
+        for (int s = 0; s < ML_NW; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(d1_full(b), 1); mbar_init(d1_empty(b), ML_EPI_WARPS);
-            mbar_init(h_full(b), ML_EPI_WARPS); mbar_init(h_empty(b), 1);
+            mbar_init(d1_full(b), 1); mbar_init(d1_empty(b), ML_G_WARPS);
+            mbar_init(d2_full(b), 1); mbar_init(d2_empty(b), ML_F_WARPS);
         }
-        mbar_init(d2_full, 1); mbar_init(d2_empty, ML_EPI_WARPS);
+        for (int s = 0; s < ML_NH; ++s) { mbar_init(h_full(s), ML_G_WARPS); mbar_init(h_empty(s), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w1) : "memory");
@@ -92,50 +105,53 @@ mlp_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < p.hid_p; i += ML_THREADS) sb1[i] = p.b1[i];
+    for (int i = threadIdx.x; i < p.hid_p; i += ML_THREADS) sb1[i] = 0.5f * p.b1[i];
     for (int i = threadIdx.x; i < CP; i += ML_THREADS) {
         sb2[i] = p.b2[i];
         const bool in = p.ln_g != nullptr && i < p.ln_C;
         sg[i] = in ? p.ln_g[i] : 0.f;
-        sbt[i] = in ? p.ln_b[i] : 0.f;
+        sbt[i] = in ? p.ln_b[i] : ((p.ln_pad_one && (i == p.ln_C || i == p.ln_C + 1)) ? 1.f : 0.f);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(ml_smem_raw + (tmem_slot - raw));
-    const uint32_t tD1 = tmem_base, tD2 = tmem_base + 256;
+    const uint32_t tD1 = tmem_base, tD2 = tmem_base + Cfg::TMEM_D2;
 
+    // 20 warps start with 96 registers each; the final warps keep their residual window in registers and need
+    // more, TMA / MMA / the two idle warps almost none: setmaxnreg moves registers between warp groups of 4 (it is
+    // the first instruction of each role branch, so that the register allocator sees one limit per region).
+    // An increase can only take what THIS CTA released: 128 x (96 - 48) + 256 x (96 - 80) = 10240 >= 256 x (128 - 96).
+    if (warp < 4) {
+    if constexpr (ML_THREADS == 640) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     if (warp == 0) {
         // ===================================== TMA producer =====================================
         if (lane == 0) {
             int ws = 0, wph = 0, tc = 0;
-            auto w_slot = [&](uint32_t bytes) {
-                mbar_wait(w_empty(ws), wph ^ 1);
-                mbar_expect_tx(w_full(ws), bytes);
-                return sW + ws * ML_WSLOT;
-            };
-            auto w_next = [&]() { if (++ws == ML_WSLOTS) { ws = 0; wph ^= 1; } };
+            auto w_next = [&]() { if (++ws == ML_NW) { ws = 0; wph ^= 1; } };
             auto load_w1 = [&](int c) {
-                for (int kb = 0; kb < KB1; ++kb) {
-                    const uint32_t dst = w_slot(16384);
-                    tma_load_2d(dst, &map_w1, w_full(ws), kb * 64, c * 128);
-                    w_next();
-                }
+                mbar_wait(w_empty(ws), wph ^ 1);
+                mbar_expect_tx(w_full(ws), Cfg::WSLOT);
+#pragma unroll
+                for (int kb = 0; kb < KB1; ++kb)
+                    tma_load_2d(sW + ws * Cfg::WSLOT + kb * 8192, &map_w1, w_full(ws), kb * 64, c * ML_CH);
+                w_next();
             };
             auto load_w2 = [&](int c) {
-                for (int k2 = 0; k2 < 2; ++k2) {
-                    const uint32_t dst = w_slot(CP * 128);
-                    tma_load_2d(dst, &map_w2, w_full(ws), (c * 2 + k2) * 64, 0);
-                    w_next();
-                }
+                mbar_wait(w_empty(ws), wph ^ 1);
+                mbar_expect_tx(w_full(ws), Cfg::WSLOT);
+                tma_load_2d(sW + ws * Cfg::WSLOT, &map_w2, w_full(ws), c * ML_CH, 0);
+                w_next();
             };
             for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++tc) {
                 mbar_wait(a_empty, (tc & 1) ^ 1);
                 mbar_expect_tx(a_full, Cfg::A_BYTES);
+#pragma unroll
                 for (int kb = 0; kb < KB1; ++kb) tma_load_2d(sA + kb * 16384, &map_a, a_full, kb * 64, tile * 128);
                 load_w1(0);
+                if (NC > 1) load_w1(1);
                 for (int c = 0; c < NC; ++c) {
-                    if (c + 1 < NC) load_w1(c + 1);
+                    if (c + 2 < NC) load_w1(c + 2);
                     load_w2(c);
                 }
             }
@@ -143,208 +159,258 @@ mlp_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     } else if (warp == 1) {
         // ===================================== MMA issuer =====================================
         if (lane == 0) {
-            const uint32_t idesc1 = umma_idesc(1, 128, 128), idesc2 = umma_idesc(1, 128, CP);
+            const uint32_t idesc1 = umma_idesc(1, 128, ML_CH), idesc2 = umma_idesc(1, 128, CP);
             int ws = 0, wph = 0, tc = 0;
-            int use_d1[2] = {0, 0}, use_h[2] = {0, 0};
-            auto w_next = [&]() { if (++ws == ML_WSLOTS) { ws = 0; wph ^= 1; } };
-            auto fc1 = [&](int c) {
-                const int b = c & 1;
-                mbar_wait(d1_empty(b), (use_d1[b] & 1) ^ 1);
+            int d1s = 0, d1ph = 0, hs = 0, hph = 0;
+            auto w_next = [&]() { if (++ws == ML_NW) { ws = 0; wph ^= 1; } };
+            auto fc1 = [&]() {
+                mbar_wait(d1_empty(d1s), d1ph ^ 1);
+                mbar_wait(w_full(ws), wph);
                 tc_fence_after();
+#pragma unroll
                 for (int kb = 0; kb < KB1; ++kb) {
-                    mbar_wait(w_full(ws), wph);
-                    tc_fence_after();
-                    const uint64_t da = umma_desc_sw128(sA + kb * 16384), db = umma_desc_sw128(sW + ws * ML_WSLOT);
+                    const uint64_t da = umma_desc_sw128(sA + kb * 16384), db = umma_desc_sw128(sW + ws * Cfg::WSLOT + kb * 8192);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        tc_mma_f16(tD1 + b * 128, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc1, (kb | k) != 0 ? 1u : 0u);
-                    tc_commit(w_empty(ws));
-                    w_next();
+                        tc_mma_f16(tD1 + d1s * ML_CH, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc1, (kb | k) != 0 ? 1u : 0u);
                 }
-                tc_commit(d1_full(b));
-                use_d1[b]++;
-            };
-            auto fc2 = [&](int c) {
-                const int b = c & 1;
-                mbar_wait(h_full(b), use_h[b] & 1);
-                tc_fence_after();
-                if (c == 0) { mbar_wait(d2_empty, (tc & 1) ^ 1); tc_fence_after(); }
-                for (int k2 = 0; k2 < 2; ++k2) {
-                    mbar_wait(w_full(ws), wph);
-                    tc_fence_after();
-                    const uint64_t da = umma_desc_sw128(sH + b * 32768 + k2 * 16384), db = umma_desc_sw128(sW + ws * ML_WSLOT);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        tc_mma_f16(tD2, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2, (c | k2 | k) != 0 ? 1u : 0u);
-                    tc_commit(w_empty(ws));
-                    w_next();
-                }
-                tc_commit(h_empty(b));
-                use_h[b]++;
+                tc_commit(w_empty(ws));
+                w_next();
+                tc_commit(d1_full(d1s));
+                if (++d1s == 2) { d1s = 0; d1ph ^= 1; }
             };
             for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++tc) {
+                const uint32_t d2 = tD2 + (uint32_t)((tc & 1) * CP);
+                int issued = 0;
                 mbar_wait(a_full, tc & 1);
                 tc_fence_after();
-                fc1(0);
-                if (NC == 1) tc_commit(a_empty);
+                fc1(); if (++issued == NC) tc_commit(a_empty);
+                if (NC > 1) { fc1(); if (++issued == NC) tc_commit(a_empty); }
                 for (int c = 0; c < NC; ++c) {
-                    if (c + 1 < NC) {
-                        fc1(c + 1);
-                        if (c + 2 == NC) tc_commit(a_empty);        // last fc1 of the tile issued: A may be refilled
-                    }
-                    fc2(c);
+                    if (c + 2 < NC) { fc1(); if (++issued == NC) tc_commit(a_empty); }   // A may be refilled once the last fc1 retires
+                    // fc2(c)
+                    mbar_wait(h_full(hs), hph);
+                    if (c == 0) mbar_wait(d2_empty(tc & 1), ((tc >> 1) & 1) ^ 1);
+                    mbar_wait(w_full(ws), wph);
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_sw128(sH + hs * 16384), db = umma_desc_sw128(sW + ws * Cfg::WSLOT);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        tc_mma_f16(d2, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2, (c | k) != 0 ? 1u : 0u);
+                    tc_commit(w_empty(ws));
+                    w_next();
+                    tc_commit(h_empty(hs));
+                    if (++hs == ML_NH) { hs = 0; hph ^= 1; }
                 }
-                tc_commit(d2_full);
+                tc_commit(d2_full(tc & 1));
             }
         }
-    } else {
-        // ===================================== epilogue warps =====================================
-        const int ew = warp - 2, lg = warp & 3, q = ew >> 2;          // q: 32-column quarter of a 128-col chunk
-        constexpr int NP = CP / 64;
-        float* stg = reinterpret_cast<float*>(ml_smem_raw + (sH - raw));   // [64][SROW] fp32, aliases H
-        const bool has_ln = p.ln_g != nullptr;
-        const float inv_c = 1.f / (float)(p.ln_C > 0 ? p.ln_C : 1);
-
-        // this warp finishes rows  tile*128 + half*64 + ew*RPW + i  (i < RPW) in half `half`
-        auto row_of = [&](int tile_, int j) { return tile_ * 128 + (j / ML_RPW) * 64 + ew * ML_RPW + (j % ML_RPW); };
-        float2 resv[2 * ML_RPW][NP];
-#pragma unroll
-        for (int j = 0; j < 2 * ML_RPW; ++j) {
-            const int m = row_of(blockIdx.x, j);
-            const bool ok = (int)blockIdx.x < p.m_tiles && m < p.M;
-#pragma unroll
-            for (int k = 0; k < NP; ++k)
-                resv[j][k] = ok ? __ldg(reinterpret_cast<const float2*>(p.res + (size_t)m * p.ld32 + 64 * k + 2 * lane))
-                                : make_float2(0.f, 0.f);
-        }
-        int n_d1[2] = {0, 0}, tc = 0;
-        for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++tc) {
-            // ---------------- GELU stage: D1 chunk -> bf16 operand tile H[c&1] ----------------
+    }
+    } else if (warp < 4 + ML_G_WARPS) {
+        // ===================================== GELU warps =====================================
+        if constexpr (ML_THREADS == 640) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+        const int lg = warp & 3, q = (warp - 4) >> 2;                // TMEM lane group, 32-column half of the chunk
+        const int r = lg * 32 + lane;                                // tile row of this thread
+        int d1s = 0, d1ph = 0, hs = 0, hph = 0;
+        for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
             for (int c = 0; c < NC; ++c) {
-                const int b = c & 1;
-                mbar_wait(d1_full(b), n_d1[b] & 1);
+                mbar_wait(d1_full(d1s), d1ph);
                 tc_fence_after();
-                // this warp: rows of lane group lg, hidden columns [q*W32*32, (q+1)*W32*32) of the chunk
-                constexpr int W32 = 4 / ML_QN;                           // 32-column blocks per warp
-                const int r = lg * 32 + lane;
+                uint32_t v[32];
+                tc_ld32(tD1 + ((uint32_t)(lg * 32) << 16) + (uint32_t)(d1s * ML_CH + q * 32), v);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(d1_empty(d1s));           // D1 stage may be overwritten
+                mbar_wait(h_empty(hs), hph ^ 1);                     // fc2 of the previous user of this H stage retired
+                const float4* bp = reinterpret_cast<const float4*>(sb1 + c * ML_CH + q * 32);
+                // K-major, 128B-swizzled operand layout: row r, 16 B chunk j -> r*128 + ((j ^ (r & 7)) << 4)
+                unsigned char* hrow = ml_smem_raw + (sH - raw) + hs * 16384 + r * 128;
 #pragma unroll
-                for (int sbk = 0; sbk < W32; ++sbk) {
-                    const int col0 = (q * W32 + sbk) * 32;               // column offset inside the 128-col chunk
-                    uint32_t v[32];
-                    tc_ld32(tD1 + ((uint32_t)(lg * 32) << 16) + (uint32_t)(b * 128 + col0), v);
-                    if (sbk == W32 - 1) {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(d1_empty(b));         // D1[b] may be overwritten
-                    }
-                    if (sbk == 0) mbar_wait(h_empty(b), (n_d1[b] & 1) ^ 1);   // fc2 of the previous user of H[b] retired
-                    const float4* bp = reinterpret_cast<const float4*>(sb1 + c * 128 + col0);
-                    // K-major, 128B-swizzled operand layout: row r, 16 B chunk j -> r*128 + ((j ^ (r & 7)) << 4)
-                    unsigned char* hrow = ml_smem_raw + (sH - raw) + b * 32768 + (col0 >> 6) * 16384 + r * 128;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float4 b0 = bp[2 * j], b1v = bp[2 * j + 1];
-                        const uint32_t p0 = packf<SRK_BF16>(gelu_erf(__uint_as_float(v[8 * j]) + b0.x), gelu_erf(__uint_as_float(v[8 * j + 1]) + b0.y));
-                        const uint32_t p1 = packf<SRK_BF16>(gelu_erf(__uint_as_float(v[8 * j + 2]) + b0.z), gelu_erf(__uint_as_float(v[8 * j + 3]) + b0.w));
-                        const uint32_t p2 = packf<SRK_BF16>(gelu_erf(__uint_as_float(v[8 * j + 4]) + b1v.x), gelu_erf(__uint_as_float(v[8 * j + 5]) + b1v.y));
-                        const uint32_t p3 = packf<SRK_BF16>(gelu_erf(__uint_as_float(v[8 * j + 6]) + b1v.z), gelu_erf(__uint_as_float(v[8 * j + 7]) + b1v.w));
-                        const int chunk = ((col0 >> 5) & 1) * 4 + j;
-                        *reinterpret_cast<uint4*>(hrow + ((chunk ^ (r & 7)) << 4)) = make_uint4(p0, p1, p2, p3);
-                    }
+                for (int j = 0; j < 4; ++j) {
+                    const float4 b0 = bp[2 * j], b1v = bp[2 * j + 1];
+                    uint32_t a0, a1, pk[4];
+                    unpack64(gelu2(pack64(v[8 * j], v[8 * j + 1]), pack64(__float_as_uint(b0.x), __float_as_uint(b0.y))), a0, a1);
+                    pk[0] = packf<SRK_BF16>(__uint_as_float(a0), __uint_as_float(a1));
+                    unpack64(gelu2(pack64(v[8 * j + 2], v[8 * j + 3]), pack64(__float_as_uint(b0.z), __float_as_uint(b0.w))), a0, a1);
+                    pk[1] = packf<SRK_BF16>(__uint_as_float(a0), __uint_as_float(a1));
+                    unpack64(gelu2(pack64(v[8 * j + 4], v[8 * j + 5]), pack64(__float_as_uint(b1v.x), __float_as_uint(b1v.y))), a0, a1);
+                    pk[2] = packf<SRK_BF16>(__uint_as_float(a0), __uint_as_float(a1));
+                    unpack64(gelu2(pack64(v[8 * j + 6], v[8 * j + 7]), pack64(__float_as_uint(b1v.z), __float_as_uint(b1v.w))), a0, a1);
+                    pk[3] = packf<SRK_BF16>(__uint_as_float(a0), __uint_as_float(a1));
+                    const int chunk = q * 4 + j;
+                    *reinterpret_cast<uint4*>(hrow + ((chunk ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
                 __syncwarp();
-                if (lane == 0) mbar_arrive(h_full(b));
-                n_d1[b]++;
+                if (lane == 0) mbar_arrive(h_full(hs));
+                if (++d1s == 2) { d1s = 0; d1ph ^= 1; }
+                if (++hs == ML_NH) { hs = 0; hph ^= 1; }
             }
-            // ---------------- final stage: D2 -> x', LayerNorm / cast ----------------
-            mbar_wait(d2_full, tc & 1);
-            tc_fence_after();
+        }
+    } else {
+        // ===================================== final warps =====================================
+        if constexpr (ML_THREADS == 640) asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
+        constexpr int QN = ML_F_WARPS / 4;                                   // final warps per TMEM lane group
+        const int fw = warp - 4 - ML_G_WARPS, lg = warp & 3, qh = fw >> 2;   // qh: column slice drained in phase T
+        constexpr int NP = CP / 64;
+        constexpr int RB = ML_RB;                                            // rows whose LayerNorm butterflies are interleaved
+        constexpr int NBK = ML_NBK;
+        static_assert(ML_RPW % (2 * NBK * RB) == 0 && (CP / 32) % QN == 0, "final-stage tiling");
+        float* stg = reinterpret_cast<float*>(ml_smem_raw + (sStg - raw));   // [64][SROW] fp32
+        const float inv_c = 1.f / (float)(p.ln_C > 0 ? p.ln_C : 1);
+
+        // This warp finishes rows  tile*128 + half*64 + fw*RPW + i  (i < RPW) of each half.  Its rows form one
+        // sequence over (tile, half, i); position pos = (2 * tile_iteration + half) * RPW + i.
+        auto row_at = [&](int pos) {
+            const int th = pos / ML_RPW, i = pos - th * ML_RPW;
+            const int tile_ = (int)blockIdx.x + (th >> 1) * (int)gridDim.x;
+            return tile_ < p.m_tiles ? tile_ * 128 + (th & 1) * 64 + fw * ML_RPW + i : p.M;
+        };
+        // Phase R layout: a warp finishes TWO rows at a time, one per half-warp; lane hl = lane & 15 owns the four
+        // consecutive columns 64 k + 4 hl (k < NP) of its row, so every access is a 16 B vector and a half-warp
+        // covers 256 contiguous bytes of the row.
+        const int hl = lane & 15, hh = lane >> 4;
+        // (rows beyond the problem are clamped to the last row: an unconditional load keeps the request in flight in
+        //  the slot's own registers -- a predicated load + select makes the compiler wait for it on the spot)
+        auto load_res = [&](float4 (&dst)[NP], int m) {
+            const float* rp = p.res + (size_t)(m < p.M ? m : p.M - 1) * p.ld32 + 4 * hl;
 #pragma unroll
+            for (int k = 0; k < NP; ++k)
+                asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(dst[k].x), "=f"(dst[k].y), "=f"(dst[k].z), "=f"(dst[k].w) : "l"(rp + 64 * k));
+        };
+        // residual rows: a rolling window of NBK banks x RB row pairs, NBK * RB pairs ahead of the pair being finished
+        float4 resv[NBK][RB][NP];
+#pragma unroll
+        for (int i = 0; i < NBK * RB; ++i) load_res(resv[i / RB][i % RB], row_at(2 * i + hh));
+        // lane i (< RPW) describes row i of the half being finished: its GEMM row and the row of the 16-bit output
+        // (my_m, my_r16) and the GEMM row 2 * NBK * RB positions further on (my_mn: the residual row to request)
+        int my_m = 0, my_r16 = 0, my_mn = 0;
+        bool colin[NP];                                                      // this lane's column group lies inside the LayerNorm width
+#pragma unroll
+        for (int k = 0; k < NP; ++k) colin[k] = 64 * k + 4 * hl < p.ln_C;
+        const bool o_bf16 = p.out16_dtype == SRK_BF16;
+        auto pack = [&](float a, float b) { return o_bf16 ? packf<SRK_BF16>(a, b) : packf<SRK_FP16>(a, b); };
+
+        // one step: RB row pairs starting at row i0 of the staged half, residuals in bank `rs`
+        auto step = [&](float4 (&rs)[RB][NP], int i0) {
+            int m[RB], r16[RB];
+            float4 v[RB][NP];
+#pragma unroll
+            for (int rr = 0; rr < RB; ++rr) {
+                const int i = i0 + 2 * rr + hh;                              // this half-warp's row of the staged half
+                m[rr] = __shfl_sync(0xffffffffu, my_m, i);
+                r16[rr] = __shfl_sync(0xffffffffu, my_r16, i);
+                const float* srow = stg + (size_t)(fw * ML_RPW + i) * Cfg::SROW + 4 * hl;
+#pragma unroll
+                for (int k = 0; k < NP; ++k) {
+                    v[rr][k] = *reinterpret_cast<const float4*>(srow + 64 * k);
+                    const float4 bb = *reinterpret_cast<const float4*>(sb2 + 64 * k + 4 * hl);
+                    v[rr][k].x += bb.x + rs[rr][k].x; v[rr][k].y += bb.y + rs[rr][k].y;
+                    v[rr][k].z += bb.z + rs[rr][k].z; v[rr][k].w += bb.w + rs[rr][k].w;
+                }
+                load_res(rs[rr], __shfl_sync(0xffffffffu, my_mn, i));        // the row NBK * RB pairs ahead, same slot
+                if (m[rr] < p.M) {
+                    float* oo = p.out32 + (size_t)m[rr] * p.ld32 + 4 * hl;
+#pragma unroll
+                    for (int k = 0; k < NP; ++k) *reinterpret_cast<float4*>(oo + 64 * k) = v[rr][k];
+                }
+            }
+            if constexpr (LN) {
+                float sm[RB], mean[RB], qq[RB];
+#pragma unroll
+                for (int rr = 0; rr < RB; ++rr) {
+                    sm[rr] = 0.f;
+#pragma unroll
+                    for (int k = 0; k < NP; ++k) sm[rr] += (v[rr][k].x + v[rr][k].y) + (v[rr][k].z + v[rr][k].w);   // pad columns are exactly 0
+                }
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+                    for (int rr = 0; rr < RB; ++rr) sm[rr] += __shfl_xor_sync(0xffffffffu, sm[rr], o);
+#pragma unroll
+                for (int rr = 0; rr < RB; ++rr) {
+                    mean[rr] = sm[rr] * inv_c; qq[rr] = 0.f;
+#pragma unroll
+                    for (int k = 0; k < NP; ++k) {
+                        v[rr][k].x -= mean[rr]; v[rr][k].y -= mean[rr]; v[rr][k].z -= mean[rr]; v[rr][k].w -= mean[rr];
+                        const float q4 = (v[rr][k].x * v[rr][k].x + v[rr][k].y * v[rr][k].y) + (v[rr][k].z * v[rr][k].z + v[rr][k].w * v[rr][k].w);
+                        qq[rr] += colin[k] ? q4 : 0.f;
+                    }
+                }
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+                    for (int rr = 0; rr < RB; ++rr) qq[rr] += __shfl_xor_sync(0xffffffffu, qq[rr], o);
+#pragma unroll
+                for (int rr = 0; rr < RB; ++rr) {
+                    const float rstd = rsqrtf(qq[rr] * inv_c + 1e-5f);
+                    if (m[rr] < p.M) {
+                        uint16_t* o16 = p.out16 + (size_t)r16[rr] * p.ld16 + 4 * hl;
+#pragma unroll
+                        for (int k = 0; k < NP; ++k) {
+                            const float4 gg = *reinterpret_cast<const float4*>(sg + 64 * k + 4 * hl);    // gamma = 0 on pad columns
+                            const float4 bb = *reinterpret_cast<const float4*>(sbt + 64 * k + 4 * hl);
+                            *reinterpret_cast<uint2*>(o16 + 64 * k) =
+                                make_uint2(pack(v[rr][k].x * rstd * gg.x + bb.x, v[rr][k].y * rstd * gg.y + bb.y),
+                                           pack(v[rr][k].z * rstd * gg.z + bb.z, v[rr][k].w * rstd * gg.w + bb.w));
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int rr = 0; rr < RB; ++rr)
+                    if (p.out16 && m[rr] < p.M) {
+                        uint16_t* o16 = p.out16 + (size_t)m[rr] * p.ld16 + 4 * hl;
+#pragma unroll
+                        for (int k = 0; k < NP; ++k)
+                            *reinterpret_cast<uint2*>(o16 + 64 * k) = make_uint2(pack(v[rr][k].x, v[rr][k].y), pack(v[rr][k].z, v[rr][k].w));
+                    }
+            }
+        };
+
+        int tc = 0, pos = 0;
+        for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++tc) {
+            const uint32_t d2 = tD2 + (uint32_t)((tc & 1) * CP);
+            mbar_wait(d2_full(tc & 1), (tc >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
             for (int half = 0; half < 2; ++half) {
+                // ---- phase T: this half's two lane groups drain D2 into the staging tile (thread = row) ----
                 if ((lg >> 1) == half) {
                     float* srow = stg + (size_t)((lg & 1) * 32 + lane) * Cfg::SROW;
-#pragma unroll
-                    for (int jj = 0; jj < CP / (16 * ML_QN); ++jj) {
-                        const int c16 = q + ML_QN * jj;
+                    const uint32_t t_row = d2 + ((uint32_t)(lg * 32) << 16);
+#pragma unroll 1
+                    for (int jj = 0; jj < CP / 16 / QN; ++jj) {              // x16 loads, not unrolled: the residual window owns the registers
+                        const int c16 = qh * (CP / 16 / QN) + jj;
                         uint32_t v[16];
-                        asm volatile(
-                            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-                            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-                            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                            : "r"(tD2 + ((uint32_t)(lg * 32) << 16) + (uint32_t)(c16 * 16)));
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        tc_ld16_nowait(t_row + (uint32_t)(c16 * 16), v);
+                        tc_wait_ld16(v);
 #pragma unroll
                         for (int j = 0; j < 16; j += 4)
                             *reinterpret_cast<uint4*>(srow + c16 * 16 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                     }
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(d2_empty);                // this warp's part of D2 is drained
+                    if (lane == 0) mbar_arrive(d2_empty(tc & 1));            // this warp's part of D2 is drained
                 }
-                asm volatile("bar.sync 5, %0;" ::"n"(32 * ML_EPI_WARPS) : "memory");   // staging complete
-#pragma unroll
-                for (int i = 0; i < ML_RPW; ++i) {
-                    const int j = half * ML_RPW + i;
-                    const int m = row_of(tile, j);
-                    const bool valid = m < p.M;
-                    const float* srow = stg + (size_t)(ew * ML_RPW + i) * Cfg::SROW;
-                    float2 v[NP];
-#pragma unroll
-                    for (int k = 0; k < NP; ++k) {
-                        v[k] = *reinterpret_cast<const float2*>(srow + 64 * k + 2 * lane);
-                        const float2 b2v = *reinterpret_cast<const float2*>(sb2 + 64 * k + 2 * lane);
-                        v[k].x += b2v.x + resv[j][k].x;
-                        v[k].y += b2v.y + resv[j][k].y;
-                    }
-                    {   // request row j of the next tile into the same registers
-                        const int tn = tile + gridDim.x;
-                        const int mn = row_of(tn, j);
-                        const bool ok = tn < p.m_tiles && mn < p.M;
-#pragma unroll
-                        for (int k = 0; k < NP; ++k)
-                            resv[j][k] = ok ? __ldg(reinterpret_cast<const float2*>(p.res + (size_t)mn * p.ld32 + 64 * k + 2 * lane))
-                                            : make_float2(0.f, 0.f);
-                    }
-                    if (valid) {
-                        float* oo = p.out32 + (size_t)m * p.ld32 + 2 * lane;
-#pragma unroll
-                        for (int k = 0; k < NP; ++k) *reinterpret_cast<float2*>(oo + 64 * k) = v[k];
-                    }
-                    if (has_ln) {
-                        float sm = 0.f;
-#pragma unroll
-                        for (int k = 0; k < NP; ++k) sm += v[k].x + v[k].y;
-                        const float mean = warp_sum(sm) * inv_c;
-                        float qq = 0.f;
-#pragma unroll
-                        for (int k = 0; k < NP; ++k)
-                            if (64 * k + 2 * lane < p.ln_C) { const float a0 = v[k].x - mean, a1 = v[k].y - mean; qq += a0 * a0 + a1 * a1; }
-                        const float rstd = rsqrtf(warp_sum(qq) * inv_c + 1e-5f);
-                        int r16 = m;
-                        if (valid && p.ln_win_shift >= 0) {
-                            const int bi = m / p.T;
-                            r16 = bi * p.T + token_to_win_pos(m - bi * p.T, p.H, p.W, p.ln_win_shift);
-                        }
-                        if (valid) {
-                            uint16_t* o16 = p.out16 + (size_t)r16 * p.ld16 + 2 * lane;
-#pragma unroll
-                            for (int k = 0; k < NP; ++k) {
-                                const float2 gg = *reinterpret_cast<const float2*>(sg + 64 * k + 2 * lane);
-                                const float2 bb = *reinterpret_cast<const float2*>(sbt + 64 * k + 2 * lane);
-                                const float y0 = (v[k].x - mean) * rstd * gg.x + bb.x;     // gamma = beta = 0 on pad columns
-                                const float y1 = (v[k].y - mean) * rstd * gg.y + bb.y;
-                                *reinterpret_cast<uint32_t*>(o16 + 64 * k) = pack2(y0, y1, p.out16_dtype);
-                            }
-                        }
-                    } else if (p.out16 && valid) {
-                        uint16_t* o16 = p.out16 + (size_t)m * p.ld16 + 2 * lane;
-#pragma unroll
-                        for (int k = 0; k < NP; ++k) *reinterpret_cast<uint32_t*>(o16 + 64 * k) = pack2(v[k].x, v[k].y, p.out16_dtype);
+                {   // row bookkeeping of this half: one row per lane
+                    my_m = row_at(pos + (lane < ML_RPW ? lane : 0));
+                    my_mn = row_at(pos + 2 * NBK * RB + (lane < ML_RPW ? lane : 0));
+                    my_r16 = my_m;
+                    if (LN && my_m < p.M && p.ln_win_shift >= 0) {
+                        const int bi = my_m / p.T;
+                        my_r16 = bi * p.T + token_to_win_pos(my_m - bi * p.T, p.H, p.W, p.ln_win_shift);
                     }
                 }
-                asm volatile("bar.sync 5, %0;" ::"n"(32 * ML_EPI_WARPS) : "memory");   // staging free
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * ML_F_WARPS) : "memory");   // staging complete
+                // ---- phase R: RPW rows per warp, lane = column pair, RB rows per step ----
+#pragma unroll 1
+                for (int i0 = 0; i0 < ML_RPW; i0 += 2 * NBK * RB, pos += 2 * NBK * RB) {
+#pragma unroll
+                    for (int bk = 0; bk < NBK; ++bk) step(resv[bk], i0 + 2 * bk * RB);
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * ML_F_WARPS) : "memory");   // staging free
             }
         }
     }
@@ -356,15 +422,15 @@ mlp_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
 }
 
-template <int CP>
+template <int CP, bool LN>
 static int launch_mlp(const srk_mlp_args* a, cudaStream_t st) {
     using Cfg = MlCfg<CP>;
     MlpP p{};
-    p.M = a->M; p.C = a->C; p.hid_p = a->hid_p; p.NC = a->hid_p / 128; p.m_tiles = ceil_div(a->M, 128);
+    p.M = a->M; p.C = a->C; p.hid_p = a->hid_p; p.NC = a->hid_p / ML_CH; p.m_tiles = ceil_div(a->M, 128);
     p.H = a->H; p.W = a->W; p.T = (a->H > 0 && a->W > 0) ? a->H * a->W : 0;
     p.b1 = a->b1; p.b2 = a->b2; p.res = a->res; p.out32 = a->out32; p.ld32 = a->ld32;
     p.out16 = (uint16_t*)a->out16; p.ld16 = a->ld16; p.out16_dtype = a->out16_dtype;
-    p.ln_g = a->ln_g; p.ln_b = a->ln_b; p.ln_C = a->ln_C; p.ln_win_shift = a->ln_win_shift;
+    p.ln_g = a->ln_g; p.ln_b = a->ln_b; p.ln_C = a->ln_C; p.ln_win_shift = a->ln_win_shift; p.ln_pad_one = a->ln_pad_one;
     CUtensorMap ma, mw1, mw2;
     {
         cuuint64_t dims[2] = {(cuuint64_t)CP, (cuuint64_t)a->M};
@@ -375,21 +441,22 @@ static int launch_mlp(const srk_mlp_args* a, cudaStream_t st) {
     {
         cuuint64_t dims[2] = {(cuuint64_t)CP, (cuuint64_t)a->hid_p};
         cuuint64_t strides[1] = {(cuuint64_t)CP * 2};
-        cuuint32_t box[2] = {64, 128};
+        cuuint32_t box[2] = {64, ML_CH};
         if (int rc = encode_map(&mw1, SRK_BF16, 2, a->W1, dims, strides, box)) return rc;
     }
     {
         cuuint64_t dims[2] = {(cuuint64_t)a->hid_p, (cuuint64_t)CP};
         cuuint64_t strides[1] = {(cuuint64_t)a->hid_p * 2};
-        cuuint32_t box[2] = {64, (cuuint32_t)CP};
+        cuuint32_t box[2] = {ML_CH, (cuuint32_t)CP};
         if (int rc = encode_map(&mw2, SRK_BF16, 2, a->W2, dims, strides, box)) return rc;
     }
-    const size_t smem = (size_t)Cfg::A_BYTES + Cfg::H_BYTES + Cfg::W_BYTES + Cfg::AUX + (size_t)(a->hid_p + 3 * CP) * 4 + 1024;
+    const size_t smem = (size_t)Cfg::A_BYTES + Cfg::H_BYTES + Cfg::W_BYTES + Cfg::STG_BYTES + Cfg::AUX +
+                        (size_t)(a->hid_p + 3 * CP) * 4 + 1024;
     SRK_REQUIRE(smem <= (size_t)ML_SMEM_TOTAL, "mlp: hidden dim %d needs too much shared memory", a->hid_p);
     static bool attr[64] = {};
-    if (first_use_on_device(attr)) SRK_CUDA(cudaFuncSetAttribute(mlp_tc5_kernel<CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, ML_SMEM_TOTAL));
+    if (first_use_on_device(attr)) SRK_CUDA(cudaFuncSetAttribute(mlp_tc5_kernel<CP, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, ML_SMEM_TOTAL));
     const int grid = p.m_tiles < num_sms() ? p.m_tiles : num_sms();
-    mlp_tc5_kernel<CP><<<grid, ML_THREADS, smem, st>>>(ma, mw1, mw2, p);
+    mlp_tc5_kernel<CP, LN><<<grid, ML_THREADS, smem, st>>>(ma, mw1, mw2, p);
     SRK_LAUNCH_CHECK("mlp_tc5_kernel");
     return 0;
 }
@@ -401,11 +468,13 @@ using namespace srk;
 extern "C" int srk_mlp(const srk_mlp_args* a, void* stream) {
     SRK_REQUIRE(a && a->A && a->W1 && a->W2 && a->b1 && a->b2 && a->res && a->out32, "mlp: null pointer");
     SRK_REQUIRE(a->M > 0 && a->Cp % 64 == 0 && a->Cp >= 64 && a->Cp <= 192, "mlp: Cp must be 64, 128 or 192");
-    SRK_REQUIRE(a->hid_p % 128 == 0 && a->hid_p >= 128, "mlp: hidden dim must be padded to a multiple of 128");
+    SRK_REQUIRE(a->hid_p % ML_CH == 0 && a->hid_p >= ML_CH, "mlp: hidden dim must be padded to a multiple of 64");
     SRK_REQUIRE(a->lda >= a->Cp && a->lda % 8 == 0 && a->ld32 >= a->Cp && a->ld32 % 4 == 0, "mlp: bad leading dims");
+    SRK_REQUIRE(((uintptr_t)a->res & 15) == 0 && ((uintptr_t)a->out32 & 15) == 0 && ((uintptr_t)a->out16 & 7) == 0, "mlp: res / out32 must be 16 B aligned, out16 8 B aligned");
     SRK_REQUIRE(!a->out16 || (a->ld16 >= a->Cp && a->ld16 % 8 == 0), "mlp: bad ld16");
     if (a->ln_g) {
-        SRK_REQUIRE(a->ln_b && a->out16 && a->ln_C > 0 && a->ln_C <= a->Cp, "mlp: bad LayerNorm arguments");
+        SRK_REQUIRE(a->ln_b && a->out16 && a->ln_C > 0 && a->ln_C <= a->Cp && a->ln_C % 4 == 0, "mlp: bad LayerNorm arguments (ln_C must be a multiple of 4)");
+        SRK_REQUIRE(!a->ln_pad_one || (a->ln_C % 2 == 0 && a->ln_C + 2 <= a->Cp), "mlp: ln_pad_one needs two pad columns");
         if (a->ln_win_shift >= 0)
             SRK_REQUIRE(a->H > 0 && a->W > 0 && a->H % 8 == 0 && a->W % 8 == 0 && a->M % (a->H * a->W) == 0 &&
                         (a->ln_win_shift == 0 || a->ln_win_shift == 4), "mlp: bad window geometry");
@@ -414,9 +483,10 @@ extern "C" int srk_mlp(const srk_mlp_args* a, void* stream) {
         return fail(SRK_ERR_UNSUPPORTED, "mlp: the fused MLP kernel exists for the tcgen05 engine only");
     ProfScope ps(SRK_PROF_GEMM, stream);
     cudaStream_t st = (cudaStream_t)stream;
+    const bool ln = a->ln_g != nullptr;
     switch (a->Cp) {
-        case 64: return launch_mlp<64>(a, st);
-        case 128: return launch_mlp<128>(a, st);
-        default: return launch_mlp<192>(a, st);
+        case 64: return ln ? launch_mlp<64, true>(a, st) : launch_mlp<64, false>(a, st);
+        case 128: return ln ? launch_mlp<128, true>(a, st) : launch_mlp<128, false>(a, st);
+        default: return ln ? launch_mlp<192, true>(a, st) : launch_mlp<192, false>(a, st);
     }
 }

@@ -3,7 +3,6 @@
 // token-major (NHWC) activations with an fp32 residual stream.
 #include "common.cuh"
 #include <vector>
-#include <stdlib.h>
 
 namespace srk {
 
@@ -82,10 +81,9 @@ static int check_swin_plan(const srk_swinir_plan* p) {
 using namespace srk;
 
 namespace srk {
-// SRK_FOLD_TAIL=0 runs the upsampler convs one by one (the folded tail needs the tcgen05 engine's 5x5 conv)
-bool fold_tail_enabled() {
-    const char* e = getenv("SRK_FOLD_TAIL");
-    return (!e || atoi(e) != 0) && srk_get_engine() == SRK_ENGINE_TCGEN05;
+// the folded tail needs the tcgen05 engine's 5x5 conv; SRK_OPT_NO_FOLD_TAIL runs the upsampler convs one by one
+static bool fold_tail_enabled(int options) {
+    return !(options & SRK_OPT_NO_FOLD_TAIL) && srk_get_engine() == SRK_ENGINE_TCGEN05;
 }
 // the folded reconstruction tail: ONE 5x5 conv F -> s*s written as image pixels + the ring pass
 int run_folded_tail(const srk_tail_fold& f, const void* feat, int B, int H, int W, int s, float out_scale, float* y,
@@ -104,65 +102,13 @@ int run_folded_tail(const srk_tail_fold& f, const void* feat, int B, int H, int 
 extern "C" size_t srk_swinir_workspace_bytes(const srk_swinir_plan* p, int B, int h, int w) {
     if (!p || B <= 0 || h <= 0 || w <= 0) return 0;
     SwinBufs b;
-    const size_t whole = swin_layout(p, B, pad8(h), pad8(w), nullptr, &b);
-    if (B < 2) return whole;
-    // the two-stream mode lays the two half batches out one after the other
-    const size_t halves = swin_layout(p, B / 2, pad8(h), pad8(w), nullptr, &b) + swin_layout(p, B - B / 2, pad8(h), pad8(w), nullptr, &b);
-    return whole > halves ? whole : halves;
+    return swin_layout(p, B, pad8(h), pad8(w), nullptr, &b);
 }
 
 #define TRY(expr) do { int rc__ = (expr); if (rc__) return rc__; } while (0)
 
-namespace srk {
-extern thread_local int g_sm_cap;
-int num_sms();
-// SRK_STREAMS=2 (experiment): the batch is split in two halves that run on two streams, each with persistent
-// grids sized for half of the SMs, so the HBM-bound kernels of one half overlap the compute-bound ones of the other
-static int n_streams() {
-    const char* e = getenv("SRK_STREAMS");
-    return e && atoi(e) == 2 ? 2 : 1;
-}
-}  // namespace srk
-static int swinir_forward_one(const srk_swinir_plan* p, const float* x, float* y, int B, int h, int w, void* workspace,
-                              size_t workspace_bytes, void* stream);
-
 extern "C" int srk_swinir_forward(const srk_swinir_plan* p, const float* x, float* y, int B, int h,
                                   int w, void* workspace, size_t workspace_bytes, void* stream) {
-    if (n_streams() == 1 || B < 2 || !p || !workspace)
-        return swinir_forward_one(p, x, y, B, h, w, workspace, workspace_bytes, stream);
-    TRY(check_swin_plan(p));
-    const int B0 = B / 2, B1 = B - B0, H = pad8(h), W = pad8(w);
-    SwinBufs bb;
-    const size_t need0 = swin_layout(p, B0, H, W, nullptr, &bb), need1 = swin_layout(p, B1, H, W, nullptr, &bb);
-    if (need0 + need1 > workspace_bytes)
-        return fail(SRK_ERR_WORKSPACE, "swinir: workspace %zu < %zu bytes", workspace_bytes, need0 + need1);
-    static cudaStream_t side[64] = {};
-    static cudaEvent_t ev_fork[64] = {}, ev_join[64] = {};
-    int dev = 0;
-    SRK_CUDA(cudaGetDevice(&dev));
-    SRK_REQUIRE(dev >= 0 && dev < 64, "swinir: device index out of range");
-    if (!side[dev]) {
-        SRK_CUDA(cudaStreamCreateWithFlags(&side[dev], cudaStreamNonBlocking));
-        SRK_CUDA(cudaEventCreateWithFlags(&ev_fork[dev], cudaEventDisableTiming));
-        SRK_CUDA(cudaEventCreateWithFlags(&ev_join[dev], cudaEventDisableTiming));
-    }
-    cudaStream_t st = (cudaStream_t)stream;
-    SRK_CUDA(cudaEventRecord(ev_fork[dev], st));
-    SRK_CUDA(cudaStreamWaitEvent(side[dev], ev_fork[dev], 0));
-    const int s = p->upscale;
-    g_sm_cap = 0;
-    g_sm_cap = num_sms() / 2;
-    int rc = swinir_forward_one(p, x, y, B0, h, w, workspace, need0, stream);
-    if (!rc) rc = swinir_forward_one(p, x + (size_t)B0 * h * w, y + (size_t)B0 * h * s * w * s, B1, h, w,
-                                     (char*)workspace + need0, need1, (void*)side[dev]);
-    g_sm_cap = 0;
-    SRK_CUDA(cudaEventRecord(ev_join[dev], side[dev]));
-    SRK_CUDA(cudaStreamWaitEvent(st, ev_join[dev], 0));
-    return rc;
-}
-
-static int swinir_forward_one(const srk_swinir_plan* p, const float* x, float* y, int B, int h,
-                              int w, void* workspace, size_t workspace_bytes, void* stream) {
     TRY(check_swin_plan(p));
     SRK_REQUIRE(x && y && workspace, "swinir: null pointer");
     SRK_REQUIRE(B > 0 && h > 0 && w > 0, "swinir: bad input shape");
@@ -225,8 +171,7 @@ static int swinir_forward_one(const srk_swinir_plan* p, const float* x, float* y
     bool a16_ready = first_fused; // A16 already holds LN1 of the next block (fused producer)
     // qkv bias folded into the GEMM: the LayerNorm epilogue that produces a block's A rows writes 1.0 into the pad
     // columns C, C + 1 and the block's folded weight (w_qkv_fb) carries the bias there -> no bias add in the epilogue
-    static const bool fold_env = !(getenv("SRK_FOLD_QKV_BIAS") && atoi(getenv("SRK_FOLD_QKV_BIAS")) == 0);
-    const bool fold_ok = fold_env && Cp - C >= 2 && C % 2 == 0;
+    const bool fold_ok = !(p->options & SRK_OPT_NO_FOLD_QKV_BIAS) && Cp - C >= 2 && C % 2 == 0;
     bool a16_ones = false;
     bool final_norm_done = false;
     for (int l = 0; l < p->n_layers; ++l) {
@@ -242,8 +187,7 @@ static int swinir_forward_one(const srk_swinir_plan* p, const float* x, float* y
                 a16_ones = false;
             }
             a16_ready = false;
-            static const bool attn_env = !(getenv("SRK_FUSED_ATTN") && atoi(getenv("SRK_FUSED_ATTN")) == 0);
-            const bool fused_attn = attn_env && fuse_ln && p->dp == 32 && nH % 2 == 0 && p->ao_p == nH * 32 &&
+            const bool fused_attn = !(p->options & SRK_OPT_NO_FUSED_ATTN) && fuse_ln && p->dp == 32 && nH % 2 == 0 && p->ao_p == nH * 32 &&
                                     b.nq_p == 3 * nH * 32;
             if (fused_attn) {
                 // qkv projection + window attention in one kernel: q, k, v stay in shared memory
@@ -275,11 +219,10 @@ static int swinir_forward_one(const srk_swinir_plan* p, const float* x, float* y
             if (!fuse_ln)
                 TRY(srk_layernorm(b.XB, Cp, M, C, s.ln2_g, s.ln2_b, eps, a16, Cp, ldt, nullptr, H, W, -1, stream));
             const bool last = d == p->depths[l] - 1;
-            // the fused MLP kernel is correct but not yet faster than fc1 + fc2 (epilogue bound): opt-in
-            static const bool mlp_env = getenv("SRK_FUSED_MLP") && atoi(getenv("SRK_FUSED_MLP")) != 0;
-            const bool fused_mlp = mlp_env && fuse_ln && (Cp == 64 || Cp == 128 || Cp == 192) && p->hid_p % 128 == 0;
+            // fc1 + GELU + fc2 + residual [+ next norm1 | + fp16 cast] in ONE tcgen05 kernel (mlp_tc5.cu): the hidden
+            // activation never reaches HBM.  The two-GEMM sequence below remains for the legacy engine / odd shapes.
+            const bool fused_mlp = !(p->options & SRK_OPT_NO_FUSED_MLP) && fuse_ln && (Cp == 64 || Cp == 128 || Cp == 192) && p->hid_p % 64 == 0;
             if (fused_mlp) {
-                // fc1 + GELU + fc2 + residual [+ next norm1 | + fp16 cast] in one tcgen05 kernel
                 srk_mlp_args m{};
                 m.A = a16; m.lda = Cp; m.M = M; m.C = C; m.Cp = Cp; m.hid_p = p->hid_p;
                 m.W1 = s.w_fc1; m.b1 = s.b_fc1; m.W2 = s.w_fc2; m.b2 = s.b_fc2;
@@ -290,7 +233,8 @@ static int swinir_forward_one(const srk_swinir_plan* p, const float* x, float* y
                 } else {
                     const srk_stb_params& nx = p->stbs[blk + 1];
                     m.ln_g = nx.ln1_g; m.ln_b = nx.ln1_b; m.ln_C = C; m.ln_win_shift = nx.shift; m.out16_dtype = ldt;
-                    a16_ready = true; a16_ones = false;
+                    m.ln_pad_one = fold_ok && nx.w_qkv_fb != nullptr; a16_ones = m.ln_pad_one != 0;
+                    a16_ready = true;
                 }
                 // the kernel reads A (a16) by TMA tile-by-tile and writes out16 rows of OTHER tiles when the
                 // next block is shifted, so the 16-bit output must not alias the operand: ping-pong
@@ -369,7 +313,7 @@ static int swinir_forward_one(const srk_swinir_plan* p, const float* x, float* y
             g.act = SRK_ACT_LRELU; g.out16 = b.U[0]; g.ld16 = 64;
             TRY(srk_gemm(&g, stream));
         }
-        if (p->tail_fold.w && H >= 3 && W >= 3 && fold_tail_enabled()) {
+        if (p->tail_fold.w && H >= 3 && W >= 3 && fold_tail_enabled(p->options)) {
             TRY(run_folded_tail(p->tail_fold, b.U[0], B, H, W, s_up, out_scale, y, h * s_up, w * s_up, stream));
         } else {
             int Hh = H, Ww = W;
@@ -476,7 +420,7 @@ extern "C" int srk_edsr_forward(const srk_edsr_plan* p, const float* x, float* y
         g.res = b.HF; g.ld32 = Fp; g.out16 = b.U[0]; g.ld16 = Fp;
         TRY(srk_gemm(&g, stream));
     }
-    if (p->tail_fold.w && Fp == 64 && h >= 3 && w >= 3 && fold_tail_enabled())
+    if (p->tail_fold.w && Fp == 64 && h >= 3 && w >= 3 && fold_tail_enabled(p->options))
         return run_folded_tail(p->tail_fold, b.U[0], B, h, w, p->scale, 1.f, y, h * p->scale, w * p->scale, stream);
     int Hh = h, Ww = w;
     for (int k = 0; k < p->n_tail_up; ++k) {

@@ -184,6 +184,5 @@ __device__ __forceinline__ float actf(float v) {
 int encode_map(CUtensorMap* map, int dtype, int rank, const void* ptr, const cuuint64_t* dims,
                const cuuint64_t* strides_bytes, const cuuint32_t* box);
 int num_sms();
-extern thread_local int g_sm_cap;
 
 }  // namespace srk

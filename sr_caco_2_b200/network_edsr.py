@@ -52,6 +52,7 @@ class EDSR(nn.Module):
             ups += [nn.Conv2d(n_feats, 4 * n_feats, 3, padding=1), nn.PixelShuffle(2)]
         self.tail = nn.Sequential(nn.Sequential(*ups), nn.Conv2d(n_feats, in_chans, 3, padding=1))
         self._plan = self._keep = self._ws = None
+        self.options = 0             # srk.h SRK_OPT_* bits; 0 = product path
         self.register_load_state_dict_post_hook(lambda mod, keys: mod._invalidate())
 
     def _invalidate(self):
@@ -118,6 +119,7 @@ class EDSR(nn.Module):
         B, _, h, w = x.shape
         if self._plan is None:
             self._build_plan()
+        self._plan.options = int(self.options)
         with torch.cuda.device(x.device):
             need = lib.srk_edsr_workspace_bytes(C.byref(self._plan), B, h, w)
             if self._ws is None or self._ws.numel() < need or self._ws.device != x.device:

@@ -177,6 +177,7 @@ class SwinIR(nn.Module):
         self._plan = None
         self._keep = None
         self._ws = None
+        self.options = 0             # srk.h SRK_OPT_* bits (tests switch single fusions off); 0 = product path
         self.register_load_state_dict_post_hook(lambda mod, keys: mod._invalidate())
 
     @staticmethod
@@ -317,6 +318,7 @@ class SwinIR(nn.Module):
             plan.upsample[0] = L.ConvParams(k(w), k(b), Cp, 64)
             plan.n_upsample = 1
         plan.linear_dtype, plan.conv_dtype = linear_dtype, conv_dtype
+        plan.options = int(self.options)
         keep += [stbs, convs, convs0, convs1, depths]
         self._plan, self._keep = plan, keep
         assert all(t.device == dev for t in keep if isinstance(t, torch.Tensor))
@@ -337,6 +339,7 @@ class SwinIR(nn.Module):
         B, _, h, w = x.shape
         if self._plan is None:
             self._build_plan()
+        self._plan.options = int(self.options)
         with torch.cuda.device(x.device):
             need = lib.srk_swinir_workspace_bytes(C.byref(self._plan), B, h, w)
             if self._ws is None or self._ws.numel() < need or self._ws.device != x.device:

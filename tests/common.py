@@ -162,3 +162,39 @@ def cfg_classical(scale, img_size=None):   # configs[2..4]; img_size = h_size//s
 
 def cfg_edsr_x4():       # configs[1]
     return O.EDSRCfg(in_chans=1, n_resblocks=16, n_feats=64, scale=4, rgb_range=1.0)
+
+
+def cfg_imgsize8():
+    """img_size == window_size: the reference constructor disables the cyclic shift of every block
+    (network_swinir.py:232-236) -- no attn_mask buffers, all windows unshifted."""
+    return O.SwinIRCfg(upscale=2, in_chans=1, img_size=8, window_size=8, img_range=1.0, depths=[2, 2],
+                       embed_dim=60, num_heads=[6, 6], mlp_ratio=2, upsampler="pixelshuffledirect",
+                       resi_connection="1conv")
+
+
+def cfg_stress():
+    return O.SwinIRCfg(upscale=4, in_chans=1, img_size=16, window_size=8, img_range=1.0, depths=[2, 2],
+                       embed_dim=180, num_heads=[6, 6], mlp_ratio=2, upsampler="pixelshuffle",
+                       resi_connection="1conv")
+
+
+STRESS_GAIN = 2048.0
+
+
+def stress_state_dict(sd, gain=STRESS_GAIN):
+    """Large-magnitude residual stream: conv_first scaled by `gain`, so every fp16 conv operand (the
+    un-normalised residual stream, conv_after_body's sum with the shallow features, the upsampler features)
+    is ~gain times larger than with random-init-like weights -- the range a trained checkpoint could reach,
+    still below the fp16 maximum the conv operands saturate at."""
+    sd = dict(sd)
+    sd["conv_first.weight"] = sd["conv_first.weight"] * gain
+    sd["conv_first.bias"] = sd["conv_first.bias"] * gain
+    return sd
+
+
+def synthetic_hr(B, H, W, seed):
+    """uint8-representable HR targets in [0,1] (what the loader delivers)."""
+    g = torch.Generator().manual_seed(seed)
+    base = torch.rand(B, 1, H // 8 + 2, W // 8 + 2, generator=g)
+    Hr = torch.nn.functional.interpolate(base, size=(H, W), mode="bilinear", align_corners=False)
+    return (Hr * 255).round() / 255

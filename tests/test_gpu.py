@@ -347,40 +347,6 @@ def test_gemm_conv5x5_image_epilogue(L, engine):
     assert float((img.cpu() - exp).abs().max()) < 3e-3 * max(1.0, float(exp.abs().max()))
 
 
-def test_conv_halo_mode_equals_per_tap_mode(L):
-    """SRK_CONV_HALO=1: one halo TMA box per channel block, taps read as shifted windows of the swizzled tile
-    (absolute-address swizzle, csrc/dbg_umma.cu) -- same results as the per-tap boxes, 3x3 and 5x5."""
-    if "tcgen05" not in ENGINES:
-        pytest.skip("tcgen05 engine not under test")
-    L.set_engine("tcgen05")
-    from sr_caco_2_b200 import packing as P
-    g = torch.Generator().manual_seed(31)
-    B, H, W = 2, 21, 13
-    prev = os.environ.get("SRK_CONV_HALO")
-    try:
-        for (Cin, Cout, kk) in [(192, 192, 3), (64, 64, 3), (64, 64, 5)]:
-            x = torch.randn(B, Cin, H, W, generator=g).half()
-            wt = (torch.randn(Cout, Cin, kk, kk, generator=g) * 0.04).half()
-            bias = torch.randn(Cout, generator=g)
-            wk = wt.float().permute(0, 2, 3, 1).reshape(Cout, kk * kk * Cin).half().contiguous().to(DEV)
-            a = x.permute(0, 2, 3, 1).contiguous().to(DEV)
-            outs = []
-            for mode in ("0", "1"):
-                os.environ["SRK_CONV_HALO"] = mode
-                o32 = torch.zeros(B * H * W, Cout, device=DEV)
-                _gemm(L, A=a, a_mode=L.A_CONV3X3, conv_k=kk, lda=Cin, nB=B, H=H, W=W, Wt=wk, M=B * H * W, N=Cout,
-                      K=kk * kk * Cin, dtype=L.SRK_FP16, bias=bias.to(DEV), out32=o32, ld32=Cout)
-                outs.append(o32)
-            exp = F.conv2d(x.float(), wt.float(), bias, padding=kk // 2).permute(0, 2, 3, 1).reshape(B * H * W, Cout)
-            assert float((outs[1].cpu() - exp).abs().max()) < 3e-3 * max(1.0, float(exp.abs().max()))
-            assert float((outs[1] - outs[0]).abs().max()) < 1e-4 * max(1.0, float(exp.abs().max()))
-    finally:
-        if prev is None:
-            os.environ.pop("SRK_CONV_HALO", None)
-        else:
-            os.environ["SRK_CONV_HALO"] = prev
-
-
 @pytest.mark.parametrize("scale", [2, 4, 8])
 def test_folded_tail_equals_conv_chain(L, scale):
     """packing.fold_tail + 5x5 conv GEMM + srk_tail_border vs the upsampler as the reference runs it:
@@ -415,7 +381,7 @@ def test_folded_tail_equals_conv_chain(L, scale):
 
 
 def test_folded_tail_network_equals_unfolded(L):
-    """SRK_FOLD_TAIL=0 (upsampler convs one by one, fp16 intermediates) vs the folded tail, whole network."""
+    """options = SRK_OPT_NO_FOLD_TAIL (upsampler convs one by one, fp16 intermediates) vs the folded tail, whole network."""
     if "tcgen05" not in ENGINES:
         pytest.skip("tcgen05 engine not under test")
     L.set_engine("tcgen05")
@@ -423,17 +389,10 @@ def test_folded_tail_network_equals_unfolded(L):
                       upsampler="pixelshuffle")
     net = make_swinir(cfg, T.swinir_state_dict(cfg, 5))
     x = T.synthetic_lr(2, 21, 27, 3).to(DEV)
-    prev = os.environ.get("SRK_FOLD_TAIL")
-    try:
-        os.environ["SRK_FOLD_TAIL"] = "1"
-        y1 = net(x).clone()
-        os.environ["SRK_FOLD_TAIL"] = "0"
-        y0 = net(x).clone()
-    finally:
-        if prev is None:
-            os.environ.pop("SRK_FOLD_TAIL", None)
-        else:
-            os.environ["SRK_FOLD_TAIL"] = prev
+    y1 = net(x).clone()
+    net.options = L.OPT_NO_FOLD_TAIL
+    y0 = net(x).clone()
+    net.options = 0
     assert y1.shape == y0.shape == (2, 1, 84, 108)
     assert float((y1 - y0).abs().max()) < 1.5e-3
 
