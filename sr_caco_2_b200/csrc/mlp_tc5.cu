@@ -10,9 +10,9 @@
 //                     fc2(c):  D2[t&1] (TMEM, CP cols)  += H[c%3] . W2[:, 64c..]^T
 //                issued as fc1(0) fc1(1) | fc1(2) fc2(0) | fc1(3) fc2(1) | ... so the tensor pipe
 //                always has the fc1 of a later chunk queued while a chunk is in the GELU warps.
-//   warps 4..11  GELU warps (2 per TMEM lane group, 32 chunk columns each): tcgen05.ld D1 ->
-//                + b1 -> exact-erf GELU (packed fp32x2, one MUFU per element) -> bf16 -> written
-//                into shared memory in the 128B-swizzled K-major operand layout fc2 reads.
+//   warps 4..11  GELU warps, two sets of 4 (one warp per TMEM lane group) on alternate chunks:
+//                tcgen05.ld D1 -> + b1 -> exact-erf GELU (packed fp32x2, one MUFU per element) -> bf16 ->
+//                written into shared memory in the 128B-swizzled K-major operand layout fc2 reads.
 //   warps 12..19 final warps: D2 -> padded fp32 staging (64 rows at a time) -> + b2 + residual
 //                (fp32 stream, register-prefetched half a tile ahead) -> x' store + LayerNorm /
 //                cast store, all as coalesced row segments.  D2 is double buffered, so the final
@@ -92,10 +92,10 @@ mlp_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         mbar_init(a_full, 1); mbar_init(a_empty, 1);
         for (int s = 0; s < ML_NW; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(d1_full(b), 1); mbar_init(d1_empty(b), ML_G_WARPS);
+            mbar_init(d1_full(b), 1); mbar_init(d1_empty(b), ML_G_WARPS / 2);
             mbar_init(d2_full(b), 1); mbar_init(d2_empty(b), ML_F_WARPS);
         }
-        for (int s = 0; s < ML_NH; ++s) { mbar_init(h_full(s), ML_G_WARPS); mbar_init(h_empty(s), 1); }
+        for (int s = 0; s < ML_NH; ++s) { mbar_init(h_full(s), ML_G_WARPS / 2); mbar_init(h_empty(s), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w1) : "memory");
@@ -209,43 +209,61 @@ mlp_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     } else if (warp < 4 + ML_G_WARPS) {
         // ===================================== GELU warps =====================================
         if constexpr (ML_THREADS == 640) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
-        const int lg = warp & 3, q = (warp - 4) >> 2;                // TMEM lane group, 32-column half of the chunk
+        // Two sets of 4 warps (one per TMEM lane group) take alternate chunks of the CTA's chunk sequence
+        // q = tile_iteration * NC + c: set s owns the chunks with q % 2 == s, i.e. always D1 stage s, so one set
+        // drains / converts a chunk while the MMAs of the other set's chunk run.  A warp converts the 64 columns of
+        // its 32 rows in four 16-column pieces; the tcgen05.ld of a piece is in flight while the previous one is
+        // converted (the TMEM read port is shared by every warp of the SM: an exposed load costs hundreds of cycles).
+        const int lg = warp & 3, set = (warp - 4) >> 2;
         const int r = lg * 32 + lane;                                // tile row of this thread
-        int d1s = 0, d1ph = 0, hs = 0, hph = 0;
-        for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
-            for (int c = 0; c < NC; ++c) {
-                mbar_wait(d1_full(d1s), d1ph);
-                tc_fence_after();
-                uint32_t v[32];
-                tc_ld32(tD1 + ((uint32_t)(lg * 32) << 16) + (uint32_t)(d1s * ML_CH + q * 32), v);
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(d1_empty(d1s));           // D1 stage may be overwritten
-                mbar_wait(h_empty(hs), hph ^ 1);                     // fc2 of the previous user of this H stage retired
-                const float4* bp = reinterpret_cast<const float4*>(sb1 + c * ML_CH + q * 32);
-                // K-major, 128B-swizzled operand layout: row r, 16 B chunk j -> r*128 + ((j ^ (r & 7)) << 4)
-                unsigned char* hrow = ml_smem_raw + (sH - raw) + hs * 16384 + r * 128;
+        const int n_my_tiles = (int)blockIdx.x < p.m_tiles ? (p.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+        const int n_chunks = n_my_tiles * NC;
+        const uint32_t t_row = tD1 + ((uint32_t)(lg * 32) << 16) + (uint32_t)(set * ML_CH);
+        auto convert = [&](const uint32_t (&v)[16], const float* bias16, unsigned char* hrow, int piece) {
+            const float4* bp = reinterpret_cast<const float4*>(bias16);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float4 b0 = bp[2 * j], b1v = bp[2 * j + 1];
-                    uint32_t a0, a1, pk[4];
-                    unpack64(gelu2(pack64(v[8 * j], v[8 * j + 1]), pack64(__float_as_uint(b0.x), __float_as_uint(b0.y))), a0, a1);
-                    pk[0] = packf<SRK_BF16>(__uint_as_float(a0), __uint_as_float(a1));
-                    unpack64(gelu2(pack64(v[8 * j + 2], v[8 * j + 3]), pack64(__float_as_uint(b0.z), __float_as_uint(b0.w))), a0, a1);
-                    pk[1] = packf<SRK_BF16>(__uint_as_float(a0), __uint_as_float(a1));
-                    unpack64(gelu2(pack64(v[8 * j + 4], v[8 * j + 5]), pack64(__float_as_uint(b1v.x), __float_as_uint(b1v.y))), a0, a1);
-                    pk[2] = packf<SRK_BF16>(__uint_as_float(a0), __uint_as_float(a1));
-                    unpack64(gelu2(pack64(v[8 * j + 6], v[8 * j + 7]), pack64(__float_as_uint(b1v.z), __float_as_uint(b1v.w))), a0, a1);
-                    pk[3] = packf<SRK_BF16>(__uint_as_float(a0), __uint_as_float(a1));
-                    const int chunk = q * 4 + j;
-                    *reinterpret_cast<uint4*>(hrow + ((chunk ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
-                __syncwarp();
-                if (lane == 0) mbar_arrive(h_full(hs));
-                if (++d1s == 2) { d1s = 0; d1ph ^= 1; }
-                if (++hs == ML_NH) { hs = 0; hph ^= 1; }
+            for (int j = 0; j < 2; ++j) {
+                const float4 b0 = bp[2 * j], b1v = bp[2 * j + 1];
+                uint32_t a0, a1, pk[4];
+                unpack64(gelu2(pack64(v[8 * j], v[8 * j + 1]), pack64(__float_as_uint(b0.x), __float_as_uint(b0.y))), a0, a1);
+                pk[0] = packf<SRK_BF16>(__uint_as_float(a0), __uint_as_float(a1));
+                unpack64(gelu2(pack64(v[8 * j + 2], v[8 * j + 3]), pack64(__float_as_uint(b0.z), __float_as_uint(b0.w))), a0, a1);
+                pk[1] = packf<SRK_BF16>(__uint_as_float(a0), __uint_as_float(a1));
+                unpack64(gelu2(pack64(v[8 * j + 4], v[8 * j + 5]), pack64(__float_as_uint(b1v.x), __float_as_uint(b1v.y))), a0, a1);
+                pk[2] = packf<SRK_BF16>(__uint_as_float(a0), __uint_as_float(a1));
+                unpack64(gelu2(pack64(v[8 * j + 6], v[8 * j + 7]), pack64(__float_as_uint(b1v.z), __float_as_uint(b1v.w))), a0, a1);
+                pk[3] = packf<SRK_BF16>(__uint_as_float(a0), __uint_as_float(a1));
+                // K-major, 128B-swizzled operand layout: row r, 16 B chunk j -> r*128 + ((j ^ (r & 7)) << 4)
+                const int chunk = piece * 2 + j;
+                *reinterpret_cast<uint4*>(hrow + ((chunk ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
+        };
+        for (int q = set, k = 0; q < n_chunks; q += 2, ++k) {
+            const int c = q % NC, hs = q % ML_NH, hu = q / ML_NH;
+            mbar_wait(d1_full(set), k & 1);
+            tc_fence_after();
+            uint32_t va[16], vb[16];
+            tc_ld16_nowait(t_row, va);
+            tc_wait_ld16(va);
+            tc_ld16_nowait(t_row + 16, vb);
+            mbar_wait(h_empty(hs), (hu & 1) ^ 1);                    // fc2 of the previous user of this H stage retired
+            const float* bias = sb1 + c * ML_CH;
+            unsigned char* hrow = ml_smem_raw + (sH - raw) + hs * 16384 + r * 128;
+            convert(va, bias, hrow, 0);
+            tc_wait_ld16(vb);
+            tc_ld16_nowait(t_row + 32, va);
+            convert(vb, bias + 16, hrow, 1);
+            tc_wait_ld16(va);
+            tc_ld16_nowait(t_row + 48, vb);
+            convert(va, bias + 32, hrow, 2);
+            tc_wait_ld16(vb);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(d1_empty(set));               // D1 stage may be overwritten
+            convert(vb, bias + 48, hrow, 3);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
+            __syncwarp();
+            if (lane == 0) mbar_arrive(h_full(hs));
         }
     } else {
         // ===================================== final warps =====================================
