@@ -179,6 +179,25 @@ typedef struct {
 } srk_mlp_args;
 int srk_mlp(const srk_mlp_args* a, void* stream);
 
+/* The attention half of a Swin block in one kernel (tcgen05 engine, padded embedding 192 = 6 heads x 32):
+ *   x' = x + proj(window_attention(qkv(A))) + b_proj ;  out32[token] = x' ;  out16[token] = LayerNorm(x'; ln_g, ln_b)
+ * A: (M, lda) bf16 = LN1(x) rows in window-major order under cyclic shift `shift`, with 1.0 in the pad columns
+ *    C, C + 1 (the qkv bias is folded into those K columns of Wqkv);
+ * Wqkv: (6 * 96, Cp) bf16, head-major rows [head][q | k | v][32] (packing.pack_qkv_heads);
+ * Wproj: (Cp, 192) bf16 (packing.pack_proj); rel_table: (6, 225) fp32; scale = head_dim^-0.5;
+ * res / out32: fp32 residual stream in token order (may alias: every row is read before it is written, by the
+ * same warp); out16: LN2 rows in token order.  q, k, v, the attention output and the proj accumulator never reach HBM.
+ * Replaces network_swinir.py:287-334 (norm1 output -> attention -> proj -> residual -> norm2) incl. :148-176, :260-285. */
+typedef struct {
+    const void* A; int lda; int M, C, Cp, H, W, shift, num_heads;
+    const void* Wqkv; const void* Wproj; const float* b_proj;
+    const float* rel_table; float scale;
+    const float* res; float* out32; int ld32;
+    void* out16; int ld16; int out16_dtype;
+    const float* ln_g; const float* ln_b; int ln_C;
+} srk_attn_block_args;
+int srk_attn_block(const srk_attn_block_args* a, void* stream);
+
 /* LayerNorm over the first C of ld32 columns of fp32 rows -> 16-bit rows (pad columns zeroed).
  * mode 0: out row m <- LN(x row m); mode 1 (win_shift>=0): out row m (window-major) <-
  * LN(x row token(m)); g == NULL: plain cast without normalisation.  Optionally also writes
@@ -268,6 +287,8 @@ typedef struct {
     /* optional: w_qkv with the bias folded into K columns embed_dim (bf16 hi part) and embed_dim + 1 (bf16 of the
      * remainder); used with a NULL bias when the producer of the A rows wrote 1.0 there (ln_pad_one). NULL: not built */
     const void* w_qkv_fb;
+    /* optional: the same folded weight with head-major rows [head][q | k | v][32] for srk_attn_block. NULL: not built */
+    const void* w_qkv_hm;
 } srk_stb_params;
 
 typedef struct {

@@ -75,6 +75,29 @@ def run_mlp():
 if eng == "tcgen05":
     us = run_mlp()
     report("fused MLP 192-384-192 +LN", us, 2*M*192*384*2, M*(384+768+768+384))
+def run_attn_block():
+    a = L.AttnBlockArgs()
+    whm = t16(576, Cp); tab = torch.randn(6, 225, device=dev) * 0.3
+    a.A, a.lda, a.M, a.C, a.Cp, a.H, a.W, a.shift, a.num_heads = L.ptr(A), Cp, M, 180, Cp, H, W, 4, 6
+    a.Wqkv, a.Wproj, a.b_proj, a.rel_table, a.scale = L.ptr(whm), L.ptr(Wp), L.ptr(bias), L.ptr(tab), 30 ** -0.5
+    a.res, a.out32, a.ld32, a.out16, a.ld16, a.out16_dtype = L.ptr(X), L.ptr(X2), Cp, L.ptr(A16), Cp, 0
+    a.ln_g, a.ln_b, a.ln_C = L.ptr(lng192), L.ptr(lnb192), 180
+    keep.extend([whm, tab])
+    lib = L.load()
+    if os.environ.get("SRK_PROFILE_ONCE"):
+        L.check(lib.srk_attn_block(C.byref(a), L.stream_ptr())); torch.cuda.synchronize(); return 1.0
+    for _ in range(3): L.check(lib.srk_attn_block(C.byref(a), L.stream_ptr()))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10): L.check(lib.srk_attn_block(C.byref(a), L.stream_ptr()))
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / 10 * 1e3
+keep = []
+lng192 = torch.ones(192, device=dev); lnb192 = torch.zeros(192, device=dev)
+if eng == "tcgen05":
+    us = run_attn_block()
+    report("attn block (qkv+attn+proj+LN)", us, 2*M*(192*576 + 2*64*192 + 192*192), M*(384+768+768+384))
 Ah = t16(M, Cp, dt=torch.float16); Wc = t16(192, 9*192, dt=torch.float16)
 us = run("convCC", A=Ah, a_mode=1, lda=Cp, nB=B, H=H, W=W, Wt=Wc, M=M, N=192, K=9*192, dtype=1, bias=bias, res=X, out32=X2, ld32=Cp)
 report("conv 192->192 +res", us, 2*M*192*1728, M*(384+768+768))

@@ -41,6 +41,14 @@ class MlpArgs(C.Structure):
                 ("ln_win_shift", C.c_int), ("H", C.c_int), ("W", C.c_int), ("ln_pad_one", C.c_int)]
 
 
+class AttnBlockArgs(C.Structure):
+    _fields_ = [("A", vp), ("lda", C.c_int), ("M", C.c_int), ("C", C.c_int), ("Cp", C.c_int), ("H", C.c_int),
+                ("W", C.c_int), ("shift", C.c_int), ("num_heads", C.c_int), ("Wqkv", vp), ("Wproj", vp),
+                ("b_proj", fp), ("rel_table", fp), ("scale", C.c_float), ("res", fp), ("out32", fp),
+                ("ld32", C.c_int), ("out16", vp), ("ld16", C.c_int), ("out16_dtype", C.c_int),
+                ("ln_g", fp), ("ln_b", fp), ("ln_C", C.c_int)]
+
+
 class ConvParams(C.Structure):
     _fields_ = [("w", vp), ("b", fp), ("cin_p", C.c_int), ("n_p", C.c_int)]
 
@@ -53,7 +61,7 @@ class StbParams(C.Structure):
     _fields_ = [("ln1_g", fp), ("ln1_b", fp), ("ln2_g", fp), ("ln2_b", fp),
                 ("w_qkv", vp), ("w_proj", vp), ("w_fc1", vp), ("w_fc2", vp),
                 ("b_qkv", fp), ("b_proj", fp), ("b_fc1", fp), ("b_fc2", fp),
-                ("rel_table", fp), ("shift", C.c_int), ("num_heads", C.c_int), ("w_qkv_fb", vp)]
+                ("rel_table", fp), ("shift", C.c_int), ("num_heads", C.c_int), ("w_qkv_fb", vp), ("w_qkv_hm", vp)]
 
 
 class SwinIRPlan(C.Structure):
@@ -100,6 +108,7 @@ PROTOTYPES = {
     "srk_bicubic_upsample": (C.c_int, [fp, C.c_int, C.c_int, C.c_int, C.c_int, fp, vp]),
     "srk_gemm": (C.c_int, [C.POINTER(GemmArgs), vp]),
     "srk_mlp": (C.c_int, [C.POINTER(MlpArgs), vp]),
+    "srk_attn_block": (C.c_int, [C.POINTER(AttnBlockArgs), vp]),
     "srk_layernorm": (C.c_int, [fp, C.c_int, C.c_int, C.c_int, fp, fp, C.c_float, vp, C.c_int,
                                 C.c_int, fp, C.c_int, C.c_int, C.c_int, vp]),
     "srk_window_attention": (C.c_int, [vp, C.c_int, vp, C.c_int, fp, C.c_int, C.c_int, C.c_int,

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libsrk.so")
 STAMP = os.path.join(HERE, "build", "stamp.txt")
 SOURCES = ["api.cu", "metrics.cu", "elementwise.cu", "attention.cu", "gemm_mma.cu",
-           "gemm_tc5.cu", "mlp_tc5.cu", "attn_tc5.cu", "net.cu"]
+           "gemm_tc5.cu", "mlp_tc5.cu", "attn_block_tc5.cu", "net.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--use_fast_math=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default",
               "-Xptxas", "-v", "--expt-relaxed-constexpr"]

@@ -39,10 +39,12 @@ __device__ __forceinline__ uint32_t packbf(float a, float b) {
 //   tb            : this head's 225-entry relative-position-bias table (shared memory)
 //   lab, masked   : region labels of the window's 64 positions (shift mask), and whether any differ
 // S / P / O live in registers (mma.sync m16n8k16, bf16 in, fp32 accumulate); O (normalised) is
-// written over the strip's own q slot.
-template <int DP>
+// written over the strip's own q slot, or (AO_OUT) straight into a 128-row K-major 128B-swizzled UMMA
+// operand tile `ao` (k-blocks of 16 KB: row r, column head * DP + d), rows ao_row0 + window position.
+template <int DP, bool AO_OUT = false, typename LT = int>
 __device__ __forceinline__ void attn_unit(uint32_t rows_s, unsigned char* rows, int RS, int strip, int qc, int kc,
-                                          int vc, const float* tb, const int* lab, bool masked, float scale, int lane) {
+                                          int vc, const float* tb, const LT* lab, bool masked, float scale, int lane,
+                                          unsigned char* ao = nullptr, int ao_row0 = 0, int head = 0) {
     const int g = lane >> 2, t = lane & 3;
     const int r0 = strip * 16;
     const float LOG2E = 1.4426950408889634f;
@@ -135,6 +137,20 @@ __device__ __forceinline__ void attn_unit(uint32_t rows_s, unsigned char* rows, 
             mma_bf16(o[2 * nd], a, b[0], b[1]);
             mma_bf16(o[2 * nd + 1], a, b[2], b[3]);
         }
+    }
+    if constexpr (AO_OUT) {
+        static_assert(DP == 32, "the operand-tile output is built for a padded head dim of 32");
+        // column head * 32 + nt * 8 + 2 t  ->  k-block head / 2, 16 B chunk (head & 1) * 4 + nt, byte 4 t inside it
+        const int ra = ao_row0 + r0 + g, rb = ra + 8;
+        unsigned char* pa = ao + (head >> 1) * 16384 + ra * 128 + 4 * t;
+        unsigned char* pb = ao + (head >> 1) * 16384 + rb * 128 + 4 * t;
+#pragma unroll
+        for (int nt = 0; nt < DP / 8; ++nt) {
+            const int ch = (head & 1) * 4 + nt;
+            *reinterpret_cast<uint32_t*>(pa + ((ch ^ (ra & 7)) << 4)) = packbf(o[nt][0] * inv0, o[nt][1] * inv0);
+            *reinterpret_cast<uint32_t*>(pb + ((ch ^ (rb & 7)) << 4)) = packbf(o[nt][2] * inv1, o[nt][3] * inv1);
+        }
+        return;
     }
     // ---- O overwrites this strip's own q slot (only this warp reads it, and it is done) ----
     __syncwarp();

@@ -1,0 +1,451 @@
+// The attention half of a Swin block as ONE persistent tcgen05 kernel:
+//
+//     x' = x + proj(window_attention(qkv(LN1(x)))) + b_proj ;   a2 = LN2(x')
+//
+// per 128-token tile (two 8x8 windows, window-major rows under the block's cyclic shift).  q, k, v, the
+// attention output and the proj accumulator never leave the SM: the kernel reads the LN1 rows (bf16, TMA)
+// and the fp32 residual rows and writes x' (fp32) and LN2(x') (bf16) -- 2304 B per token instead of the
+// 3072 B (+ 2 launches) of the qkv+attention kernel followed by the proj GEMM.
+// Restates SwinTransformerBlock.forward (dlib/models/network_swinir.py:287-337, first half),
+// WindowAttention.forward (:148-176) and calculate_mask (:260-285).
+//
+//   warp 0       TMA producer: the A tile (LN1 rows) once per tile; the weights stream through a ring of
+//                six 12 KB slots in exactly the order the MMA warp consumes them: per head the 96 rows
+//                [q | k | v] x 32 of the head-major packed qkv weight (3 k-blocks), and the proj weight
+//                (3 k-blocks x 2 slots).  The qkv bias rides in the two pad K columns (fold_qkv_bias).
+//   warp 1       MMA issuer.  Head job h:  Q[j % 3] (TMEM, 96 cols) = A . Wqkv[h]^T   (M128 N96  K192)
+//                proj job:               PD (TMEM, 192 cols)      = AO . Wproj^T     (M128 N192 K192)
+//                issued as  h0 h1 proj(t-1) h2 h3 h4 h5  per tile, so that the first heads of a tile are
+//                in flight before the previous tile's proj (which has to wait for its last head).
+//   warps 4..19  two groups of 8.  Group g runs the head units h = g, g+2, g+4 of every tile:
+//                  drain Q (thread = row) into a bf16 staging tile [q | k | v] of 128 rows,
+//                  8 x (window, 16-query strip) attention units (attention.cuh: mma.sync S and PV, softmax
+//                  in registers, rel-pos bias + shift mask arithmetic), O written straight into the
+//                  128B-swizzled K-major operand tile AO that the proj MMAs read.
+//                After the first unit of tile t both groups together finish tile t-1: PD -> fp32 staging
+//                (aliases the two bf16 staging tiles) -> + b_proj + residual (gathered through the
+//                window_reverse + roll map) -> x' store, LayerNorm, bf16 store -- two rows per warp at a
+//                time, 16 B per lane, like the final stage of mlp_tc5.cu.
+#include "tc5_ptx.cuh"
+#include "attention.cuh"
+
+namespace srk {
+
+constexpr int AB_CP = 192;                  // padded embedding = heads * 32 (the only instantiation: 6 heads)
+constexpr int AB_KB = AB_CP / 64;
+constexpr int AB_NH = 6;
+constexpr int AB_THREADS = 128 + 32 * 16;
+constexpr int AB_WSLOT = 96 * 128;          // 96 weight rows x 64 k, bf16
+constexpr int AB_NW = 6;
+constexpr int AB_SROW16 = 96 * 2 + 16;      // staged [q | k | v] row stride (bytes): an odd multiple of 16 B
+constexpr int AB_STG = 128 * AB_SROW16;     // one group's staging tile
+constexpr int AB_SROW32 = AB_CP + 4;        // fp32 staging row stride (floats) of the final stage
+constexpr int AB_A_OFF = 0;
+constexpr int AB_W_OFF = AB_A_OFF + AB_KB * 16384;
+constexpr int AB_AO_OFF = AB_W_OFF + AB_NW * AB_WSLOT;
+constexpr int AB_STG_OFF = AB_AO_OFF + AB_KB * 16384;
+constexpr int AB_BAR_OFF = AB_STG_OFF + 2 * AB_STG;
+constexpr int AB_AUX = 256 + AB_NH * 225 * 4 + 256;          // barriers, rel-pos tables, shift-mask labels
+constexpr size_t AB_SMEM = (size_t)AB_BAR_OFF + AB_AUX + 1024;
+static_assert(64 * AB_SROW32 * 4 <= 2 * AB_STG, "the fp32 staging of the final stage aliases the two bf16 staging tiles");
+static_assert(AB_SMEM <= 232448, "shared memory plan exceeds the 227 KB per-CTA limit");
+
+struct AbP {
+    int M, m_tiles, C, H, W, T, shift;
+    float scale;
+    const float* table;                       // (heads, 225)
+    const float* b_proj;
+    const float* res; float* out32; int ld32;
+    uint16_t* out16; int ld16; int out16_dtype;
+    const float* ln_g; const float* ln_b; int ln_C;
+};
+
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attn_block_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_wq,
+                      const __grid_constant__ CUtensorMap map_wp, const AbP p) {
+    extern __shared__ unsigned char ab_raw[];
+    const uint32_t raw = smem_u32(ab_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    unsigned char* sm = ab_raw + (base - raw);
+    const uint32_t sA = base + AB_A_OFF, sW = base + AB_W_OFF, sAO = base + AB_AO_OFF, sStg = base + AB_STG_OFF,
+                   bars = base + AB_BAR_OFF;
+    const uint32_t a_full = bars, a_empty = bars + 8;
+    auto w_full = [&](int s) { return bars + 16 + 8u * s; };
+    auto w_empty = [&](int s) { return bars + 64 + 8u * s; };
+    auto q_full = [&](int s) { return bars + 112 + 8u * s; };
+    auto q_empty = [&](int s) { return bars + 136 + 8u * s; };
+    const uint32_t ao_full = bars + 160, ao_empty = bars + 168, pd_full = bars + 176, pd_empty = bars + 184,
+                   tmem_slot = bars + 192;
+    float* stab = reinterpret_cast<float*>(sm + AB_BAR_OFF + 256);                    // [heads][225]
+    unsigned char* slab = sm + AB_BAR_OFF + 256 + AB_NH * 225 * 4;                   // [group][window][64] region labels
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_my = (int)blockIdx.x < p.m_tiles ? (p.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+    if (threadIdx.x == 0) {
+        mbar_init(a_full, 1); mbar_init(a_empty, 1);
+        for (int s = 0; s < AB_NW; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
+        for (int s = 0; s < 3; ++s) { mbar_init(q_full(s), 1); mbar_init(q_empty(s), 8); }
+        mbar_init(ao_full, 8 * AB_NH); mbar_init(ao_empty, 1);
+        mbar_init(pd_full, 1); mbar_init(pd_empty, 16);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wq) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wp) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < AB_NH * 225; i += AB_THREADS) stab[i] = p.table[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sm + AB_BAR_OFF + 192);
+    const uint32_t tQ = tmem_base, tPD = tmem_base + 288;          // Q: 3 stages x 96 columns, PD: 192 columns
+
+    if (warp < 4) {
+    // 20 warps start with 96 registers; the 16 unit warps take what the TMA / MMA / idle warps release:
+    // 128 x (96 - 56) = 5120 >= 512 x (104 - 96)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 0) {
+        // ======================================= TMA producer =======================================
+        if (lane == 0) {
+            int ws = 0, wph = 0;
+            auto slot = [&]() {
+                mbar_wait(w_empty(ws), wph ^ 1);
+                mbar_expect_tx(w_full(ws), AB_WSLOT);
+                return sW + ws * AB_WSLOT;
+            };
+            auto w_next = [&]() { if (++ws == AB_NW) { ws = 0; wph ^= 1; } };
+            auto load_head = [&](int h) {
+                for (int kb = 0; kb < AB_KB; ++kb) { const uint32_t d = slot(); tma_load_2d(d, &map_wq, w_full(ws), kb * 64, h * 96); w_next(); }
+            };
+            auto load_proj = [&]() {
+                for (int kb = 0; kb < AB_KB; ++kb)
+                    for (int half = 0; half < 2; ++half) { const uint32_t d = slot(); tma_load_2d(d, &map_wp, w_full(ws), kb * 64, half * 96); w_next(); }
+            };
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
+                mbar_wait(a_empty, (it & 1) ^ 1);
+                mbar_expect_tx(a_full, AB_KB * 16384);
+                for (int kb = 0; kb < AB_KB; ++kb) tma_load_2d(sA + kb * 16384, &map_a, a_full, kb * 64, tile * 128);
+                load_head(0); load_head(1);
+                if (it > 0) load_proj();
+                for (int h = 2; h < AB_NH; ++h) load_head(h);
+            }
+            if (n_my > 0) load_proj();
+        }
+    } else if (warp == 1) {
+        // ======================================= MMA issuer =======================================
+        if (lane == 0) {
+            const uint32_t id_q = umma_idesc(1, 128, 96), id_p = umma_idesc(1, 128, AB_CP);
+            int ws = 0, wph = 0, j = 0;
+            auto w_next = [&]() { if (++ws == AB_NW) { ws = 0; wph ^= 1; } };
+            auto head_job = [&]() {
+                const int s = j % 3;
+                mbar_wait(q_empty(s), ((j / 3) & 1) ^ 1);
+                tc_fence_after();
+                for (int kb = 0; kb < AB_KB; ++kb) {
+                    mbar_wait(w_full(ws), wph);
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_sw128(sA + kb * 16384), db = umma_desc_sw128(sW + ws * AB_WSLOT);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        tc_mma_f16(tQ + (uint32_t)(s * 96), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), id_q, (kb | k) != 0 ? 1u : 0u);
+                    tc_commit(w_empty(ws));
+                    w_next();
+                }
+                tc_commit(q_full(s));
+                ++j;
+            };
+            auto proj_job = [&](int tp) {
+                mbar_wait(ao_full, tp & 1);                         // every head unit of the tile wrote its O
+                mbar_wait(pd_empty, (tp & 1) ^ 1);                  // the previous tile's accumulator was drained
+                tc_fence_after();
+                for (int kb = 0; kb < AB_KB; ++kb) {
+                    mbar_wait(w_full(ws), wph);
+                    const int ws1 = ws + 1;                         // ws is even here: the two halves are adjacent slots
+                    mbar_wait(w_full(ws1), wph);
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_sw128(sAO + kb * 16384), db = umma_desc_sw128(sW + ws * AB_WSLOT);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        tc_mma_f16(tPD, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), id_p, (kb | k) != 0 ? 1u : 0u);
+                    tc_commit(w_empty(ws)); w_next();
+                    tc_commit(w_empty(ws)); w_next();
+                }
+                tc_commit(pd_full);
+                tc_commit(ao_empty);
+            };
+            for (int it = 0; it < n_my; ++it) {
+                mbar_wait(a_full, it & 1);
+                tc_fence_after();
+#pragma unroll 1
+                for (int h = 0; h <= AB_NH; ++h) {
+                    if (h == 2 || h == AB_NH) {                      // proj of the previous tile after the first two heads;
+                        const int tp = h == 2 ? it - 1 : (it == n_my - 1 ? it : -1);   // the last tile's own proj at the end
+                        if (tp >= 0) proj_job(tp);
+                        if (h == AB_NH) break;
+                    }
+                    head_job();
+                    if (h == AB_NH - 1) tc_commit(a_empty);         // the A tile may be refilled once the last head retires
+                }
+            }
+        }
+    }
+    } else {
+        // ======================================= unit warps =======================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        const int uw = warp - 4, grp = uw >> 3, gw = uw & 7;          // group, warp inside the group
+        const int lg = warp & 3;                                      // TMEM lane group
+        const int hq = gw >> 2;                                       // drain: which 48 of the 96 accumulator columns
+        const int window = gw >> 2, strip = gw & 3;                   // attention: (window, 16-query strip) of this warp
+        unsigned char* stg = sm + AB_STG_OFF + grp * AB_STG;          // this group's bf16 staging tile
+        const uint32_t stg_s = sStg + grp * AB_STG;
+        unsigned char* lab = slab + grp * 128;
+        const int nWy = p.H >> 3, wpr = p.W >> 3, nW = nWy * wpr;
+        const int bar_g = 1 + grp;
+        unsigned char* ao = sm + AB_AO_OFF;
+
+        // ---- head unit: head h of tile iteration it (job index 6 it + h) ----
+        auto unit = [&](int it, int tile, int h) {
+            const int j = it * AB_NH + h, s = j % 3;
+            // shift-mask region labels of the tile's two windows (threads 0..127 of the group)
+            const int tg = gw * 32 + lane;
+            const int wg = tile * 2 + (tg >> 6);
+            const int win = wg % nW, wi = win / wpr, wj = win - wi * wpr;
+            const bool m_any = p.shift > 0 && (wi == nWy - 1 || wj == wpr - 1);
+            if (tg < 128) lab[tg] = (unsigned char)(m_any ? win_pos_label(win, tg & 63, p.H, p.W, p.shift) : 0);
+            mbar_wait(q_full(s), (j / 3) & 1);
+            tc_fence_after();
+            {   // drain: thread = row, 48 columns -> 96 B of the staged row [q 32 | k 32 | v 32]
+                const uint32_t t_row = tQ + ((uint32_t)(lg * 32) << 16) + (uint32_t)(s * 96 + hq * 48);
+                unsigned char* srow = stg + (size_t)(lg * 32 + lane) * AB_SROW16 + hq * 96;
+                uint32_t va[16], vb[16];
+                tc_ld16_nowait(t_row, va);
+                tc_wait_ld16(va);
+                tc_ld16_nowait(t_row + 16, vb);
+                auto put = [&](const uint32_t (&v)[16], int c) {
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) pk[e] = packf<SRK_BF16>(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+                    *reinterpret_cast<uint4*>(srow + c * 32) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    *reinterpret_cast<uint4*>(srow + c * 32 + 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                };
+                put(va, 0);
+                tc_wait_ld16(vb);
+                tc_ld16_nowait(t_row + 32, va);
+                put(vb, 1);
+                tc_wait_ld16(va);
+                put(va, 2);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(q_empty(s));                       // accumulator stage drained
+            asm volatile("bar.sync %0, 256;" ::"r"(bar_g) : "memory");   // the head is staged (+ labels)
+            if (it > 0) mbar_wait(ao_empty, (it - 1) & 1);                // the previous tile's proj MMAs have read AO
+            {
+                const int wg2 = tile * 2 + window;
+                if ((long long)wg2 * 64 < p.M) {
+                    const int win2 = wg2 % nW, wi2 = win2 / wpr, wj2 = win2 - wi2 * wpr;
+                    const bool masked = p.shift > 0 && (wi2 == nWy - 1 || wj2 == wpr - 1);
+                    attn_unit<32, true, unsigned char>(stg_s + window * 64 * AB_SROW16, stg + (size_t)window * 64 * AB_SROW16, AB_SROW16,
+                                                       strip, 0, 32, 64, stab + h * 225, lab + window * 64, masked, p.scale, lane,
+                                                       ao, window * 64, h);
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes of AO -> visible to UMMA
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ao_full);
+            asm volatile("bar.sync %0, 256;" ::"r"(bar_g) : "memory");   // staging (k, v) free for the group's next unit
+        };
+
+        // ---- final stage of tile iteration tp: PD -> x', LN2 (both groups together, 16 warps) ----
+        const int fw = uw;                                            // 0..15: rows fw*4 .. fw*4+3 of each 64-row half
+        const int hl = lane & 15, hh = lane >> 4;
+        float* stg32 = reinterpret_cast<float*>(sm + AB_STG_OFF);     // [64][AB_SROW32] fp32, aliases both bf16 staging tiles
+        const float inv_c = 1.f / (float)p.ln_C;
+        bool colin[AB_KB];
+#pragma unroll
+        for (int k = 0; k < AB_KB; ++k) colin[k] = 64 * k + 4 * hl < p.ln_C;
+        const bool o_bf16 = p.out16_dtype == SRK_BF16;
+        auto pack = [&](float a, float b) { return o_bf16 ? packf<SRK_BF16>(a, b) : packf<SRK_FP16>(a, b); };
+        auto final_stage = [&](int tp, int tile) {
+            asm volatile("bar.sync 3, 512;" ::: "memory");           // both groups left their staging tiles
+            mbar_wait(pd_full, tp & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                // rows of this warp in this half: tile row half*64 + fw*4 + i; lane i (< 4) computes its token row
+                int my_r = -1;
+                {
+                    const long long m = (long long)tile * 128 + half * 64 + fw * 4 + (lane & 3);
+                    if (m < p.M) {
+                        const int bi = (int)(m / p.T);
+                        my_r = bi * p.T + win_pos_to_token((int)(m - (long long)bi * p.T), p.H, p.W, p.shift);
+                    }
+                }
+                // residual rows of the half: requested now, they arrive under the TMEM drain (two row pairs per warp)
+                float4 resv[2][AB_KB];
+                int row[2];
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    row[rr] = __shfl_sync(0xffffffffu, my_r, 2 * rr + hh);
+                    const float* rp = p.res + (size_t)(row[rr] >= 0 ? row[rr] : 0) * p.ld32 + 4 * hl;
+#pragma unroll
+                    for (int k = 0; k < AB_KB; ++k)
+                        asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                     : "=f"(resv[rr][k].x), "=f"(resv[rr][k].y), "=f"(resv[rr][k].z), "=f"(resv[rr][k].w) : "l"(rp + 64 * k));
+                }
+                // phase T: the half's two lane groups (4 warps each, 48 columns per warp) drain PD into the staging tile
+                if ((lg >> 1) == half) {
+                    const int qc = (uw >> 2) & 3;                     // 0..3: which 48 of the 192 columns
+                    float* srow = stg32 + (size_t)((lg & 1) * 32 + lane) * AB_SROW32 + qc * 48;
+                    const uint32_t t_row = tPD + ((uint32_t)(lg * 32) << 16) + (uint32_t)(qc * 48);
+#pragma unroll 1
+                    for (int c = 0; c < 3; ++c) {
+                        uint32_t v[16];
+                        tc_ld16_nowait(t_row + (uint32_t)(c * 16), v);
+                        tc_wait_ld16(v);
+#pragma unroll
+                        for (int e = 0; e < 16; e += 4)
+                            *reinterpret_cast<uint4*>(srow + c * 16 + e) = make_uint4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(pd_empty);
+                }
+                asm volatile("bar.sync 3, 512;" ::: "memory");       // staging complete
+                // phase R: two row pairs per warp (one row per half-warp), lane hl owns columns 64 k + 4 hl
+                float4 v[2][AB_KB];
+                float sm_[2], mean[2], qq[2];
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    const float* srow = stg32 + (size_t)(fw * 4 + 2 * rr + hh) * AB_SROW32 + 4 * hl;
+                    sm_[rr] = 0.f;
+#pragma unroll
+                    for (int k = 0; k < AB_KB; ++k) {
+                        v[rr][k] = *reinterpret_cast<const float4*>(srow + 64 * k);
+                        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b_proj + 64 * k + 4 * hl));
+                        v[rr][k].x += bb.x + resv[rr][k].x; v[rr][k].y += bb.y + resv[rr][k].y;
+                        v[rr][k].z += bb.z + resv[rr][k].z; v[rr][k].w += bb.w + resv[rr][k].w;
+                        sm_[rr] += (v[rr][k].x + v[rr][k].y) + (v[rr][k].z + v[rr][k].w);      // pad columns are exactly 0
+                    }
+                    if (row[rr] >= 0) {
+                        float* oo = p.out32 + (size_t)row[rr] * p.ld32 + 4 * hl;
+#pragma unroll
+                        for (int k = 0; k < AB_KB; ++k) *reinterpret_cast<float4*>(oo + 64 * k) = v[rr][k];
+                    }
+                }
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr) sm_[rr] += __shfl_xor_sync(0xffffffffu, sm_[rr], o);
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    mean[rr] = sm_[rr] * inv_c; qq[rr] = 0.f;
+#pragma unroll
+                    for (int k = 0; k < AB_KB; ++k) {
+                        v[rr][k].x -= mean[rr]; v[rr][k].y -= mean[rr]; v[rr][k].z -= mean[rr]; v[rr][k].w -= mean[rr];
+                        const float q4 = (v[rr][k].x * v[rr][k].x + v[rr][k].y * v[rr][k].y) + (v[rr][k].z * v[rr][k].z + v[rr][k].w * v[rr][k].w);
+                        qq[rr] += colin[k] ? q4 : 0.f;
+                    }
+                }
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr) qq[rr] += __shfl_xor_sync(0xffffffffu, qq[rr], o);
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    const float rstd = rsqrtf(qq[rr] * inv_c + 1e-5f);
+                    if (row[rr] >= 0) {
+                        uint16_t* o16 = p.out16 + (size_t)row[rr] * p.ld16 + 4 * hl;
+#pragma unroll
+                        for (int k = 0; k < AB_KB; ++k) {
+                            float4 gg = make_float4(0.f, 0.f, 0.f, 0.f), bt = gg;                     // pad columns: 0
+                            if (colin[k]) {
+                                gg = __ldg(reinterpret_cast<const float4*>(p.ln_g + 64 * k + 4 * hl));
+                                bt = __ldg(reinterpret_cast<const float4*>(p.ln_b + 64 * k + 4 * hl));
+                            }
+                            *reinterpret_cast<uint2*>(o16 + 64 * k) =
+                                make_uint2(pack(v[rr][k].x * rstd * gg.x + bt.x, v[rr][k].y * rstd * gg.y + bt.y),
+                                           pack(v[rr][k].z * rstd * gg.z + bt.z, v[rr][k].w * rstd * gg.w + bt.w));
+                        }
+                    }
+                }
+                asm volatile("bar.sync 3, 512;" ::: "memory");       // staging free
+            }
+        };
+
+        int it = 0;
+        int prev_tile = 0;
+        for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
+            unit(it, tile, grp);
+            if (it > 0) final_stage(it - 1, prev_tile);
+            unit(it, tile, grp + 2);
+            unit(it, tile, grp + 4);
+            prev_tile = tile;
+        }
+        if (n_my > 0) final_stage(n_my - 1, prev_tile);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+}  // namespace srk
+
+using namespace srk;
+
+extern "C" int srk_attn_block(const srk_attn_block_args* a, void* stream) {
+    SRK_REQUIRE(a && a->A && a->Wqkv && a->Wproj && a->b_proj && a->rel_table && a->res && a->out32 && a->out16 && a->ln_g && a->ln_b,
+                "attn_block: null pointer");
+    if (srk_get_engine() != SRK_ENGINE_TCGEN05)
+        return fail(SRK_ERR_UNSUPPORTED, "attn_block: the fused attention block exists for the tcgen05 engine only");
+    if (a->Cp != AB_CP || a->num_heads != AB_NH)
+        return fail(SRK_ERR_UNSUPPORTED, "attn_block: built for a padded embedding of 192 = 6 heads x 32 (Cp=%d, heads=%d)", a->Cp, a->num_heads);
+    SRK_REQUIRE(a->M > 0 && a->H > 0 && a->W > 0 && a->H % 8 == 0 && a->W % 8 == 0 && a->M % (a->H * a->W) == 0,
+                "attn_block: rows must be whole images of 8x8 windows");
+    SRK_REQUIRE(a->shift == 0 || a->shift == 4, "attn_block: shift must be 0 or window_size / 2");
+    SRK_REQUIRE(a->lda >= AB_CP && a->lda % 8 == 0 && a->ld32 >= AB_CP && a->ld32 % 4 == 0 && a->ld16 >= AB_CP && a->ld16 % 8 == 0,
+                "attn_block: bad leading dims");
+    SRK_REQUIRE(a->ln_C > 0 && a->ln_C <= AB_CP && a->ln_C % 4 == 0 && a->C == a->ln_C, "attn_block: bad LayerNorm width");
+    SRK_REQUIRE(((uintptr_t)a->A & 15) == 0 && ((uintptr_t)a->res & 15) == 0 && ((uintptr_t)a->out32 & 15) == 0 && ((uintptr_t)a->out16 & 7) == 0 &&
+                ((uintptr_t)a->b_proj & 15) == 0 && ((uintptr_t)a->ln_g & 15) == 0 && ((uintptr_t)a->ln_b & 15) == 0, "attn_block: misaligned pointer");
+    AbP p{};
+    p.M = a->M; p.m_tiles = ceil_div(a->M, 128); p.C = a->C; p.H = a->H; p.W = a->W; p.T = a->H * a->W; p.shift = a->shift;
+    p.scale = a->scale; p.table = a->rel_table; p.b_proj = a->b_proj;
+    p.res = a->res; p.out32 = a->out32; p.ld32 = a->ld32;
+    p.out16 = (uint16_t*)a->out16; p.ld16 = a->ld16; p.out16_dtype = a->out16_dtype;
+    p.ln_g = a->ln_g; p.ln_b = a->ln_b; p.ln_C = a->ln_C;
+    CUtensorMap ma, mq, mp;
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)AB_CP, (cuuint64_t)a->M};
+        cuuint64_t strides[1] = {(cuuint64_t)a->lda * 2};
+        cuuint32_t box[2] = {64, 128};
+        if (int rc = encode_map(&ma, SRK_BF16, 2, a->A, dims, strides, box)) return rc;
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)AB_CP, (cuuint64_t)(AB_NH * 96)};
+        cuuint64_t strides[1] = {(cuuint64_t)AB_CP * 2};
+        cuuint32_t box[2] = {64, 96};
+        if (int rc = encode_map(&mq, SRK_BF16, 2, a->Wqkv, dims, strides, box)) return rc;
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)AB_CP, (cuuint64_t)AB_CP};
+        cuuint64_t strides[1] = {(cuuint64_t)AB_CP * 2};
+        cuuint32_t box[2] = {64, 96};
+        if (int rc = encode_map(&mp, SRK_BF16, 2, a->Wproj, dims, strides, box)) return rc;
+    }
+    static bool attr[64] = {};
+    if (first_use_on_device(attr)) SRK_CUDA(cudaFuncSetAttribute(attn_block_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AB_SMEM));
+    ProfScope ps(SRK_PROF_GEMM, stream);
+    const int grid = p.m_tiles < num_sms() ? p.m_tiles : num_sms();
+    attn_block_tc5_kernel<<<grid, AB_THREADS, AB_SMEM, (cudaStream_t)stream>>>(ma, mq, mp, p);
+    SRK_LAUNCH_CHECK("attn_block_tc5_kernel");
+    return 0;
+}

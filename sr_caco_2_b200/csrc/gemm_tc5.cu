@@ -20,7 +20,6 @@
 //   The epilogue of tile i overlaps the MMAs of tile i+1 (two TMEM stages).
 #include "tc5_ptx.cuh"
 #include "attention.cuh"
-#include <stdlib.h>
 
 namespace srk {
 
@@ -556,13 +555,12 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         v[k].x = v[k].x * g.res_scale + t.x;
                         v[k].y = v[k].y * g.res_scale + t.y;
                     }
-                    if (kPrefetch) {                           // request row i of the next tile
-                        const int mx = __shfl_sync(0xffffffffu, nx_m, i);
+                    if (kPrefetch) {                           // request row i of the next tile (unconditionally, see process_rows)
                         const int rx = __shfl_sync(0xffffffffu, nx_r32, i);
                         const float* rn = g.res + (size_t)rx * g.ld32 + n0x + 2 * lane;
 #pragma unroll
                         for (int k = 0; k < NP; ++k)
-                            rslot[k] = mx >= 0 ? __ldg(reinterpret_cast<const float2*>(rn + 64 * k)) : make_float2(0.f, 0.f);
+                            asm volatile("ld.global.v2.f32 {%0, %1}, [%2];" : "=f"(rslot[k].x), "=f"(rslot[k].y) : "l"(rn + 64 * k));
                     }
                 }
                 if ((EPI == E_GENERIC || kRes) && g.out32 && valid) {
@@ -637,12 +635,13 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         v[r][k].y = actf<ACT>(v[r][k].y + bia[k].y) * g.res_scale + rs[k].y;
                     }
                     // request row i of the next tile into the same registers
-                    const int mx = __shfl_sync(0xffffffffu, nx_m, i0 + r);
+                    // (rows outside the problem carry r32 = 0: an unconditional load keeps the request in flight in the slot's
+                    //  own registers; a predicated load + select makes the compiler wait for the data on the spot)
                     const int rx = __shfl_sync(0xffffffffu, nx_r32, i0 + r);
                     const float* rn = g.res + (size_t)rx * g.ld32 + n0x + 2 * lane;
 #pragma unroll
                     for (int k = 0; k < NP; ++k)
-                        rs[k] = mx >= 0 ? __ldg(reinterpret_cast<const float2*>(rn + 64 * k)) : make_float2(0.f, 0.f);
+                        asm volatile("ld.global.v2.f32 {%0, %1}, [%2];" : "=f"(rs[k].x), "=f"(rs[k].y) : "l"(rn + 64 * k));
                     if (m[r] >= 0) {
                         float* oo = g.out32 + (size_t)r32[r] * g.ld32 + n0 + 2 * lane;
 #pragma unroll
@@ -817,16 +816,6 @@ static int dispatch_tc5(const srk_gemm_args* a, const CUtensorMap& ma, const CUt
     return launch_tc5<BN, E_GENERIC, 0, 0>(ma, mb, p, st);
 }
 
-int qkv_attention_tcgen05(const srk_gemm_args* a, cudaStream_t st);      // attn_tc5.cu
-// SRK_ATTN_TC5=1 routes the fused qkv + attention call to the all-tcgen05 kernel of attn_tc5.cu
-// (S and P V on tensor memory).  It is parity-tested but measured slower than the mma.sync attention
-// epilogue below (80 vs 67 us at cfg3: it is bound by the 64 B/clk TMEM read port and by per-row
-// softmax latency), so it stays opt-in.  Read per call so that a test can flip it.
-static bool attn_tc5_enabled() {
-    const char* e = getenv("SRK_ATTN_TC5");
-    return e && atoi(e) != 0;
-}
-
 int gemm_tcgen05(const srk_gemm_args* a, cudaStream_t st) {
     SRK_REQUIRE(a->N % 64 == 0, "gemm(tcgen05): N=%d must be a multiple of 64", a->N);
     SRK_REQUIRE(((uintptr_t)a->A & 15) == 0 && ((uintptr_t)a->Wt & 15) == 0, "gemm(tcgen05): operands must be 16 B aligned");
@@ -847,7 +836,6 @@ int gemm_tcgen05(const srk_gemm_args* a, cudaStream_t st) {
     p.n_tiles = a->N / BN;
     p.nkb = a->K / TBK;
     const bool attn = a->attn_table != nullptr;
-    if (attn && a->K == 192 && attn_tc5_enabled()) return qkv_attention_tcgen05(a, st);
     if (attn) SRK_REQUIRE(BN == 192 && a->N == p.n_tiles * 192, "gemm(tcgen05): fused attention needs N == pairs * 192");
     CUtensorMap ma, mb;
     if (a->a_mode == SRK_A_CONV3X3) {

@@ -189,6 +189,22 @@ extern "C" int srk_swinir_forward(const srk_swinir_plan* p, const float* x, floa
             a16_ready = false;
             const bool fused_attn = !(p->options & SRK_OPT_NO_FUSED_ATTN) && fuse_ln && p->dp == 32 && nH % 2 == 0 && p->ao_p == nH * 32 &&
                                     b.nq_p == 3 * nH * 32;
+            // the whole attention half in ONE kernel (attn_block_tc5.cu): q, k, v, the attention output and the proj
+            // accumulator stay on the SM; built for 6 heads x 32 with the qkv bias folded into the pad K columns
+            const bool fused_block = fused_attn && !(p->options & SRK_OPT_NO_FUSED_BLOCK) && a16_ones && s.w_qkv_hm != nullptr &&
+                                     Cp == 192 && nH == 6 && ldt == SRK_BF16;
+            if (fused_block) {
+                srk_attn_block_args ab{};
+                ab.A = a16; ab.lda = Cp; ab.M = M; ab.C = C; ab.Cp = Cp; ab.H = H; ab.W = W; ab.shift = s.shift; ab.num_heads = nH;
+                ab.Wqkv = s.w_qkv_hm; ab.Wproj = s.w_proj; ab.b_proj = s.b_proj; ab.rel_table = s.rel_table;
+                ab.scale = 1.0f / sqrtf((float)hd);
+                ab.res = cur; ab.out32 = b.XB; ab.ld32 = Cp;
+                // the kernel reads A tile by tile while other CTAs already write LN2 rows (token order): ping-pong
+                ab.out16 = alt; ab.ld16 = Cp; ab.out16_dtype = ldt;
+                ab.ln_g = s.ln2_g; ab.ln_b = s.ln2_b; ab.ln_C = C;
+                TRY(srk_attn_block(&ab, stream));
+                { void* t = a16; a16 = alt; alt = t; }
+            } else {
             if (fused_attn) {
                 // qkv projection + window attention in one kernel: q, k, v stay in shared memory
                 const bool fb = a16_ones && s.w_qkv_fb != nullptr;
@@ -215,6 +231,7 @@ extern "C" int srk_swinir_forward(const srk_swinir_plan* p, const float* x, floa
                     g.out16 = a16; g.ld16 = Cp;
                 }
                 TRY(srk_gemm(&g, stream));
+            }
             }
             if (!fuse_ln)
                 TRY(srk_layernorm(b.XB, Cp, M, C, s.ln2_g, s.ln2_b, eps, a16, Cp, ldt, nullptr, H, W, -1, stream));

@@ -235,7 +235,10 @@ class SwinIR(nn.Module):
                 wq, bq = P.pack_qkv(blk.attn.qkv.weight.detach(), blk.attn.qkv.bias.detach(), nh, d, dp, nq_p, Cp, linear_dtype)
                 s.w_qkv, s.b_qkv = k(wq), k(bq)
                 if Cp - Cdim >= 2 and Cdim % 2 == 0:
-                    s.w_qkv_fb = k(P.fold_qkv_bias(wq, bq, Cdim))
+                    wfb = P.fold_qkv_bias(wq, bq, Cdim)
+                    s.w_qkv_fb = k(wfb)
+                    if dp == 32 and nh * dp == Cp:
+                        s.w_qkv_hm = k(P.pack_qkv_heads(wfb, nh, dp))
                 s.w_proj = k(P.pack_proj(blk.attn.proj.weight.detach(), nh, d, dp, Cp, ao_p, linear_dtype))
                 s.b_proj = k(P.pad_bias(blk.attn.proj.bias.detach(), Cp))
                 s.w_fc1 = k(P.pack_linear(blk.mlp.fc1.weight.detach(), hid_p, Cp, linear_dtype))

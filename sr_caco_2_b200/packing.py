@@ -57,6 +57,13 @@ def fold_qkv_bias(w_packed: torch.Tensor, bias_packed: torch.Tensor, c: int) -> 
     return out.contiguous()
 
 
+def pack_qkv_heads(w_packed: torch.Tensor, nh: int, dp: int) -> torch.Tensor:
+    """Packed qkv weight rows [which][head][dp] -> head-major rows [head][which][dp] (srk_attn_block streams one
+    head's 3 * dp rows [q | k | v] per MMA job)."""
+    k_p = w_packed.shape[1]
+    return w_packed[: 3 * nh * dp].view(3, nh, dp, k_p).permute(1, 0, 2, 3).reshape(3 * nh * dp, k_p).contiguous()
+
+
 def pack_proj(w: torch.Tensor, nh: int, d: int, dp: int, n_p: int, k_p: int, dtype_code: int):
     """proj Linear (C, C): input column (head, e) = head*d + e -> column head*dp + e."""
     C = w.shape[0]

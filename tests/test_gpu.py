@@ -399,7 +399,8 @@ def test_folded_tail_network_equals_unfolded(L):
 
 @pytest.mark.parametrize("geom", [(180, 6, 24, 16, 3), (128, 4, 16, 16, 1), (180, 6, 64, 64, 9), (180, 6, 40, 24, 5)])
 def test_fused_qkv_attention_equals_unfused(L, geom):
-    """E_ATTN epilogue (qkv GEMM + window attention in one tcgen05 kernel) vs srk_gemm + srk_window_attention."""
+    """E_ATTN epilogue (qkv GEMM + window attention in one tcgen05 kernel) vs srk_gemm + srk_window_attention:
+    the same attention unit, bit for bit."""
     if "tcgen05" not in ENGINES:
         pytest.skip("tcgen05 engine not under test")
     L.set_engine("tcgen05")
@@ -417,35 +418,79 @@ def test_fused_qkv_attention_equals_unfused(L, geom):
     A = torch.zeros(M, Cp); A[:, :Cc] = torch.randn(M, Cc, generator=g)
     table = (torch.randn(225, nh, generator=g) * 0.5).t().contiguous()
     Ad, wd, bd, td = A.bfloat16().to(DEV), wpk.to(DEV), bpk.to(DEV), table.to(DEV)
-    prev = os.environ.get("SRK_ATTN_TC5")
-    try:
-        for shift in (0, 4):
-            qkv = torch.empty(M, nq, dtype=torch.bfloat16, device=DEV)
-            ref = torch.empty(M, nh * 32, dtype=torch.bfloat16, device=DEV)
-            _gemm(L, A=Ad, a_mode=L.A_ROWS, lda=Cp, nB=B, H=H, W=W, Wt=wd, M=M, N=nq, K=Cp, dtype=L.SRK_BF16, bias=bd,
-                  out16=qkv, ld16=nq, out16_dtype=L.SRK_BF16)
-            L.check(L.load().srk_window_attention(L.ptr(qkv), nq, L.ptr(ref), nh * 32, L.ptr(td), B, H, W, nh, 32,
-                                                  d ** -0.5, shift, L.stream_ptr()))
-            # "0": mma.sync attention epilogue of gemm_tc5.cu -- the same attention unit as
-            #      srk_window_attention, bit for bit.
-            # "1": all-tcgen05 kernel (attn_tc5.cu, K = 192 only): other summation order and P rounded to
-            #      bf16 before the normalisation -> compared at bf16 resolution.
-            for mode in ("0", "1"):
-                os.environ["SRK_ATTN_TC5"] = mode
-                got = torch.full((M, nh * 32), 3.0, dtype=torch.bfloat16, device=DEV)
-                _gemm(L, A=Ad, a_mode=L.A_ROWS, lda=Cp, nB=B, H=H, W=W, Wt=wd, M=M, N=nq, K=Cp, dtype=L.SRK_BF16,
-                      bias=bd, out16=got, ld16=nh * 32, out16_dtype=L.SRK_BF16, attn_table=td, attn_heads=nh,
-                      attn_scale=d ** -0.5, attn_shift=shift)
-                err = float((got.float() - ref.float()).abs().max())
-                if mode == "1" and Cp == 192:
-                    assert err <= 0.01 * float(ref.float().abs().max()) + 1e-3, (mode, shift, err)
-                else:
-                    assert torch.equal(got, ref), (mode, shift, err)
-    finally:
-        if prev is None:
-            os.environ.pop("SRK_ATTN_TC5", None)
-        else:
-            os.environ["SRK_ATTN_TC5"] = prev
+    for shift in (0, 4):
+        qkv = torch.empty(M, nq, dtype=torch.bfloat16, device=DEV)
+        ref = torch.empty(M, nh * 32, dtype=torch.bfloat16, device=DEV)
+        _gemm(L, A=Ad, a_mode=L.A_ROWS, lda=Cp, nB=B, H=H, W=W, Wt=wd, M=M, N=nq, K=Cp, dtype=L.SRK_BF16, bias=bd,
+              out16=qkv, ld16=nq, out16_dtype=L.SRK_BF16)
+        L.check(L.load().srk_window_attention(L.ptr(qkv), nq, L.ptr(ref), nh * 32, L.ptr(td), B, H, W, nh, 32,
+                                              d ** -0.5, shift, L.stream_ptr()))
+        got = torch.full((M, nh * 32), 3.0, dtype=torch.bfloat16, device=DEV)
+        _gemm(L, A=Ad, a_mode=L.A_ROWS, lda=Cp, nB=B, H=H, W=W, Wt=wd, M=M, N=nq, K=Cp, dtype=L.SRK_BF16,
+              bias=bd, out16=got, ld16=nh * 32, out16_dtype=L.SRK_BF16, attn_table=td, attn_heads=nh,
+              attn_scale=d ** -0.5, attn_shift=shift)
+        assert torch.equal(got, ref), (shift, float((got.float() - ref.float()).abs().max()))
+
+
+@pytest.mark.parametrize("geom", [(24, 16, 3), (64, 64, 5), (40, 24, 1), (8, 8, 3), (16, 8, 1)])
+def test_attn_block_kernel_equals_unfused_sequence(L, geom):
+    """srk_attn_block (LN1 rows -> qkv -> window attention -> proj + residual -> LN2 in ONE kernel) against the
+    launch sequence it replaces, through the C ABI: fused qkv + attention GEMM, then the proj GEMM with the
+    window_reverse + roll residual map and the fused LayerNorm.  The attention unit and the MMA operand order
+    are the same, so x' agrees to fp32 rounding of the residual add and LN2 to one bf16 ulp.
+    (8, 8, 3): 64-token images -> odd window counts, the last tile has one window; M % 128 != 0.)"""
+    if "tcgen05" not in ENGINES:
+        pytest.skip("tcgen05 engine not under test")
+    L.set_engine("tcgen05")
+    H, W, B = geom
+    Cc, nh, Cp, d = 180, 6, 192, 30
+    g = torch.Generator().manual_seed(21)
+    M = B * H * W
+    from sr_caco_2_b200 import packing as P
+    wq = torch.randn(3 * Cc, Cc, generator=g) * 0.08
+    bq = torch.randn(3 * Cc, generator=g) * 0.2
+    wp = torch.randn(Cc, Cc, generator=g) * 0.08
+    bp = torch.randn(Cc, generator=g) * 0.1
+    nq = 3 * nh * 32
+    wpk, bpk = P.pack_qkv(wq, bq, nh, d, 32, nq, Cp, L.SRK_BF16)
+    wfb = P.fold_qkv_bias(wpk, bpk, Cc)
+    whm = P.pack_qkv_heads(wfb, nh, 32)
+    wpr = P.pack_proj(wp, nh, d, 32, Cp, nh * 32, L.SRK_BF16)
+    bpr = P.pad_bias(bp, Cp)
+    A = torch.zeros(M, Cp); A[:, :Cc] = torch.randn(M, Cc, generator=g); A[:, Cc:Cc + 2] = 1.0
+    res = torch.zeros(M, Cp); res[:, :Cc] = torch.randn(M, Cc, generator=g)
+    gam, bet = 1.0 + 0.1 * torch.randn(Cc, generator=g), 0.1 * torch.randn(Cc, generator=g)
+    table = (torch.randn(225, nh, generator=g) * 0.5).t().contiguous()
+    dv = lambda t: t.to(DEV)
+    Ad, td = dv(A.bfloat16()), dv(table)
+    wfbd, whmd, wprd, bprd, gd, bd = dv(wfb), dv(whm), dv(wpr), dv(bpr), dv(gam), dv(bet)
+    for shift in (0, 4):
+        if shift and (H <= 8 or W <= 8):
+            continue                                          # the reference never shifts a one-window axis
+        ao = torch.empty(M, nh * 32, dtype=torch.bfloat16, device=DEV)
+        _gemm(L, A=Ad, a_mode=L.A_ROWS, lda=Cp, nB=B, H=H, W=W, Wt=wfbd, M=M, N=nq, K=Cp, dtype=L.SRK_BF16,
+              out16=ao, ld16=nh * 32, out16_dtype=L.SRK_BF16, attn_table=td, attn_heads=nh, attn_scale=d ** -0.5,
+              attn_shift=shift)
+        x_ref = dv(res.clone())
+        ln_ref = torch.full((M, Cp), 5.0, dtype=torch.bfloat16, device=DEV)
+        _gemm(L, A=ao, a_mode=L.A_ROWS, lda=nh * 32, nB=B, H=H, W=W, Wt=wprd, M=M, N=Cp, K=nh * 32, dtype=L.SRK_BF16,
+              bias=bprd, res=x_ref, out32=x_ref, ld32=Cp, win_shift=shift, ln_g=gd, ln_b=bd, ln_C=Cc,
+              out16=ln_ref, ld16=Cp, out16_dtype=L.SRK_BF16)
+        x_got = dv(res.clone())
+        ln_got = torch.full((M, Cp), 7.0, dtype=torch.bfloat16, device=DEV)
+        a = L.AttnBlockArgs()
+        a.A, a.lda, a.M, a.C, a.Cp, a.H, a.W, a.shift, a.num_heads = L.ptr(Ad), Cp, M, Cc, Cp, H, W, shift, nh
+        a.Wqkv, a.Wproj, a.b_proj, a.rel_table, a.scale = L.ptr(whmd), L.ptr(wprd), L.ptr(bprd), L.ptr(td), d ** -0.5
+        a.res, a.out32, a.ld32, a.out16, a.ld16, a.out16_dtype = L.ptr(x_got), L.ptr(x_got), Cp, L.ptr(ln_got), Cp, L.SRK_BF16
+        a.ln_g, a.ln_b, a.ln_C = L.ptr(gd), L.ptr(bd), Cc
+        L.check(L.load().srk_attn_block(C.byref(a), L.stream_ptr()))
+        torch.cuda.synchronize()
+        scale = max(1.0, float(x_ref.abs().max()))
+        assert float((x_got - x_ref).abs().max()) <= 2e-6 * scale, (shift, float((x_got - x_ref).abs().max()))
+        assert float(x_got[:, Cc:].abs().max()) == 0.0
+        dl = (ln_got.float() - ln_ref.float()).abs()
+        assert float(dl.max()) <= 0.04 and float((dl > 0).float().mean()) < 0.02, (shift, float(dl.max()))
+        assert float(ln_got.float()[:, Cc:].abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("dims", [(180, 192, 360, 384), (60, 64, 120, 128), (128, 128, 256, 256)])
