@@ -45,8 +45,9 @@ constexpr int AB_W_OFF = AB_A_OFF + AB_KB * 16384;
 constexpr int AB_AO_OFF = AB_W_OFF + AB_NW * AB_WSLOT;
 constexpr int AB_STG_OFF = AB_AO_OFF + AB_KB * 16384;
 constexpr int AB_BAR_OFF = AB_STG_OFF + 2 * AB_STG;
-constexpr int AB_AUX = 256 + AB_NH * 225 * 4 + 256;          // barriers, rel-pos tables, shift-mask labels
-constexpr size_t AB_SMEM = (size_t)AB_BAR_OFF + AB_AUX + 1024;
+constexpr int AB_TAB = (AB_NH * 225 * 4 + 15) / 16 * 16;         // rel-pos tables, padded to 16 B
+constexpr int AB_AUX = 256 + AB_TAB + 256 + AB_CP * 4;   // barriers, rel-pos tables, shift-mask labels, proj bias
+constexpr size_t AB_SMEM = (size_t)AB_BAR_OFF + AB_AUX;         // the dynamic shared memory window itself is 1024 B aligned
 static_assert(64 * AB_SROW32 * 4 <= 2 * AB_STG, "the fp32 staging of the final stage aliases the two bf16 staging tiles");
 static_assert(AB_SMEM <= 232448, "shared memory plan exceeds the 227 KB per-CTA limit");
 
@@ -63,10 +64,10 @@ struct AbP {
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_block_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_wq,
                       const __grid_constant__ CUtensorMap map_wp, const AbP p) {
-    extern __shared__ unsigned char ab_raw[];
-    const uint32_t raw = smem_u32(ab_raw);
-    const uint32_t base = (raw + 1023u) & ~1023u;
-    unsigned char* sm = ab_raw + (base - raw);
+    extern __shared__ __align__(1024) unsigned char ab_raw[];
+    const uint32_t base = smem_u32(ab_raw);
+    if ((base & 1023u) != 0) __trap();                               // SW128 operand tiles need 1024 B alignment (no slack is allocated)
+    unsigned char* sm = ab_raw;
     const uint32_t sA = base + AB_A_OFF, sW = base + AB_W_OFF, sAO = base + AB_AO_OFF, sStg = base + AB_STG_OFF,
                    bars = base + AB_BAR_OFF;
     const uint32_t a_full = bars, a_empty = bars + 8;
@@ -77,7 +78,8 @@ attn_block_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     const uint32_t ao_full = bars + 160, ao_empty = bars + 168, pd_full = bars + 176, pd_empty = bars + 184,
                    tmem_slot = bars + 192;
     float* stab = reinterpret_cast<float*>(sm + AB_BAR_OFF + 256);                    // [heads][225]
-    unsigned char* slab = sm + AB_BAR_OFF + 256 + AB_NH * 225 * 4;                   // [group][window][64] region labels
+    unsigned char* slab = sm + AB_BAR_OFF + 256 + AB_TAB;                   // [group][window][64] region labels
+    float* sbp = reinterpret_cast<float*>(slab + 256);                               // [192] proj bias
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_my = (int)blockIdx.x < p.m_tiles ? (p.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -98,6 +100,7 @@ attn_block_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     for (int i = threadIdx.x; i < AB_NH * 225; i += AB_THREADS) stab[i] = p.table[i];
+    for (int i = threadIdx.x; i < AB_CP; i += AB_THREADS) sbp[i] = p.b_proj[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -262,7 +265,9 @@ attn_block_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         };
 
         // ---- final stage of tile iteration tp: PD -> x', LN2 (both groups together, 16 warps) ----
-        const int fw = uw;                                            // 0..15: rows fw*4 .. fw*4+3 of each 64-row half
+        // A warp finishes rows fw*4 .. fw*4+3 of each 64-row half (= window), two rows at a time: half-warp hh
+        // owns one row, lane hl the columns 64 k + 4 hl.
+        const int fw = uw;
         const int hl = lane & 15, hh = lane >> 4;
         float* stg32 = reinterpret_cast<float*>(sm + AB_STG_OFF);     // [64][AB_SROW32] fp32, aliases both bf16 staging tiles
         const float inv_c = 1.f / (float)p.ln_C;
@@ -271,27 +276,61 @@ attn_block_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         for (int k = 0; k < AB_KB; ++k) colin[k] = 64 * k + 4 * hl < p.ln_C;
         const bool o_bf16 = p.out16_dtype == SRK_BF16;
         auto pack = [&](float a, float b) { return o_bf16 ? packf<SRK_BF16>(a, b) : packf<SRK_FP16>(a, b); };
+        // per-window geometry of a tile (uniform over the CTA): image base row, window origin in the shifted frame
+        struct WinGeo { int base, y0, x0; };                          // base < 0: the window lies beyond the problem
+        auto win_geo = [&](int tile, int half) {
+            WinGeo g;
+            const int wg = tile * 2 + half;
+            const int bi = wg / nW, win = wg - bi * nW;
+            const int wi = win / wpr, wj = win - wi * wpr;
+            g.base = (long long)wg * 64 < p.M ? bi * p.T : -1;
+            g.y0 = (wi << 3) + p.shift; g.x0 = (wj << 3) + p.shift;
+            return g;
+        };
+        // token row (fp32 stream / LN2 output) of this lane's row rr (0, 1) of a window, or -1
+        auto token_row = [&](const WinGeo& g, int rr) {
+            const int pos = fw * 4 + 2 * rr + hh;
+            int y = g.y0 + (pos >> 3), x = g.x0 + (pos & 7);
+            if (y >= p.H) y -= p.H;
+            if (x >= p.W) x -= p.W;
+            return g.base < 0 ? -1 : g.base + y * p.W + x;
+        };
+        // L2 prefetch of the residual rows a tile's final stage will read (issued a whole unit ahead: no registers held)
+        auto prefetch_res = [&](int tile) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const WinGeo g = win_geo(tile, half);
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    const int row = token_row(g, rr);
+                    if (row >= 0 && hl < 6)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res + (size_t)row * p.ld32 + 32 * hl));
+                }
+            }
+        };
         auto final_stage = [&](int tp, int tile) {
+            // LayerNorm parameters of this lane's columns (requested before the waits below)
+            float4 gg[AB_KB], bt[AB_KB];
+#pragma unroll
+            for (int k = 0; k < AB_KB; ++k) {
+                gg[k] = make_float4(0.f, 0.f, 0.f, 0.f); bt[k] = gg[k];                   // pad columns: 0
+                if (colin[k]) {
+                    gg[k] = __ldg(reinterpret_cast<const float4*>(p.ln_g + 64 * k + 4 * hl));
+                    bt[k] = __ldg(reinterpret_cast<const float4*>(p.ln_b + 64 * k + 4 * hl));
+                }
+            }
             asm volatile("bar.sync 3, 512;" ::: "memory");           // both groups left their staging tiles
             mbar_wait(pd_full, tp & 1);
             tc_fence_after();
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
-                // rows of this warp in this half: tile row half*64 + fw*4 + i; lane i (< 4) computes its token row
-                int my_r = -1;
-                {
-                    const long long m = (long long)tile * 128 + half * 64 + fw * 4 + (lane & 3);
-                    if (m < p.M) {
-                        const int bi = (int)(m / p.T);
-                        my_r = bi * p.T + win_pos_to_token((int)(m - (long long)bi * p.T), p.H, p.W, p.shift);
-                    }
-                }
-                // residual rows of the half: requested now, they arrive under the TMEM drain (two row pairs per warp)
+                // residual rows of the half (two row pairs per warp): L2 hits thanks to prefetch_res, they arrive under the TMEM drain
                 float4 resv[2][AB_KB];
                 int row[2];
+                const WinGeo geo = win_geo(tile, half);
 #pragma unroll
                 for (int rr = 0; rr < 2; ++rr) {
-                    row[rr] = __shfl_sync(0xffffffffu, my_r, 2 * rr + hh);
+                    row[rr] = token_row(geo, rr);
                     const float* rp = p.res + (size_t)(row[rr] >= 0 ? row[rr] : 0) * p.ld32 + 4 * hl;
 #pragma unroll
                     for (int k = 0; k < AB_KB; ++k)
@@ -303,15 +342,19 @@ attn_block_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                     const int qc = (uw >> 2) & 3;                     // 0..3: which 48 of the 192 columns
                     float* srow = stg32 + (size_t)((lg & 1) * 32 + lane) * AB_SROW32 + qc * 48;
                     const uint32_t t_row = tPD + ((uint32_t)(lg * 32) << 16) + (uint32_t)(qc * 48);
-#pragma unroll 1
-                    for (int c = 0; c < 3; ++c) {
-                        uint32_t v[16];
-                        tc_ld16_nowait(t_row + (uint32_t)(c * 16), v);
-                        tc_wait_ld16(v);
+                    uint32_t va[16], vb[16];
+                    tc_ld16_nowait(t_row, va);
+                    tc_wait_ld16(va);
+                    tc_ld16_nowait(t_row + 16, vb);
 #pragma unroll
-                        for (int e = 0; e < 16; e += 4)
-                            *reinterpret_cast<uint4*>(srow + c * 16 + e) = make_uint4(v[e], v[e + 1], v[e + 2], v[e + 3]);
-                    }
+                    for (int e = 0; e < 16; e += 4) *reinterpret_cast<uint4*>(srow + e) = make_uint4(va[e], va[e + 1], va[e + 2], va[e + 3]);
+                    tc_wait_ld16(vb);
+                    tc_ld16_nowait(t_row + 32, va);
+#pragma unroll
+                    for (int e = 0; e < 16; e += 4) *reinterpret_cast<uint4*>(srow + 16 + e) = make_uint4(vb[e], vb[e + 1], vb[e + 2], vb[e + 3]);
+                    tc_wait_ld16(va);
+#pragma unroll
+                    for (int e = 0; e < 16; e += 4) *reinterpret_cast<uint4*>(srow + 32 + e) = make_uint4(va[e], va[e + 1], va[e + 2], va[e + 3]);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(pd_empty);
@@ -327,9 +370,9 @@ attn_block_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 #pragma unroll
                     for (int k = 0; k < AB_KB; ++k) {
                         v[rr][k] = *reinterpret_cast<const float4*>(srow + 64 * k);
-                        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b_proj + 64 * k + 4 * hl));
-                        v[rr][k].x += bb.x + resv[rr][k].x; v[rr][k].y += bb.y + resv[rr][k].y;
-                        v[rr][k].z += bb.z + resv[rr][k].z; v[rr][k].w += bb.w + resv[rr][k].w;
+                        const float4 bb = *reinterpret_cast<const float4*>(sbp + 64 * k + 4 * hl);
+                        v[rr][k].x = (v[rr][k].x + bb.x) + resv[rr][k].x; v[rr][k].y = (v[rr][k].y + bb.y) + resv[rr][k].y;
+                        v[rr][k].z = (v[rr][k].z + bb.z) + resv[rr][k].z; v[rr][k].w = (v[rr][k].w + bb.w) + resv[rr][k].w;
                         sm_[rr] += (v[rr][k].x + v[rr][k].y) + (v[rr][k].z + v[rr][k].w);      // pad columns are exactly 0
                     }
                     if (row[rr] >= 0) {
@@ -362,32 +405,29 @@ attn_block_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                     if (row[rr] >= 0) {
                         uint16_t* o16 = p.out16 + (size_t)row[rr] * p.ld16 + 4 * hl;
 #pragma unroll
-                        for (int k = 0; k < AB_KB; ++k) {
-                            float4 gg = make_float4(0.f, 0.f, 0.f, 0.f), bt = gg;                     // pad columns: 0
-                            if (colin[k]) {
-                                gg = __ldg(reinterpret_cast<const float4*>(p.ln_g + 64 * k + 4 * hl));
-                                bt = __ldg(reinterpret_cast<const float4*>(p.ln_b + 64 * k + 4 * hl));
-                            }
+                        for (int k = 0; k < AB_KB; ++k)
                             *reinterpret_cast<uint2*>(o16 + 64 * k) =
-                                make_uint2(pack(v[rr][k].x * rstd * gg.x + bt.x, v[rr][k].y * rstd * gg.y + bt.y),
-                                           pack(v[rr][k].z * rstd * gg.z + bt.z, v[rr][k].w * rstd * gg.w + bt.w));
-                        }
+                                make_uint2(pack(v[rr][k].x * rstd * gg[k].x + bt[k].x, v[rr][k].y * rstd * gg[k].y + bt[k].y),
+                                           pack(v[rr][k].z * rstd * gg[k].z + bt[k].z, v[rr][k].w * rstd * gg[k].w + bt[k].w));
                     }
                 }
                 asm volatile("bar.sync 3, 512;" ::: "memory");       // staging free
             }
         };
 
-        int it = 0;
-        int prev_tile = 0;
-        for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
-            unit(it, tile, grp);
+        // per tile: first head unit, then (both groups together) the final stage of the PREVIOUS tile, then the other two units
+        int tile = blockIdx.x, prev_tile = 0;
+#pragma unroll 1
+        for (int it = 0; it <= n_my; ++it, tile += gridDim.x) {
+            if (it < n_my) unit(it, tile, grp);
             if (it > 0) final_stage(it - 1, prev_tile);
-            unit(it, tile, grp + 2);
-            unit(it, tile, grp + 4);
+            if (it < n_my) {
+                prefetch_res(tile);
+                unit(it, tile, grp + 2);
+                unit(it, tile, grp + 4);
+            }
             prev_tile = tile;
         }
-        if (n_my > 0) final_stage(n_my - 1, prev_tile);
     }
     tc_fence_before();
     __syncthreads();
