@@ -21,6 +21,14 @@
 
 namespace srk {
 
+#ifdef SRK_MLP_TRACE
+// experiment builds only (scripts/micro/trace_mlp.py): per-role clock64 stamps of CTA 0
+__device__ long long g_ml_trace[4 * 64 * 8];
+#define ML_TR(role, idx, ev) do { if (blockIdx.x == 0 && lane == 0 && (idx) < 64) g_ml_trace[((role) * 64 + (idx)) * 8 + (ev)] = clock64(); } while (0)
+#else
+#define ML_TR(role, idx, ev) do { } while (0)
+#endif
+
 constexpr int ML_CH = 64;                  // hidden columns per chunk
 constexpr int ML_G_WARPS = 8;              // GELU warps
 #ifndef SRK_ML_F_WARPS
@@ -143,18 +151,34 @@ mlp_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 tma_load_2d(sW + ws * Cfg::WSLOT, &map_w2, w_full(ws), c * ML_CH, 0);
                 w_next();
             };
-            for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++tc) {
-                mbar_wait(a_empty, (tc & 1) ^ 1);
+            // The CTA's chunks form ONE sequence q = tile_iteration * NC + c that runs across tile boundaries: the
+            // weights arrive in the MMA warp's issue order  W1(0) W1(1) | W1(q+2) W2(q) ...,  and the A tile of the next
+            // tile iteration is requested right in front of its first W1 (its bytes were prefetched into L2 a tile earlier).
+            const int n_my = (int)blockIdx.x < p.m_tiles ? (p.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+            const int Q = n_my * NC;
+            auto load_a = [&](int ti) {
+                const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+                mbar_wait(a_empty, (ti & 1) ^ 1);
                 mbar_expect_tx(a_full, Cfg::A_BYTES);
 #pragma unroll
                 for (int kb = 0; kb < KB1; ++kb) tma_load_2d(sA + kb * 16384, &map_a, a_full, kb * 64, tile * 128);
-                load_w1(0);
-                if (NC > 1) load_w1(1);
-                for (int c = 0; c < NC; ++c) {
-                    if (c + 2 < NC) load_w1(c + 2);
-                    load_w2(c);
+                if (ti + 1 < n_my) {
+#pragma unroll
+                    for (int kb = 0; kb < KB1; ++kb) tma_prefetch_2d(&map_a, kb * 64, (tile + (int)gridDim.x) * 128);
                 }
+            };
+            auto load_fc1 = [&](int q) {
+                const int c = q % NC;
+                if (c == 0) load_a(q / NC);
+                load_w1(c);
+            };
+            if (Q > 0) load_fc1(0);
+            if (Q > 1) load_fc1(1);
+            for (int q = 0; q < Q; ++q) {
+                if (q + 2 < Q) load_fc1(q + 2);
+                load_w2(q % NC);
             }
+            (void)tc;
         }
     } else if (warp == 1) {
         // ===================================== MMA issuer =====================================
@@ -179,31 +203,42 @@ mlp_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 tc_commit(d1_full(d1s));
                 if (++d1s == 2) { d1s = 0; d1ph ^= 1; }
             };
-            for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++tc) {
-                const uint32_t d2 = tD2 + (uint32_t)((tc & 1) * CP);
-                int issued = 0;
-                mbar_wait(a_full, tc & 1);
+            const int n_my = (int)blockIdx.x < p.m_tiles ? (p.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+            const int Q = n_my * NC;
+            // fc1 of chunk q (tile iteration q / NC): the first chunk of a tile waits for its A tile, the last one hands
+            // the A buffer back to the producer
+            auto fc1_q = [&](int q) {
+                const int c = q % NC, ti = q / NC;
+                if (c == 0) { mbar_wait(a_full, ti & 1); tc_fence_after(); }
+                fc1();
+                if (c == NC - 1) tc_commit(a_empty);
+            };
+            if (Q > 0) fc1_q(0);
+            if (Q > 1) fc1_q(1);
+            for (int q = 0; q < Q; ++q) {
+                ML_TR(0, q, 0);
+                if (q + 2 < Q) fc1_q(q + 2);                      // two chunks ahead, also across the tile boundary
+                ML_TR(0, q, 1);
+                const int c = q % NC, ti = q / NC;
+                const uint32_t d2 = tD2 + (uint32_t)((ti & 1) * CP);
+                // fc2(q)
+                mbar_wait(h_full(hs), hph);
+                if (c == 0) mbar_wait(d2_empty(ti & 1), ((ti >> 1) & 1) ^ 1);
+                ML_TR(0, q, 2);
+                mbar_wait(w_full(ws), wph);
                 tc_fence_after();
-                fc1(); if (++issued == NC) tc_commit(a_empty);
-                if (NC > 1) { fc1(); if (++issued == NC) tc_commit(a_empty); }
-                for (int c = 0; c < NC; ++c) {
-                    if (c + 2 < NC) { fc1(); if (++issued == NC) tc_commit(a_empty); }   // A may be refilled once the last fc1 retires
-                    // fc2(c)
-                    mbar_wait(h_full(hs), hph);
-                    if (c == 0) mbar_wait(d2_empty(tc & 1), ((tc >> 1) & 1) ^ 1);
-                    mbar_wait(w_full(ws), wph);
-                    tc_fence_after();
-                    const uint64_t da = umma_desc_sw128(sH + hs * 16384), db = umma_desc_sw128(sW + ws * Cfg::WSLOT);
+                ML_TR(0, q, 3);
+                const uint64_t da = umma_desc_sw128(sH + hs * 16384), db = umma_desc_sw128(sW + ws * Cfg::WSLOT);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        tc_mma_f16(d2, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2, (c | k) != 0 ? 1u : 0u);
-                    tc_commit(w_empty(ws));
-                    w_next();
-                    tc_commit(h_empty(hs));
-                    if (++hs == ML_NH) { hs = 0; hph ^= 1; }
-                }
-                tc_commit(d2_full(tc & 1));
+                for (int k = 0; k < 4; ++k)
+                    tc_mma_f16(d2, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2, (c | k) != 0 ? 1u : 0u);
+                tc_commit(w_empty(ws));
+                w_next();
+                tc_commit(h_empty(hs));
+                if (++hs == ML_NH) { hs = 0; hph ^= 1; }
+                if (c == NC - 1) tc_commit(d2_full(ti & 1));
             }
+            (void)tc;
         }
     }
     } else if (warp < 4 + ML_G_WARPS) {
@@ -240,8 +275,10 @@ mlp_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         };
         for (int q = set, k = 0; q < n_chunks; q += 2, ++k) {
             const int c = q % NC, hs = q % ML_NH, hu = q / ML_NH;
+            if (lg == 0) ML_TR(1, q, 0);
             mbar_wait(d1_full(set), k & 1);
             tc_fence_after();
+            if (lg == 0) ML_TR(1, q, 1);
             uint32_t va[16], vb[16];
             tc_ld16_nowait(t_row, va);
             tc_wait_ld16(va);
@@ -260,10 +297,12 @@ mlp_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(d1_empty(set));               // D1 stage may be overwritten
+            if (lg == 0) ML_TR(1, q, 2);
             convert(vb, bias + 48, hrow, 3);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
             __syncwarp();
             if (lane == 0) mbar_arrive(h_full(hs));
+            if (lg == 0) ML_TR(1, q, 3);
         }
     } else {
         // ===================================== final warps =====================================
@@ -390,8 +429,10 @@ mlp_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         int tc = 0, pos = 0;
         for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++tc) {
             const uint32_t d2 = tD2 + (uint32_t)((tc & 1) * CP);
+            if (fw == 0) ML_TR(2, tc, 0);
             mbar_wait(d2_full(tc & 1), (tc >> 1) & 1);
             tc_fence_after();
+            if (fw == 0) ML_TR(2, tc, 1);
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
                 // ---- phase T: this half's two lane groups drain D2 into the staging tile (thread = row) ----
@@ -482,6 +523,12 @@ static int launch_mlp(const srk_mlp_args* a, cudaStream_t st) {
 }  // namespace srk
 
 using namespace srk;
+
+#ifdef SRK_MLP_TRACE
+extern "C" int srk_debug_mlp_trace(long long* out) {
+    return cudaMemcpyFromSymbol(out, g_ml_trace, sizeof(long long) * 4 * 64 * 8) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 extern "C" int srk_mlp(const srk_mlp_args* a, void* stream) {
     SRK_REQUIRE(a && a->A && a->W1 && a->W2 && a->b1 && a->b2 && a->res && a->out32, "mlp: null pointer");
