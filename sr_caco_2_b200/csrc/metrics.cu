@@ -144,9 +144,10 @@ metrics_tile_kernel(const MetParams p) {
             const size_t off = (size_t)(r + p.border) * p.Wpx + (c + p.border);
             e = __ldg(Eb + off);
             h = __ldg(Hb + off);
+            if (!isfinite(e) || !isfinite(h)) bad |= 2;        // before the clamp of quant255() hides a NaN
             if (p.quantize) { e = quant255(e); h = quant255(h); }
             if (EXT_ROI) w = __ldg(Rb + off);
-            if (!(e >= 0.f && e <= 255.f) || !(h >= 0.f && h <= 255.f)) bad = 1;
+            if (!(e >= 0.f && e <= 255.f) || !(h >= 0.f && h <= 255.f)) bad |= 1;
             if (lr < MT && lc < MT) {           // owned pixel
                 const double d = (double)e - (double)h;
                 const double dy = (double)luma255(e) - (double)luma255(h);
@@ -242,8 +243,8 @@ metrics_tile_kernel(const MetParams p) {
     }
     int k2 = block_reduce_min(mn_all, red_i, false);
     if (threadIdx.x == 0) atomicMin(&p.img[b].mn_all_key, k2);
-    int k3 = block_reduce_min(bad, red_i, true);
-    if (threadIdx.x == 0 && k3) atomicOr(&p.img[b].range_bad, 1);
+    const int any_range = __syncthreads_or(bad & 1), any_nonfinite = __syncthreads_or(bad & 2);
+    if (threadIdx.x == 0 && (any_range || any_nonfinite)) atomicOr(&p.img[b].range_bad, (any_range ? 1 : 0) | (any_nonfinite ? 2 : 0));
 }
 
 __global__ void metrics_init_kernel(MetAcc* acc, MetImg* img, int B, int NV) {
@@ -288,7 +289,8 @@ __global__ void metrics_finalize_kernel(const MetAcc* acc, const MetImg* img, in
         if (!isfinite(vals[k])) f |= 1;
         if (vals[k] < 0.0) f |= 2;
     }
-    if (img[b].range_bad) f |= 4;
+    if (img[b].range_bad & 1) f |= 4;
+    if (img[b].range_bad & 2) f |= 1;                      // non-finite input pixel
     if (f) atomicOr(&flags[b], f);
 }
 
@@ -327,6 +329,7 @@ struct FastParams {
     int B, Hpx, Wpx, border, n_ths;
     float ths[SRK_MAX_ROI_THS];
     BucketAcc* acc;
+    int32_t* flags;               // bit 0 is also raised for a non-finite INPUT pixel (the reference's NaN / Inf then reaches its metrics)
 };
 
 __global__ void __launch_bounds__(NTHREADS, 3)
@@ -373,6 +376,13 @@ metrics_fast_kernel(const FastParams p) {
             ev[u] = __ldg(Eb + off);
             hv[u] = H8b ? (float)__ldg(H8b + off) : __ldg(Hb + off);
         }
+    }
+    {   // tensor2uint82float (utils_image.py:369-372) propagates NaN into every metric; the clamp in quant255() would
+        // hide it (fminf / fmaxf return the non-NaN operand), so the raw loads are tested here
+        bool nonfinite = false;
+#pragma unroll
+        for (int u = 0; u < NPIX; ++u) nonfinite = nonfinite || !isfinite(ev[u]) || !isfinite(hv[u]);
+        if (__any_sync(0xffffffffu, nonfinite) && lane == 0) atomicOr(&p.flags[b], 1);
     }
 #pragma unroll
     for (int u = 0; u < NPIX; ++u) {
@@ -616,6 +626,7 @@ static int run_metrics(const float* E, const float* H, const float* roi, int B, 
         fp.E = E; fp.H = H; fp.H8 = H8; fp.B = B; fp.Hpx = Hpx; fp.Wpx = Wpx; fp.border = border; fp.n_ths = n_ths;
         for (int i = 0; i < n_ths; ++i) fp.ths[i] = (float)roi_ths[i];
         fp.acc = reinterpret_cast<BucketAcc*>(scratch);
+        fp.flags = flags;
         ProfScope ps(SRK_PROF_METRICS, st);
         SRK_CUDA(cudaMemsetAsync(flags, 0, sizeof(int32_t) * B, st));
         metrics_fast_init_kernel<<<ceil_div((long long)B * MAXV, 128), 128, 0, st>>>(fp.acc, B * MAXV);

@@ -117,8 +117,11 @@ class EDSR(nn.Module):
             raise ValueError(f"expected (B,{self.in_chans},h,w), got {tuple(x.shape)}")
         x = x.float().contiguous()
         B, _, h, w = x.shape
-        if self._plan is None:
+        ps = list(self.parameters())
+        fp = (ps[0].data_ptr(), sum(p._version for p in ps), len(ps))
+        if self._plan is None or fp != getattr(self, "_plan_fp", None):   # in-place parameter updates bump ._version
             self._build_plan()
+            self._plan_fp = fp
         self._plan.options = int(self.options)
         with torch.cuda.device(x.device):
             need = lib.srk_edsr_workspace_bytes(C.byref(self._plan), B, h, w)

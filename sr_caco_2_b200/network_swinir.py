@@ -175,6 +175,7 @@ class SwinIR(nn.Module):
                 nn.init.constant_(m.bias, 0)
                 nn.init.constant_(m.weight, 1.0)
         self._plan = None
+        self._plan_fp = None
         self._keep = None
         self._ws = None
         self.options = 0             # srk.h SRK_OPT_* bits (tests switch single fusions off); 0 = product path
@@ -196,6 +197,12 @@ class SwinIR(nn.Module):
     def _apply(self, fn, *a, **k):
         self._invalidate()
         return super()._apply(fn, *a, **k)
+
+    def _fingerprint(self):
+        """Cheap identity of the parameter values the packed plan was built from: storage address of the first
+        parameter + the sum of all tensor version counters (every in-place write increments one)."""
+        ps = list(self.parameters())
+        return (ps[0].data_ptr(), sum(p._version for p in ps), len(ps))
 
     def flush(self):  # called by the reference's ModelPlain (model_plain.py:55) when present
         self._invalidate()
@@ -340,8 +347,10 @@ class SwinIR(nn.Module):
             raise L.SrkError("input and parameters are on different devices")
         x = x.float().contiguous()
         B, _, h, w = x.shape
-        if self._plan is None:
+        fp = self._fingerprint()
+        if self._plan is None or fp != self._plan_fp:        # in-place parameter updates (EMA, optimizer steps) bump ._version
             self._build_plan()
+            self._plan_fp = fp
         self._plan.options = int(self.options)
         with torch.cuda.device(x.device):
             need = lib.srk_swinir_workspace_bytes(C.byref(self._plan), B, h, w)

@@ -139,7 +139,8 @@ def fold_tail(up_convs, last_w: torch.Tensor, last_b: torch.Tensor, scale: int):
     X = torch.zeros(G * G * F + 1, F, G, G, dtype=torch.float64, device=dev)
     idx = torch.arange(G * G * F, device=dev)
     X[idx, idx % F, (idx // F) // G, (idx // F) % G] = 1.0
-    out = tail(X)[:, 0]                                            # (1601, 5s, 5s)
+    # (in chunks: at X8 the fp64 intermediates of all 1601 impulse images at once would take several GB)
+    out = torch.cat([tail(X[i:i + 128])[:, 0] for i in range(0, X.shape[0], 128)], 0)   # (1601, 5s, 5s)
     W = torch.zeros(9, 64, 25 * F, dtype=torch.float64, device=dev)
     Bv = torch.zeros(9, 64, dtype=torch.float64, device=dev)
     for vy in range(3):

@@ -51,7 +51,8 @@ def _run(a, b, border, roi, quantize, ths: Sequence[int] = ()):
     a = a.float().contiguous()
     # uint8 target = the levels the loader holds: no float copy, the kernel reads the bytes
     b_u8 = b.dtype == torch.uint8 and quantize and roi is None and list(ths) == sorted(set(int(t) for t in ths))
-    b = b.contiguous() if b_u8 else (b.float().div(255.0) if b.dtype == torch.uint8 else b.float()).contiguous()
+    # (a uint8 tensor is levels in [0,255]: scaled to [0,1] only for the quantising path, which maps it back)
+    b = b.contiguous() if b_u8 else (b.float().div(255.0) if (b.dtype == torch.uint8 and quantize) else b.float()).contiguous()
     B, _, Hh, Ww = a.shape
     if Hh - 2 * border < 11 or Ww - 2 * border < 11:
         raise ValueError("Kernel size can't be greater than actual input size. "
@@ -113,7 +114,7 @@ def compute_metrics(E: torch.Tensor, H: torch.Tensor, border: int,
     if len(roi_ths) > L.MAX_ROI_THS:
         raise ValueError(f"at most {L.MAX_ROI_THS} ROI thresholds")
     out, flags = _run(E, H, border, None, True, roi_ths)
-    if check:
+    if check:                                     # (check=False: the caller accumulates res['flags'] and tests them once)
         f = int(flags.max().item()) if flags.numel() else 0
         if f & 1:
             raise FloatingPointError("non-finite metric value (inf/nan)")
@@ -126,4 +127,5 @@ def compute_metrics(E: torch.Tensor, H: torch.Tensor, border: int,
         res.update({"roi_" + n: m[:, i] for i, n in enumerate(names)})
         res["per_threshold"] = out[:, 1:, :]
     res["raw"] = out
+    res["flags"] = flags                          # (B,) int32: bit 0 non-finite (metric or input pixel), bit 1 negative metric
     return res

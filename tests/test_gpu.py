@@ -752,3 +752,161 @@ def test_evaluator_end_to_end_matches_oracle(L):
     assert abs(res["ssim"] - float(om["ssim"].double().mean())) < 1e-4
     assert abs(res["roi_psnr"] - float(orm["psnr"].mean())) < 0.01
     assert abs(res["roi_ssim"] - float(orm["ssim"].double().mean())) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------
+# round 2: the geometries / batch sizes the headline numbers are quoted on
+# ------------------------------------------------------------------------------------------
+def _r2_gold():
+    return json.load(open(os.path.join(T.GOLDEN, "fullsize_r2.json")))
+
+
+@pytest.mark.parametrize("name", ["cfg5_classical_x2_128", "cfg5_classical_x2_136", "cfg4_classical_x4_64"])
+def test_baseline_cfg4_cfg5_against_reference_samples(L, name):
+    """BASELINE configs[3] at 64x64 and configs[4] at 128x128 and at 136x136 (eval.py's padded geometry: 17 x 17
+    windows, odd window counts): 2048 strided samples of the unmodified reference's output
+    (tests/golden/make_golden_r2.py), 2e-3 max-abs.  Product path: fused attention block + fused MLP kernels."""
+    L.set_engine("tcgen05")
+    cfg, shape, seed = {"cfg5_classical_x2_128": (T.cfg_classical(2), (1, 128, 128), 105),
+                        "cfg5_classical_x2_136": (T.cfg_classical(2), (1, 136, 136), 105),
+                        "cfg4_classical_x4_64": (T.cfg_classical(4), (1, 64, 64), 104)}[name]
+    net = make_swinir(cfg, T.swinir_state_dict(cfg, seed=seed))
+    y = net(T.synthetic_lr(*shape, seed).to(DEV)).cpu()
+    gd = _r2_gold()[name]
+    assert list(y.shape) == gd["shape"]
+    got = y.reshape(-1)[torch.tensor(gd["idx"])].double().numpy()
+    assert np.abs(got - np.array(gd["val"])).max() < 2e-3
+    assert abs(float(y.double().sum()) - gd["sum"]) < 2e-3 * y.numel() * 0.05
+
+
+def test_img_size_8_disables_the_shift(L):
+    """img_size == window_size: the reference constructor sets shift_size = 0 for every block
+    (network_swinir.py:232-236); golden from the unmodified reference on a 16 x 24 input."""
+    for engine in ENGINES:
+        L.set_engine(engine)
+        cfg = T.cfg_imgsize8()
+        net = make_swinir(cfg, T.swinir_state_dict(cfg, seed=106))
+        assert all(s == 0 for _, s in net._block_geometry)
+        y = net(T.synthetic_lr(2, 16, 24, 106).to(DEV)).cpu()
+        gd = _r2_gold()["swinir_imgsize8"]
+        assert list(y.shape) == gd["shape"]
+        got = y.reshape(-1)[torch.tensor(gd["idx"])].double().numpy()
+        assert np.abs(got - np.array(gd["val"])).max() < 2e-3
+
+
+def test_large_magnitude_activations_stress(L):
+    """conv_first scaled by 2048: every fp16 conv operand (residual stream, conv_after_body's sum with the shallow
+    features, the upsampler features) is three orders of magnitude larger than with random-init-like weights, the
+    range a trained checkpoint could reach (none is available offline), still below the fp16 maximum the conv
+    operands saturate at.  Tolerance relative to the output magnitude (|y| up to ~200)."""
+    L.set_engine("tcgen05")
+    cfg = T.cfg_stress()
+    sd = T.stress_state_dict(T.swinir_state_dict(cfg, seed=107))
+    net = make_swinir(cfg, sd)
+    y = net(T.synthetic_lr(2, 24, 32, 107).to(DEV)).cpu()
+    gd = _r2_gold()["swinir_stress_large_weights"]
+    assert list(y.shape) == gd["shape"] and bool(torch.isfinite(y).all())
+    got = y.reshape(-1)[torch.tensor(gd["idx"])].double().numpy()
+    assert np.abs(got - np.array(gd["val"])).max() < 2e-3 * gd["absmax"]
+
+
+def test_cfg3_batch32_patches_and_scores_against_reference(L):
+    """The headline configuration AT its batch size: cfg3 (classical X8, 64 -> 512) on the seeded batch of 32; the
+    full 512 x 512 output of patches 0, 13 and 31 against the unmodified reference (2e-3), and PSNR / SSIM / NRMSE
+    of those patches against the reference's own metric functions on the reference's output (0.01 dB / 1e-4)."""
+    from sr_caco_2_b200 import utils_image as UI
+    L.set_engine("tcgen05")
+    z = np.load(os.path.join(T.GOLDEN, "cfg3_b32_patches.npz"))
+    cfg = T.cfg_classical(8)
+    net = make_swinir(cfg, T.swinir_state_dict(cfg, seed=103))
+    x = T.synthetic_lr(32, 64, 64, 203)
+    hr = T.synthetic_hr(32, 512, 512, 204)
+    y = net(x.to(DEV))
+    m = UI.compute_metrics(y, hr.to(DEV), 8, (4, 7, 10))
+    for i in [int(v) for v in z["patches"]]:
+        ref = torch.from_numpy(z[f"y{i}"])
+        assert float((y[i, 0].cpu() - ref).abs().max()) < 2e-3, i
+        assert abs(float(m["psnr"][i]) - float(z[f"psnr{i}"][0])) < 0.01, i
+        assert abs(float(m["ssim"][i]) - float(z[f"ssim{i}"][0])) < 1e-4, i
+        assert abs(float(m["nrmse"][i]) - float(z[f"nrmse{i}"][0])) < 1e-4 * max(1.0, float(z[f"nrmse{i}"][0])), i
+    # the batch is processed as independent patches: a patch alone gives the same pixels
+    y13 = net(x[13:14].to(DEV))
+    assert float((y13[0] - y[13]).abs().max()) < 1e-5
+
+
+def test_fused_block_kernels_equal_unfused_network(L):
+    """Whole network with the fused attention block / fused MLP kernels switched off one at a time (plan options):
+    same output to the fp32 rounding of the reordered residual adds and a bf16 ulp of the LayerNorm rows."""
+    L.set_engine("tcgen05")
+    cfg = O.SwinIRCfg(upscale=4, img_size=16, embed_dim=180, depths=[3, 2], num_heads=[6, 6], mlp_ratio=2.0,
+                      upsampler="pixelshuffle")
+    net = make_swinir(cfg, T.swinir_state_dict(cfg, 9))
+    x = T.synthetic_lr(3, 24, 40, 4).to(DEV)
+    y = net(x).clone()
+    for opt in (L.OPT_NO_FUSED_BLOCK, L.OPT_NO_FUSED_MLP, L.OPT_NO_FUSED_BLOCK | L.OPT_NO_FUSED_MLP,
+                L.OPT_NO_FUSED_ATTN, L.OPT_NO_FOLD_QKV_BIAS):
+        net.options = opt
+        y2 = net(x)
+        assert float((y2 - y).abs().max()) < 1e-3, opt
+    net.options = 0
+
+
+def test_nan_and_inf_in_the_sr_output_are_reported(L):
+    """the clamp of the uint8 quantisation hides NaN / Inf pixels; the reference propagates them into every
+    metric and aborts (check_negative_non_float, utils_trainer.py:933-958).  flags bit 0 must be raised by a
+    non-finite INPUT pixel, compute_metrics(check=True) and the evaluator sweep must raise."""
+    from sr_caco_2_b200 import utils_image as UI
+    from sr_caco_2_b200 import evaluator as EV
+    E, Hr = T.synthetic_pair(3, 64, 72, 5)
+    for bad in (float("nan"), float("inf"), float("-inf")):
+        Eb = E.clone(); Eb[1, 0, 20, 31] = bad
+        m = UI.compute_metrics(Eb.to(DEV), Hr.to(DEV), 4, (4, 7), check=False)
+        f = m["flags"].cpu()
+        assert int(f[1]) & 1 and not (int(f[0]) & 1) and not (int(f[2]) & 1), (bad, f)
+        with pytest.raises(FloatingPointError):
+            UI.compute_metrics(Eb.to(DEV), (Hr * 255).round().to(torch.uint8).to(DEV), 4, (4, 7), check=True)
+        out, fl = UI._run(Eb.to(DEV) * 255, Hr.to(DEV) * 255, 4, None, False)      # generic (non-quantising) path
+        assert int(fl[1].cpu()) & 1
+    clean = UI.compute_metrics(E.to(DEV), Hr.to(DEV), 4, (4, 7), check=True)
+    assert int(clean["flags"].max().cpu()) == 0
+
+    class Net(torch.nn.Module):
+        window_size = 8
+        def __init__(self):
+            super().__init__(); self.p = torch.nn.Parameter(torch.zeros(1, device=DEV))
+        def forward(self, x):
+            y = torch.nn.functional.interpolate(x, scale_factor=2, mode="nearest")
+            y[0, 0, 3, 3] = float("nan")
+            return y
+    step = EV.make_cuda_step(Net(), 2, swinir_padding=False)
+    lr = T.synthetic_lr(4, 32, 32, 1); hr = T.synthetic_hr(4, 64, 64, 2)
+    with pytest.raises(FloatingPointError):
+        EV.evaluate_patches(step, lr, hr, 2, device=torch.device(DEV))
+
+
+def test_metric_shims_keep_uint8_levels_unscaled(L):
+    """the mbatch_gpu_calculate_* shims take inputs in [0,255]; a uint8 target is levels, not [0,1]."""
+    from sr_caco_2_b200 import utils_image as UI
+    E, Hr = T.synthetic_pair(2, 48, 48, 9)
+    e255 = (E.clamp(0, 1) * 255).round()
+    h255 = (Hr * 255).round()
+    a = UI.mbatch_gpu_calculate_psnr(e255.to(DEV), h255.to(DEV), border=2)
+    b = UI.mbatch_gpu_calculate_psnr(e255.to(DEV), h255.to(torch.uint8).to(DEV), border=2)
+    assert torch.allclose(a, b, rtol=0, atol=1e-9)
+
+
+def test_plan_follows_in_place_parameter_updates(L):
+    """the packed-weight plan is rebuilt after an in-place parameter change (EMA update, optimizer step)."""
+    L.set_engine("tcgen05")
+    cfg = O.SwinIRCfg(upscale=2, img_size=16, embed_dim=60, depths=[2], num_heads=[6], mlp_ratio=2.0,
+                      upsampler="pixelshuffledirect")
+    sd = T.swinir_state_dict(cfg, 3)
+    net = make_swinir(cfg, sd)
+    x = T.synthetic_lr(1, 16, 16, 2).to(DEV)
+    y0 = net(x).clone()
+    with torch.no_grad():
+        net.conv_first.weight.mul_(1.5)
+    y1 = net(x)
+    sd2 = dict(sd); sd2["conv_first.weight"] = sd["conv_first.weight"] * 1.5
+    ref = O.swinir_forward(sd2, cfg, x.cpu())
+    assert float((y1.cpu() - ref).abs().max()) < 2e-3 and float((y1 - y0).abs().max()) > 1e-3
