@@ -43,12 +43,12 @@ def test_ctypes_struct_layouts_match_header_sizes(lib, tmp_path):
     src = tmp_path / "sz.c"
     src.write_text('#include "srk.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu\\n",'
                    'sizeof(srk_gemm_args),sizeof(srk_conv_params),sizeof(srk_stb_params),'
-                   'sizeof(srk_swinir_plan),sizeof(srk_edsr_plan));printf("%zu %zu\\n",sizeof(srk_mlp_args),sizeof(srk_tail_fold));return 0;}\n')
+                   'sizeof(srk_swinir_plan),sizeof(srk_edsr_plan));printf("%zu %zu %zu\\n",sizeof(srk_mlp_args),sizeof(srk_tail_fold),sizeof(srk_attn_block_args));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     sizes = list(map(int, subprocess.check_output([str(exe)]).split()))
     from sr_caco_2_b200 import _lib as L
-    got = [ctypes.sizeof(c) for c in (L.GemmArgs, L.ConvParams, L.StbParams, L.SwinIRPlan, L.EDSRPlan, L.MlpArgs, L.TailFold)]
+    got = [ctypes.sizeof(c) for c in (L.GemmArgs, L.ConvParams, L.StbParams, L.SwinIRPlan, L.EDSRPlan, L.MlpArgs, L.TailFold, L.AttnBlockArgs)]
     assert got == sizes
 
 
@@ -197,7 +197,8 @@ def _gloo_worker(rank, world, port, q):
         a, b = O.all_metrics(e, h, 2), O.roi_marginal_metrics(e, h, 2)
         return torch.stack([a[k].double() for k in ("psnr", "mse", "nrmse", "ssim", "psnr_y")] +
                            [b[k].double() for k in ("psnr", "mse", "nrmse", "ssim", "psnr_y")], 1)
-    res = evaluate_patches(step, E, H, batch_size=2, rank=rank, world=world, device=torch.device("cpu"))
+    ids = [f"cell/{i:03d}.tif" for i in range(7)]
+    res = evaluate_patches(step, E, H, batch_size=2, rank=rank, world=world, device=torch.device("cpu"), ids=ids)
     q.put((rank, res))
     dist.destroy_process_group()
 
@@ -218,6 +219,32 @@ def test_two_rank_gloo_metric_exchange_equals_single_process():
         for k in ("psnr", "mse", "nrmse", "ssim", "psnr_y"):
             assert abs(results[r][k] - float(a[k].double().mean())) < 1e-9 * max(1, abs(results[r][k]))
             assert abs(results[r]["roi_" + k] - float(b[k].double().mean())) < 1e-9 * max(1, abs(results[r][k]))
+        # per-image details: ragged shards (4 + 3 images) gathered with ONE all_gather, every rank holds all 7 images in order
+        det, roi = results[r]["details"], results[r]["roi_details"]
+        assert list(det.keys()) == [f"cell/{i:03d}.tif" for i in range(7)]
+        for i, im_id in enumerate(det):
+            for k in ("psnr", "mse", "nrmse", "ssim", "psnr_y"):
+                assert abs(det[im_id][k] - float(a[k][i])) < 1e-9 * max(1, abs(det[im_id][k]))
+                assert abs(roi[im_id][k] - float(b[k][i])) < 1e-9 * max(1, abs(roi[im_id][k]))
+
+
+def test_details_and_summary_files_have_the_reference_shape(tmp_path):
+    """details_<ds>.yml / roi_details_<ds>.yml (utils_trainer.py:1140-1147) and the write_current_perf_eval summary
+    (utils_tracker.py:133-165): same file names and keys."""
+    import yaml
+    from sr_caco_2_b200 import evaluator as EV
+    block = torch.arange(30, dtype=torch.float64).view(3, 10)
+    det, roi = EV.details_dicts(block, ["a", "b", "c"])
+    EV.write_details(det, roi, str(tmp_path), "caco2")
+    d = yaml.safe_load(open(tmp_path / "details_caco2.yml"))
+    r = yaml.safe_load(open(tmp_path / "roi_details_caco2.yml"))
+    assert d["b"] == {"psnr": 10.0, "mse": 11.0, "nrmse": 12.0, "ssim": 13.0, "psnr_y": 14.0}
+    assert r["c"]["psnr"] == 25.0
+    means = {m: 1.0 + i for i, m in enumerate(EV.METRICS)}
+    means.update({"roi_" + m: 2.0 + i for i, m in enumerate(EV.METRICS)})
+    out = EV.write_current_perf_eval(means, "test", "caco2", str(tmp_path), "perf.yml", current_step=7)
+    y = yaml.safe_load(open(tmp_path / "perf.yml"))
+    assert y == out and y["last_ssim"] == 4.0 and y["best_psnr"] == 1.0 and y["dataset"] == "caco2" and y["split"] == "test"
 
 
 def test_fold_tail_equals_layer_chain_on_cpu():

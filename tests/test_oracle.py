@@ -199,3 +199,19 @@ def test_bicubic_baseline_oracle_matches_reference_golden():
         assert got.shape == z[f"y{s}"].shape
         assert float(np.abs(got - z[f"y{s}"]).max()) < 1e-6
         assert got.min() >= 0.0 and got.max() <= 1.0
+
+
+def test_oracle_matches_round2_reference_goldens():
+    """The oracle restatement against the round-2 fixtures of the unmodified reference that are small enough for the
+    CPU suite: img_size == window_size (shift disabled at construction) and the large-magnitude stress network."""
+    gold = json.load(open(os.path.join(T.GOLDEN, "fullsize_r2.json")))
+    for name, cfg, shape, seed, gain in [("swinir_imgsize8", T.cfg_imgsize8(), (2, 16, 24), 106, 1.0),
+                                         ("swinir_stress_large_weights", T.cfg_stress(), (2, 24, 32), 107, T.STRESS_GAIN)]:
+        sd = T.swinir_state_dict(cfg, seed=seed)
+        if gain != 1.0:
+            sd = T.stress_state_dict(sd, gain)
+        y = O.swinir_forward(sd, cfg, T.synthetic_lr(*shape, seed))
+        gd = gold[name]
+        assert list(y.shape) == gd["shape"]
+        got = y.reshape(-1)[torch.tensor(gd["idx"])].double().numpy()
+        assert np.abs(got - np.array(gd["val"])).max() <= 2e-6 * max(1.0, gd["absmax"]), name
