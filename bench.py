@@ -2,7 +2,12 @@
 """Benchmark of the SR-CACO-2 evaluation hot path on B200 (contract: see the task statement).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
-                    [--workload cfg3|cfg1|cfg2|cfg4|cfg5] [--engine tcgen05|mma_sync]
+                    [--workload cfg3|cfg1|cfg2|cfg4|cfg5] [--engine tcgen05|mma_sync] [--sweep N_PATCHES]
+
+--sweep N_PATCHES switches to the STRONG-scaling form of BASELINE.json configs[3]: a fixed list of N patches is
+sharded over the ranks (ragged shards, tail batches), every rank evaluates its shard, ONE all-reduce of the 11
+metric sums, and rank 0 re-evaluates the whole list alone (untimed) to assert that the sharded means equal the
+single-GPU means.
 
 A "step" is one pass of the hot path over one batch of synthetic patches: SwinIR forward
 (SwinIR-classical X8, 64x64 -> 512x512, batch 32 per GPU = BASELINE.json configs[2]) followed by
@@ -113,6 +118,70 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi / NVML unavailable"]}
 
 
+def host_cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.lower().startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def patch_pair(idx, h, w, scale, seed):
+    """Patch `idx` of a synthetic evaluation list: the same bytes whatever the rank count (uint8 levels as stored)."""
+    g = torch.Generator().manual_seed(seed * 100003 + idx)
+    lr = torch.randint(0, 256, (1, h, w), generator=g, dtype=torch.uint8)
+    hr = torch.randint(0, 256, (1, h * scale, w * scale), generator=g, dtype=torch.uint8)
+    return lr, hr
+
+
+def gpu_eager_run(kind, kw, sd_cpu, h, w, seed, batch, dev):
+    """SURVEY 8(d) "the bar to beat on the same box": the reference algorithm as plain PyTorch eager modules on this
+    GPU (the oracle port IS plain PyTorch: cuBLAS / cuDNN / ATen kernels), forward + the reference's metric formulas,
+    in fp32 without TF32, fp32 with TF32 allowed, and autocast(bf16).  CUDA-event timed, 1 warm-up + 2 steps."""
+    from oracle import sr_oracle as O
+    out = {}
+    if kind == "swinir":
+        cfg = O.SwinIRCfg(**{k: kw[k] for k in ("upscale", "in_chans", "img_size", "window_size", "img_range",
+                                                 "depths", "embed_dim", "num_heads", "mlp_ratio", "upsampler",
+                                                 "resi_connection")})
+        scale = cfg.upscale
+        fwd = lambda sd, x: O.swinir_forward(sd, cfg, x)
+    else:
+        cfg = O.EDSRCfg(**{k: kw[k] for k in ("in_chans", "n_resblocks", "n_feats", "scale", "rgb_range")})
+        scale = cfg.scale
+        fwd = lambda sd, x: O.edsr_forward(sd, cfg, x)
+    sd = {k: v.to(dev) for k, v in sd_cpu.items()}
+    x, hr = synthetic_batch(batch, h, w, scale, seed)
+    x, hr = x.to(dev), hr.to(dev)
+
+    def step():
+        y = fwd(sd, x)
+        m = O.all_metrics(y.float(), hr, scale)
+        r = O.roi_marginal_metrics(y.float(), hr, scale, ROI_THS)
+        return m["psnr"].sum() + r["psnr"].sum()
+    modes = (("fp32_no_tf32", False, None), ("fp32_tf32", True, None), ("autocast_bf16", True, torch.bfloat16))
+    prev = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    try:
+        for name, tf32, ac in modes:
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+            with torch.no_grad(), torch.autocast("cuda", dtype=ac, enabled=ac is not None):
+                step(); torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(2):
+                    step()
+                e1.record(); torch.cuda.synchronize()
+            out[name] = batch * 2 / (e0.elapsed_time(e1) * 1e-3)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev
+    return {"unit": "patches/s", "batch": batch, "steps": 2, "warmup": 1, "values": out,
+            "what": "oracle/sr_oracle.py (plain PyTorch restatement of the reference modules and metric formulas) "
+                    "run eagerly on this GPU"}
+
+
 def cpu_reference_run(kind, kw, sd, h, w, seed, steps, warmup, sample_b):
     """The reference's CPU path for this workload: oracle port (oracle/sr_oracle.py) forward +
     metrics on the host cores.  Used ONLY as the measured baseline."""
@@ -145,6 +214,78 @@ def cpu_reference_run(kind, kw, sd, h, w, seed, steps, warmup, sample_b):
     return sample_b * steps / dt, dt / steps, torch.get_num_threads()
 
 
+def run_sweep(args, kind, kw, desc, net, B, h, w, scale, seed, swin_pad, rank, world, dev, metric, unit, W):
+    """Strong scaling (BASELINE.json configs[3]: the 1471-patch test sweep): a fixed patch list, exact ragged shards
+    (evaluator.shard_range), tail batches, one all-reduce of the 11 metric sums.  Inputs are device resident (uint8
+    levels) when the timed region starts."""
+    import torch.distributed as dist
+    from sr_caco_2_b200 import evaluator as EV, _lib as L
+    n = args.sweep
+    lo, hi = EV.shard_range(n, rank, world)
+    own = range(n) if rank == 0 else range(lo, hi)              # rank 0 also holds the whole list for the untimed cross-check
+    pairs = {i: patch_pair(i, h, w, scale, seed) for i in own}
+    lr_all = torch.stack([pairs[i][0] for i in own]).to(dev)
+    hr_all = torch.stack([pairs[i][1] for i in own]).to(dev)
+    base = 0 if rank == 0 else lo
+    lr_sh, hr_sh = lr_all[lo - base:hi - base], hr_all[lo - base:hi - base]
+    step_fn = EV.make_cuda_step(net, scale, swin_pad, roi_ths=ROI_THS, check=False)
+
+    def sweep(lr, hr):
+        acc = torch.zeros(11, dtype=torch.float64, device=dev)
+        for s0 in range(0, lr.shape[0], B):
+            vals = step_fn(lr[s0:s0 + B], hr[s0:s0 + B])
+            acc[:10] += vals.sum(0)
+            acc[10] += vals.shape[0]
+        return acc
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(max(W, 3)):
+        step_fn(lr_sh[:B], hr_sh[:B])
+    barrier()
+    sampler = ClockSampler(dev.index)
+    if rank == 0:
+        sampler.start()
+    L.launch_count(reset=True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    K = max(args.steps, 1)
+    barrier()
+    ev0.record()
+    for _ in range(K):
+        acc = sweep(lr_sh, hr_sh)
+        if world > 1:
+            dist.all_reduce(acc)
+    ev1.record()
+    barrier()
+    launches = L.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    if rank != 0:
+        return
+    means = (acc[:10] / acc[10]).cpu()
+    single = sweep(lr_all, hr_all)                                 # untimed: the whole list on this GPU alone
+    means1 = (single[:10] / single[10]).cpu()
+    rel = float(((means - means1).abs() / means1.abs().clamp_min(1e-300)).max())
+    assert int(acc[10].item()) == n and rel < 1e-9, f"sharded means differ from the single-GPU means: {rel}"
+    shards = [EV.shard_range(n, r, world) for r in range(world)]
+    line = {"metric": metric, "value": n * K / (ms * 1e-3), "unit": unit, "n_gpus": world, "steps": K, "warmup": max(W, 3),
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16 linear/attention + fp16 conv operands, fp32 accumulate", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}", "sweep_patches": n, "per_gpu_batch": B,
+                       "shard_sizes": [b - a for a, b in shards], "tail_batch": [(b - a) % B for a, b in shards],
+                       "step": "one step = the whole sweep + its all-reduce", "geometry": args.geometry,
+                       "l2": "the sweep's inputs and activations (GBs) are far larger than the 126 MB L2"},
+            "clocks": clocks, "gpu_launches": launches,
+            "sharded_vs_single_gpu_means_max_rel_diff": rel,
+            "means": {k: float(means[i]) for i, k in enumerate(EV.METRICS)}}
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -157,6 +298,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--geometry", default="direct", choices=["direct", "evalpy"],
                     help="direct: net(x) on hxw; evalpy: caller-side +1 window padding (72x72)")
+    ap.add_argument("--sweep", type=int, default=0, help="strong scaling: evaluate a fixed list of this many patches")
+    ap.add_argument("--no-eager-baseline", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -177,15 +320,15 @@ def main():
         if rank != 0:
             return
         sample_b = 4 if kind == "swinir" else 8
-        steps = min(K, 3)
+        steps = min(max(K, 6), 8)
         torch.manual_seed(seed)
         sd = {k: v.detach().clone() for k, v in CF.build(kind, kw).state_dict().items()}
         v, spt, thr = cpu_reference_run(kind, kw, sd, h, w, seed, steps, 1, sample_b)
         line = {"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus,
                 "steps": steps, "warmup": 1, "ms_per_step": spt * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"{args.workload}: {desc}", "sample_batch": sample_b},
-                "cpu_baseline": {"value": v, "unit": unit, "cores": thr, "kind": "port",
+                "config": {"workload": f"{args.workload}: {desc}", "sample_batch": sample_b, "host_cpu": host_cpu_model()},
+                "cpu_baseline": {"value": v, "unit": unit, "cores": thr, "kind": "port", "host_cpu": host_cpu_model(),
                                  "sample": f"{steps} steps x batch {sample_b} of the same workload through "
                                            "oracle/sr_oracle.py (fp32 PyTorch CPU restatement of the reference; "
                                            "/root/reference is not present on the GPU box)"},
@@ -220,6 +363,12 @@ def main():
     sd_cpu = {k: v.detach().clone() for k, v in net.state_dict().items()}
     net = net.to(dev).eval()
     swin_pad = kind == "swinir" and args.geometry == "evalpy"
+
+    if args.sweep > 0:
+        run_sweep(args, kind, kw, desc, net, B, h, w, scale, seed, swin_pad, rank, world, dev, metric, unit, W)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # synthetic inputs: NB distinct batches, rotated, resident in HBM for `value`
     NB = 3
@@ -279,28 +428,36 @@ def main():
     value = world * B * K / (ms * 1e-3)
 
     # ---- e2e: host buffers in, host result out, every step ---------------------------------
+    # The plugin call a user makes: evaluator.make_cuda_step on HOST tensors.  The loader's images are uint8
+    # (SURVEY 8f-1): LR and HR travel as the stored uint8 levels, `uint2tensor` (/255) runs on the device and the
+    # metrics kernel reads the target bytes directly.  The fp32 shipping of round 1 is timed beside it.
     res_host = torch.empty(B, 10, dtype=torch.float64).pin_memory()
     step_fn = EV.make_cuda_step(net, scale, swin_pad, roi_ths=ROI_THS, check=False)
+    lr8_host = [(t * 255).round().to(torch.uint8).pin_memory() for t in lr_host]
+    hr8_host = [(t * 255).round().to(torch.uint8).pin_memory() for t in hr_host]
 
-    def e2e_step(i):
-        vals = step_fn(lr_host[i % NB], hr_host[i % NB])
-        res_host.copy_(vals, non_blocking=True)
-        torch.cuda.current_stream().synchronize()      # the caller reads the scores every step
-        return res_host[:, 0].sum().item()
+    def time_e2e(lrs, hrs):
+        def e2e_step(i):
+            vals = step_fn(lrs[i % NB], hrs[i % NB])
+            res_host.copy_(vals, non_blocking=True)
+            torch.cuda.current_stream().synchronize()      # the caller reads the scores every step
+            return res_host[:, 0].sum().item()
+        for i in range(2):
+            e2e_step(i)
+        barrier()
+        ev0.record()
+        for i in range(K):
+            e2e_step(i)
+        ev1.record()
+        barrier()
+        tt = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return world * B * K / (float(tt.item()) * 1e-3)
 
-    for i in range(2):
-        e2e_step(i)
-    barrier()
-    ev0.record()
-    for i in range(K):
-        e2e_step(i)
-    ev1.record()
-    barrier()
-    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * K / (float(t.item()) * 1e-3)
-    h2d = lr_host[0].numel() * 4 + hr_host[0].numel() * 4
+    e2e_value = time_e2e(lr8_host, hr8_host)
+    e2e_fp32 = time_e2e(lr_host, hr_host)
+    h2d = lr8_host[0].numel() + hr8_host[0].numel()
     d2h = res_host.numel() * 8
 
     if rank != 0:
@@ -308,85 +465,68 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (tensor-core GEMM family) ---------------------------
+    # ---- roofline -------------------------------------------------------------------------
+    # Headline: the tensor-core roofline of the WHOLE step (north_star / SURVEY 8d): FLOPs of one step / device time of
+    # one step against the measured cuBLAS bf16 peak -- the burst figure when the SM clock held its maximum through the
+    # timed region (median >= 1900 MHz), else the sustained one.  Both FLOP counts are given: the network as the
+    # reference executes it layer by layer, and what this implementation executes (folded reconstruction tail).
     peaks = read_peaks()
     hn, wn = (h, w)
     if swin_pad:
         hn, wn = (h // 8 + 1) * 8, (w // 8 + 1) * 8
     fl = CF.swinir_flops if kind == "swinir" else CF.edsr_flops
-    gflop_patch = fl(kw, hn, wn) / 1e9                       # the network as the reference executes it
-    folded = (args.engine == "tcgen05" and os.environ.get("SRK_FOLD_TAIL", "1") != "0"
-              and kw.get("upsampler", "pixelshuffle") == "pixelshuffle")
-    gflop_exec = fl(kw, hn, wn, folded_tail=folded) / 1e9    # what this implementation executes
-    peak = peaks["tensor_sustained"] or peaks["tensor_burst"]
-    step_tflops = value / world * gflop_exec / 1e3
-    roofline = {"bound": "tensor", "achieved": None, "peak": peak, "unit": "TFLOP/s", "frac": None,
-                "traffic": None, "peak_source": peaks["source"] + ", sustained bf16",
-                "scope": "per GPU (rank 0)", "whole_step_achieved": step_tflops, "whole_step_frac": step_tflops / peak,
-                "gflop_per_patch": gflop_exec, "reference_gflop_per_patch": gflop_patch,
-                "flops_note": "executed FLOPs; the linear reconstruction tail is folded into one 5x5 conv "
-                              "(srk_tail_fold), the reference's layer-by-layer count is reference_gflop_per_patch"
-                              if folded else "executed == reference layer-by-layer count"}
-    gemm_ms = prof_ms.get("gemm", 0.0) + prof_ms.get("gemm_res_ln", 0.0)
-    gemm_calls = prof_calls.get("gemm", 0) + prof_calls.get("gemm_res_ln", 0)
-    family = None
-    if gemm_ms > 0:
-        fused_attn = kind == "swinir" and prof_ms.get("attention", 0.0) == 0.0   # attention ran inside the qkv GEMM kernel
-        gf = fl(kw, hn, wn, gemm_only=True, attention_in_gemm=fused_attn, folded_tail=folded)
-        ach = gf * B * K / (gemm_ms * 1e-3) / 1e12
-        family = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                  "kernel": "srk tcgen05 GEMM kernel family incl. the fused qkv+window-attention kernel (every launch of "
-                            "K steps, CUDA events on the launch stream)",
-                  "algorithmic_gflop_per_patch_in_gemm": gf / 1e9, "launches_per_step": gemm_calls / K,
-                  "ms_per_step": gemm_ms / K}
-        roofline.update(achieved=ach, frac=ach / peak, kernel=family["kernel"],
-                        algorithmic_gflop_per_patch_in_gemm=gf / 1e9, launches_per_step=gemm_calls / K,
-                        ms_per_step=gemm_ms / K, family_ms_per_step={k: v / K for k, v in prof_ms.items()})
-    else:
-        roofline.update(achieved=step_tflops, frac=step_tflops / peak,
-                        kernel="whole step (per-kernel event timing unavailable)")
-    tp = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    gflop_ref = fl(kw, hn, wn) / 1e9
+    folded = args.engine == "tcgen05" and kw.get("upsampler", "pixelshuffle") == "pixelshuffle"
+    gflop_exec = fl(kw, hn, wn, folded_tail=folded) / 1e9
+    burst = bool(clocks and clocks.get("sm_mhz") and clocks["sm_mhz"] >= 1900.0 and peaks["tensor_burst"])
+    peak = peaks["tensor_burst"] if burst else (peaks["tensor_sustained"] or peaks["tensor_burst"])
+    per_gpu = value / world
+    ach_exec, ach_ref = per_gpu * gflop_exec / 1e3, per_gpu * gflop_ref / 1e3
+    roofline = {"bound": "tensor", "achieved": ach_exec, "peak": peak, "unit": "TFLOP/s", "frac": ach_exec / peak,
+                "frac_executed_flops": ach_exec / peak, "frac_reference_flops": ach_ref / peak,
+                "achieved_reference_flops": ach_ref, "traffic": None,
+                "peak_source": peaks["source"] + (", cuBLAS bf16 burst (SM clock at maximum through the timed region)" if burst
+                                                  else ", cuBLAS bf16 sustained"),
+                "kernel": "whole step: every launch of the forward + metrics (CUDA events around the K timed steps)",
+                "gflop_per_patch_executed": gflop_exec, "gflop_per_patch_reference": gflop_ref,
+                "scope": "per GPU (rank 0)",
+                "family_ms_per_step": {k: v / K for k, v in prof_ms.items() if prof_calls.get(k)},
+                "family_launches_per_step": {k: v / K for k, v in prof_calls.items() if v}}
+    tp = os.path.join(ROOT, "profiles", "r02_step_traffic.json")
     tj = json.load(open(tp)) if os.path.exists(tp) and args.workload == "cfg3" and args.geometry == "direct" and B == 32 else None
     if tj:
-        roofline["traffic"] = tj["gemm_family"]["dram_bytes"]
-        roofline["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum summed over the %d GEMM launches of one "
-                                    "step (ncu launch list profiles/r01_launches_cfg3_step.csv); same per-step scope "
-                                    "as `achieved`" % tj["gemm_family"]["launches"])
-    # The dominant single kernel of a SwinIR step is the row GEMM with residual + fused LayerNorm epilogue
-    # (proj and fc2 of every block: gemm_tc5_kernel<192, E_RES_LN>): it is HBM bound, so ITS roofline is the
-    # headline one and the tensor-pipe view of the whole GEMM family moves to `gemm_family`.
-    if kind == "swinir" and prof_ms.get("gemm_res_ln", 0.0) > 0 and peaks.get("hbm"):
-        Cp_, hid_p_ = (kw["embed_dim"] + 63) // 64 * 64, (int(kw["embed_dim"] * kw["mlp_ratio"]) + 63) // 64 * 64
-        nh_max = max(kw["num_heads"])
-        ao_p_ = ((-(-(kw["embed_dim"] // nh_max) // 16) * 16) * nh_max + 63) // 64 * 64
+        roofline["traffic"] = tj["step"]["dram_bytes"]
+        roofline["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum summed over the %d launches of one step "
+                                    "(ncu launch list profiles/r02_launches_cfg3_step.csv)" % tj["step"]["launches"])
+    # The two kernels that make up a Swin block, each with its HBM view (algorithmic bytes per token on the UN-padded
+    # embedding) and its tensor view, from CUDA-event pairs around every such launch (second pass of the same K steps).
+    if kind == "swinir":
+        C_, hid_ = kw["embed_dim"], int(kw["embed_dim"] * kw["mlp_ratio"])
         tok = B * hn * wn
-        # per token: A (16-bit) + residual in (fp32) + residual out (fp32) + LayerNorm output (16-bit)
-        b_proj, b_fc2 = 2 * ao_p_ + 10 * Cp_, 2 * hid_p_ + 10 * Cp_
-        n_l = prof_calls["gemm_res_ln"] / K
-        bytes_launch = tok * (b_proj + b_fc2) / 2.0
-        t_launch = prof_ms["gemm_res_ln"] / prof_calls["gemm_res_ln"] * 1e-3
-        ach_gbs = bytes_launch / t_launch / 1e9
-        hbm = {"bound": "hbm", "achieved": ach_gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach_gbs / peaks["hbm"],
-               "traffic": None, "peak_source": peaks["source"] + ", device copy",
-               "kernel": "gemm_tc5_kernel<192, E_RES_LN>: proj / fc2 row GEMM + bias + fp32 residual + fused LayerNorm, "
-                         "%.0f launches per step, %.1f %% of the step" % (n_l, 100.0 * prof_ms["gemm_res_ln"] / K / (ms / K)),
-               "algorithmic_bytes_per_launch": bytes_launch,
-               "algorithmic_bytes_per_token": {"proj": b_proj, "fc2": b_fc2},
-               "avg_launch_us": t_launch * 1e6, "launches_per_step": n_l,
-               "share_of_step": prof_ms["gemm_res_ln"] / K / (ms / K), "scope": "per GPU (rank 0)"}
-        if tj and "by_kernel" in tj:
-            for name, kinfo in tj["by_kernel"].items():
-                if name.startswith("gemm_tc5_kernel<192, 2, 0, 0>"):
-                    hbm["traffic"] = kinfo["dram_bytes"] / kinfo["launches"]
-                    hbm["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum per launch, average over the %d "
-                                           "launches of this kernel in profiles/r01_launches_cfg3_step.csv; below the "
-                                           "algorithmic bytes because part of the written rows is still dirty in the "
-                                           "126 MB L2 when the next kernel reads them" % kinfo["launches"])
-        hbm["gemm_family"] = family
-        hbm["whole_step"] = {k: roofline[k] for k in ("whole_step_achieved", "whole_step_frac", "gflop_per_patch",
-                                                       "reference_gflop_per_patch", "flops_note")}
-        hbm["whole_step"]["family_ms_per_step"] = {k: v / K for k, v in prof_ms.items()}
-        roofline = hbm
+        doms = []
+        for fam, name, bytes_tok, flop_tok in (
+                ("attn_block", "attn_block_tc5_kernel: LN1 rows -> qkv -> window attention -> proj + residual -> LN2",
+                 2 * C_ + 4 * C_ + 4 * C_ + 2 * C_, 2.0 * (3 * C_ * C_ + 2 * 64 * C_ + C_ * C_)),
+                ("mlp", "mlp_tc5_kernel: fc1 + GELU + fc2 + residual + next LN1",
+                 2 * C_ + 4 * C_ + 4 * C_ + 2 * C_, 2.0 * (2 * C_ * hid_)),
+                ("gemm_res_ln", "gemm_tc5_kernel<192, E_RES_LN>: proj / fc2 row GEMM + residual + LayerNorm (unfused blocks only)",
+                 2 * C_ + 4 * C_ + 4 * C_ + 2 * C_, 2.0 * C_ * C_)):
+            if prof_calls.get(fam, 0) == 0:
+                continue
+            t_l = prof_ms[fam] / prof_calls[fam] * 1e-3
+            d = {"kernel": name, "launches_per_step": prof_calls[fam] / K, "avg_launch_us": t_l * 1e6,
+                 "share_of_step": prof_ms[fam] / K / (ms / K),
+                 "hbm": {"algorithmic_bytes_per_token": bytes_tok, "achieved": tok * bytes_tok / t_l / 1e9, "unit": "GB/s",
+                         "peak": peaks["hbm"], "frac": tok * bytes_tok / t_l / 1e9 / peaks["hbm"]},
+                 "tensor": {"algorithmic_flop_per_token": flop_tok, "achieved": tok * flop_tok / t_l / 1e12, "unit": "TFLOP/s",
+                            "peak": peak, "frac": tok * flop_tok / t_l / 1e12 / peak}}
+            if tj and fam in tj.get("by_family", {}):
+                d["hbm"]["traffic"] = tj["by_family"][fam]["dram_bytes"] / max(tj["by_family"][fam]["launches"], 1)
+            doms.append(d)
+        doms.sort(key=lambda d: -d["share_of_step"])
+        if doms:
+            roofline["dominant_kernel"] = doms[0]
+            roofline["other_block_kernels"] = doms[1:]
 
     line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -396,14 +536,21 @@ def main():
                        "l2": "per-step working set (>2 GB of activations) is far larger than the 126 MB L2; "
                              f"{NB} distinct input batches are rotated"},
             "clocks": clocks, "gpu_launches": launches,
-            "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "shipping": "uint8 LR + uint8 HR (the loader's stored levels), /255 on the device",
+                    "fp32_shipping": {"value": e2e_fp32, "h2d_bytes_per_step": 4 * h2d}},
             "roofline": roofline}
+    if world == 1 and not args.no_eager_baseline:
+        try:
+            line["gpu_eager_baseline"] = gpu_eager_run(kind, kw, sd_cpu, h, w, seed, min(B, 8), dev)
+        except Exception as exc:                                   # e.g. out of memory on a shared box: report, do not fail the bench
+            line["gpu_eager_baseline"] = {"unavailable": repr(exc)[:200]}
 
     if not args.no_cpu_baseline and world >= 1:
         sample_b = 4 if kind == "swinir" else 8
         cpu_steps = 6 if kind == "swinir" else 8                 # ~10 s of host work for cfg3
         v, spt, thr = cpu_reference_run(kind, kw, sd_cpu, h, w, seed, cpu_steps, 1, sample_b)
-        line["cpu_baseline"] = {"value": v, "unit": unit, "cores": thr, "kind": "port",
+        line["cpu_baseline"] = {"value": v, "unit": unit, "cores": thr, "kind": "port", "host_cpu": host_cpu_model(),
                                 "sample": f"{cpu_steps} steps x batch {sample_b} (1 warm-up) of the same workload through "
                                           "oracle/sr_oracle.py on the host CPU, fp32"}
     print(json.dumps(line))

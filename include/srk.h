@@ -352,7 +352,9 @@ int srk_edsr_forward(const srk_edsr_plan* p, const float* x, float* y, int B, in
 enum { SRK_PROF_GEMM = 0, SRK_PROF_ATTENTION = 1, SRK_PROF_LAYERNORM = 2, SRK_PROF_CONV_IN = 3,
        SRK_PROF_CONV_OUT = 4, SRK_PROF_METRICS = 5,
        SRK_PROF_GEMM_RES_LN = 6,   /* srk_gemm calls with residual + fused LayerNorm on row operands (proj / fc2) */
-       SRK_PROF_N = 7 };
+       SRK_PROF_ATTN_BLOCK = 7,    /* srk_attn_block */
+       SRK_PROF_MLP = 8,           /* srk_mlp */
+       SRK_PROF_N = 9 };
 int srk_profile(int enable);
 int srk_profile_read(double* ms_by_family, long long* calls_by_family, int reset);
 

@@ -207,10 +207,10 @@ def _swin_block(x: Tensor, H: int, W: int, p: Dict[str, Tensor], pre: str, nh: i
     else:
         att = (q * (d ** -0.5)) @ k.transpose(-1, -2)
     table = p[pre + "attn.relative_position_bias_table"]
-    bias = table[relative_position_index(ws).reshape(-1)].view(N, N, nh).permute(2, 0, 1)
+    bias = table[relative_position_index(ws).reshape(-1).to(table.device)].view(N, N, nh).permute(2, 0, 1)
     att = att + bias[None]
     if shift > 0:
-        m = shift_attention_mask(H, W, ws, shift)                      # nW, N, N
+        m = shift_attention_mask(H, W, ws, shift).to(att.device)       # nW, N, N
         nW = m.shape[0]
         att = (att.view(-1, nW, nh, N, N) + m[None, :, None]).view(-1, nh, N, N)
     att = torch.softmax(att, dim=-1)
@@ -247,9 +247,9 @@ def swinir_forward(sd: Dict[str, Tensor], cfg: SwinIRCfg, x: Tensor,
     wsz = cfg.window_size
     ph, pw = (wsz - h0 % wsz) % wsz, (wsz - w0 % wsz) % wsz
     x = F.pad(x.float(), (0, pw, 0, ph), mode="reflect")               # :908-913
-    mean = torch.zeros(1, Cin, 1, 1)
+    mean = torch.zeros(1, Cin, 1, 1, device=x.device)
     if Cin == 3:
-        mean = torch.tensor([0.4488, 0.4371, 0.4040]).view(1, 3, 1, 1)  # :776-779
+        mean = torch.tensor([0.4488, 0.4371, 0.4040], device=x.device).view(1, 3, 1, 1)  # :776-779
     x = (x - mean) * cfg.img_range
     H, W = x.shape[2:]
     C = cfg.embed_dim
@@ -396,7 +396,7 @@ def ssim(a, b, border=0, roi=None) -> Tensor:
     assert a.shape == b.shape and a.dim() == 4
     x, y, roi = _crop(a, border) / 255.0, _crop(b, border) / 255.0, _crop(roi, border)
     ch = x.shape[1]
-    k = gaussian_window().repeat(ch, 1, 1, 1)
+    k = gaussian_window().repeat(ch, 1, 1, 1).to(x.device)
     if x.shape[-1] < 11 or x.shape[-2] < 11:
         raise ValueError("Kernel size can't be greater than actual input size")
     filt = lambda t: F.conv2d(t, k, groups=ch)

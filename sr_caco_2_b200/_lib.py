@@ -208,7 +208,7 @@ def launch_count(reset=False) -> int:
     return int(load().srk_launch_count(1 if reset else 0))
 
 
-PROF_FAMILIES = ("gemm", "attention", "layernorm", "conv_in", "conv_out", "metrics", "gemm_res_ln")
+PROF_FAMILIES = ("gemm", "attention", "layernorm", "conv_in", "conv_out", "metrics", "gemm_res_ln", "attn_block", "mlp")
 
 
 def profile(enable: bool):

@@ -483,7 +483,7 @@ extern "C" int srk_attn_block(const srk_attn_block_args* a, void* stream) {
     }
     static bool attr[64] = {};
     if (first_use_on_device(attr)) SRK_CUDA(cudaFuncSetAttribute(attn_block_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AB_SMEM));
-    ProfScope ps(SRK_PROF_GEMM, stream);
+    ProfScope ps(SRK_PROF_ATTN_BLOCK, stream);
     const int grid = p.m_tiles < num_sms() ? p.m_tiles : num_sms();
     attn_block_tc5_kernel<<<grid, AB_THREADS, AB_SMEM, (cudaStream_t)stream>>>(ma, mq, mp, p);
     SRK_LAUNCH_CHECK("attn_block_tc5_kernel");

@@ -546,7 +546,7 @@ extern "C" int srk_mlp(const srk_mlp_args* a, void* stream) {
     }
     if (srk_get_engine() != SRK_ENGINE_TCGEN05)
         return fail(SRK_ERR_UNSUPPORTED, "mlp: the fused MLP kernel exists for the tcgen05 engine only");
-    ProfScope ps(SRK_PROF_GEMM, stream);
+    ProfScope ps(SRK_PROF_MLP, stream);
     cudaStream_t st = (cudaStream_t)stream;
     const bool ln = a->ln_g != nullptr;
     switch (a->Cp) {
