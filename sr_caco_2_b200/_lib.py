@@ -204,15 +204,33 @@ def get_engine() -> str:
     return {ENGINE_TCGEN05: "tcgen05", ENGINE_MMA_SYNC: "mma_sync"}[load().srk_get_engine()]
 
 
+_graph_launches = 0          # kernel launches replayed from CUDA graphs (the library only counts what it launches itself)
+
+
+def add_graph_launches(n: int):
+    global _graph_launches
+    _graph_launches += int(n)
+
+
 def launch_count(reset=False) -> int:
-    return int(load().srk_launch_count(1 if reset else 0))
+    """Kernels of this library launched on the calling thread since the last reset, including graph replays."""
+    global _graph_launches
+    n = int(load().srk_launch_count(1 if reset else 0)) + _graph_launches
+    if reset:
+        _graph_launches = 0
+    return n
 
 
 PROF_FAMILIES = ("gemm", "attention", "layernorm", "conv_in", "conv_out", "metrics", "gemm_res_ln", "attn_block", "mlp")
 
 
+profiling = False            # per-launch event timing is on: forwards run eagerly (a graph replay has no per-kernel events)
+
+
 def profile(enable: bool):
+    global profiling
     check(load().srk_profile(1 if enable else 0))
+    profiling = bool(enable)
 
 
 def profile_read(reset=True):

@@ -18,6 +18,7 @@ import torch.nn as nn
 
 from . import _lib as L
 from . import packing as P
+from .network_swinir import GraphedForward
 
 
 class _Holder(nn.Module):
@@ -25,7 +26,7 @@ class _Holder(nn.Module):
         raise RuntimeError("parameter holder: the network is executed by EDSR.forward")
 
 
-class EDSR(nn.Module):
+class EDSR(GraphedForward, nn.Module):
     def __init__(self, in_chans=1, n_resblocks=16, n_feats=64, scale=4, rgb_range=1.0,
                  res_scale=1.0, **kwargs):
         super().__init__()
@@ -52,11 +53,13 @@ class EDSR(nn.Module):
             ups += [nn.Conv2d(n_feats, 4 * n_feats, 3, padding=1), nn.PixelShuffle(2)]
         self.tail = nn.Sequential(nn.Sequential(*ups), nn.Conv2d(n_feats, in_chans, 3, padding=1))
         self._plan = self._keep = self._ws = None
+        self._graphs = {}
         self.options = 0             # srk.h SRK_OPT_* bits; 0 = product path
         self.register_load_state_dict_post_hook(lambda mod, keys: mod._invalidate())
 
     def _invalidate(self):
         self._plan = self._keep = None
+        self._graphs = {}
 
     def _apply(self, fn, *a, **k):
         self._invalidate()
@@ -122,16 +125,24 @@ class EDSR(nn.Module):
         if self._plan is None or fp != getattr(self, "_plan_fp", None):   # in-place parameter updates bump ._version
             self._build_plan()
             self._plan_fp = fp
+            self._graphs = {}
         self._plan.options = int(self.options)
         with torch.cuda.device(x.device):
-            need = lib.srk_edsr_workspace_bytes(C.byref(self._plan), B, h, w)
+            if self._use_graph():
+                return self._forward_graph(lib, x, B, h, w, self.scale)
+            need = self._ws_bytes(lib, B, h, w)
             if self._ws is None or self._ws.numel() < need or self._ws.device != x.device:
                 self._ws = None
                 self._ws = torch.empty(need, dtype=torch.uint8, device=x.device)
             y = torch.empty(B, self.in_chans, h * self.scale, w * self.scale, dtype=torch.float32, device=x.device)
-            L.check(lib.srk_edsr_forward(C.byref(self._plan), L.ptr(x), L.ptr(y), B, h, w,
-                                         L.ptr(self._ws), self._ws.numel(), L.stream_ptr()))
+            self._launch(lib, x, y, B, h, w, self._ws)
         return y
+
+    def _ws_bytes(self, lib, B, h, w):
+        return lib.srk_edsr_workspace_bytes(C.byref(self._plan), B, h, w)
+
+    def _launch(self, lib, x, y, B, h, w, ws):
+        L.check(lib.srk_edsr_forward(C.byref(self._plan), L.ptr(x), L.ptr(y), B, h, w, L.ptr(ws), ws.numel(), L.stream_ptr()))
 
 
 def EDSR_LIIF(in_chans, n_resblocks, n_feats, scale, rgb_range, local_ensemble=True,

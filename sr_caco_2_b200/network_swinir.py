@@ -74,7 +74,52 @@ def _shift_mask(res, ws, shift):
     return torch.where(d != 0, torch.tensor(-100.0), torch.tensor(0.0))
 
 
-class SwinIR(nn.Module):
+class GraphedForward:
+    """Mixin: the launches of a forward replayed as ONE CUDA graph per (B, h, w).  The workspace, the input and the
+    output of a graph are static buffers (the workspace is caller-owned by design, include/srk.h), the tensor maps are
+    encoded once at capture.  The first call of a shape runs eagerly (lazy kernel attributes), the second captures;
+    the output is copied out of the static buffer.  Subclasses provide _ws_bytes(lib, B, h, w), _launch(lib, x, y, B,
+    h, w, ws) and the attributes in_chans / out scale."""
+    MAX_GRAPHS = 4
+
+    def _forward_graph(self, lib, x, B, h, w, scale):
+        key = (B, h, w, x.device.index, int(self.options))
+        g = self._graphs.get(key)
+        if g is None:
+            if len(self._graphs) >= self.MAX_GRAPHS:
+                self._graphs.pop(next(iter(self._graphs)))
+            need = self._ws_bytes(lib, B, h, w)
+            g = {"ws": torch.empty(need, dtype=torch.uint8, device=x.device), "x": torch.empty_like(x),
+                 "y": torch.empty(B, self.in_chans, h * scale, w * scale, dtype=torch.float32, device=x.device),
+                 "graph": None, "launches": 0}
+            self._graphs[key] = g
+
+        def run():
+            self._launch(lib, g["x"], g["y"], B, h, w, g["ws"])
+        g["x"].copy_(x)
+        if g["graph"] is None and g["launches"] == 0:          # first call of this shape: eager
+            n0 = L.launch_count()
+            run()
+            g["launches"] = L.launch_count() - n0
+        elif g["graph"] is None:                                # second call: capture, then replay
+            graph = torch.cuda.CUDAGraph()
+            n0 = int(lib.srk_launch_count(0))
+            with torch.cuda.graph(graph):
+                run()
+            L.add_graph_launches(n0 - int(lib.srk_launch_count(0)))   # the launches recorded during capture did not execute
+            g["graph"] = graph
+            graph.replay()
+            L.add_graph_launches(g["launches"])
+        else:
+            g["graph"].replay()
+            L.add_graph_launches(g["launches"])
+        return g["y"].clone()
+
+    def _use_graph(self):
+        return not (int(self.options) & L.OPT_NO_GRAPH) and not L.profiling and not torch.cuda.is_current_stream_capturing()
+
+
+class SwinIR(GraphedForward, nn.Module):
     def __init__(self, img_size=64, patch_size=1, in_chans=3, embed_dim=96,
                  depths=[6, 6, 6, 6], num_heads=[6, 6, 6, 6], window_size=7, mlp_ratio=4.,
                  qkv_bias=True, qk_scale=None, drop_rate=0., attn_drop_rate=0.,
@@ -178,6 +223,7 @@ class SwinIR(nn.Module):
         self._plan_fp = None
         self._keep = None
         self._ws = None
+        self._graphs = {}
         self.options = 0             # srk.h SRK_OPT_* bits (tests switch single fusions off); 0 = product path
         self.register_load_state_dict_post_hook(lambda mod, keys: mod._invalidate())
 
@@ -193,6 +239,7 @@ class SwinIR(nn.Module):
     def _invalidate(self):
         self._plan = None
         self._keep = None
+        self._graphs = {}
 
     def _apply(self, fn, *a, **k):
         self._invalidate()
@@ -351,14 +398,23 @@ class SwinIR(nn.Module):
         if self._plan is None or fp != self._plan_fp:        # in-place parameter updates (EMA, optimizer steps) bump ._version
             self._build_plan()
             self._plan_fp = fp
+            self._graphs = {}
         self._plan.options = int(self.options)
         with torch.cuda.device(x.device):
-            need = lib.srk_swinir_workspace_bytes(C.byref(self._plan), B, h, w)
+            if self._use_graph():
+                return self._forward_graph(lib, x, B, h, w, self.upscale)
+            need = self._ws_bytes(lib, B, h, w)
             if self._ws is None or self._ws.numel() < need or self._ws.device != x.device:
                 self._ws = None
                 self._ws = torch.empty(need, dtype=torch.uint8, device=x.device)
             y = torch.empty(B, self.in_chans, h * self.upscale, w * self.upscale,
                             dtype=torch.float32, device=x.device)
-            L.check(lib.srk_swinir_forward(C.byref(self._plan), L.ptr(x), L.ptr(y), B, h, w,
-                                           L.ptr(self._ws), self._ws.numel(), L.stream_ptr()))
+            self._launch(lib, x, y, B, h, w, self._ws)
         return y
+
+    def _ws_bytes(self, lib, B, h, w):
+        return lib.srk_swinir_workspace_bytes(C.byref(self._plan), B, h, w)
+
+    def _launch(self, lib, x, y, B, h, w, ws):
+        L.check(lib.srk_swinir_forward(C.byref(self._plan), L.ptr(x), L.ptr(y), B, h, w, L.ptr(ws), ws.numel(), L.stream_ptr()))
+

@@ -910,3 +910,25 @@ def test_plan_follows_in_place_parameter_updates(L):
     sd2 = dict(sd); sd2["conv_first.weight"] = sd["conv_first.weight"] * 1.5
     ref = O.swinir_forward(sd2, cfg, x.cpu())
     assert float((y1.cpu() - ref).abs().max()) < 2e-3 and float((y1 - y0).abs().max()) > 1e-3
+
+
+def test_cuda_graph_replay_is_bit_identical_to_eager_launches(L):
+    """The forward of a shape is launched eagerly once, captured on the second call and replayed afterwards
+    (network_swinir._forward_graph); options = SRK_OPT_NO_GRAPH keeps the plain launch sequence."""
+    L.set_engine("tcgen05")
+    cfg = O.SwinIRCfg(upscale=2, img_size=16, embed_dim=180, depths=[2, 2], num_heads=[6, 6], mlp_ratio=2.0,
+                      upsampler="pixelshuffle")
+    net = make_swinir(cfg, T.swinir_state_dict(cfg, 6))
+    xs = [T.synthetic_lr(2, 24, 32, s).to(DEV) for s in (1, 2, 3, 4)]
+    net.options = L.OPT_NO_GRAPH
+    ref = [net(x).clone() for x in xs]
+    net.options = 0
+    L.launch_count(reset=True)
+    got = [net(x) for x in xs]                        # eager, capture + replay, replay, replay
+    n = L.launch_count()
+    for a, b in zip(got, ref):
+        assert torch.equal(a, b)
+    key = next(iter(net._graphs))
+    assert net._graphs[key]["graph"] is not None and n == 4 * net._graphs[key]["launches"]
+    y2 = net(T.synthetic_lr(1, 16, 16, 9).to(DEV))    # another shape gets its own graph
+    assert y2.shape == (1, 1, 32, 32) and len(net._graphs) == 2
