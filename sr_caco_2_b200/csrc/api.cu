@@ -2,7 +2,6 @@
 #include "common.cuh"
 #include <string.h>
 #include <vector>
-#include <stdlib.h>
 
 namespace srk {
 thread_local char g_err[512] = "";
@@ -18,12 +17,6 @@ void prof_begin(int family, cudaStream_t st) {
     g_prof.push_back(r);
 }
 void prof_end(cudaStream_t st) { if (!g_prof.empty()) cudaEventRecord(g_prof.back().b, st); }
-
-bool pdl_enabled() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("SRK_PDL"); v = (e && atoi(e) != 0) ? 1 : 0; }   // measured: no gain, off by default
-    return v != 0;
-}
 
 int fail(int code, const char* fmt, ...) {
     va_list ap;

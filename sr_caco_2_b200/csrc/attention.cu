@@ -24,8 +24,6 @@ window_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int ldq,
                         __nv_bfloat16* __restrict__ out, int ldo, const float* __restrict__ rel_table, int H, int W, int nH,
                         int HG, float scale, int shift) {
     extern __shared__ __align__(16) unsigned char att_smem[];
-    pdl_launch_dependents();
-    pdl_wait();
     const int h0 = blockIdx.y * HG;              // first head of this CTA
     const int nhl = min(HG, nH - h0);            // heads handled here
     const int seg = HG * DP;                     // local elements per q / k / v section
@@ -127,9 +125,7 @@ extern "C" int srk_window_attention(const void* qkv, int ldq, void* out, int ldo
     SRK_REQUIRE(nH >= 1 && ldo % 8 == 0 && ldo >= nH * dp, "window_attention: bad nH/ldo");
     const int nq = 3 * nH * dp;
     SRK_REQUIRE(ldq % 8 == 0 && ldq >= nq, "window_attention: bad ldq");
-    static int hg_env = -1;
-    if (hg_env < 0) { const char* e = getenv("SRK_ATT_HG"); hg_env = e ? atoi(e) : 0; }
-    int HG = hg_env > 0 ? hg_env : (nH % 2 == 0 ? 2 : (nH % 3 == 0 ? 3 : 1));
+    int HG = nH % 2 == 0 ? 2 : (nH % 3 == 0 ? 3 : 1);                  // heads per CTA
     if (HG > nH) HG = nH;
     const size_t smem = (size_t)64 * (3 * HG * dp * 2 + 16) + (size_t)HG * 225 * 4 + 64 * 4;
     SRK_REQUIRE(smem <= 227 * 1024, "window_attention: window does not fit shared memory");
@@ -140,9 +136,9 @@ extern "C" int srk_window_attention(const void* qkv, int ldq, void* out, int ldo
     do {                                                                                      \
         SRK_CUDA(cudaFuncSetAttribute(window_attention_kernel<D>,                             \
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        SRK_CUDA(launch_pdl(window_attention_kernel<D>, grid, dim3(ATT_THREADS), smem, st,     \
+        window_attention_kernel<D><<<grid, ATT_THREADS, smem, st>>>(                          \
             (const __nv_bfloat16*)qkv, ldq, (__nv_bfloat16*)out, ldo, rel_table, H, W, nH, HG, scale,  \
-            shift));                                                                          \
+            shift);                                                                           \
     } while (0)
     if (dp == 16) LAUNCH(16);
     else if (dp == 32) LAUNCH(32);

@@ -203,23 +203,6 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// ---- programmatic dependent launch (PDL): the next kernel's CTAs may start (and run their
-// prologue) as soon as SMs drain; they block in pdl_wait() until the previous grid has completed
-// and its writes are visible.  Opt-in with SRK_PDL=1 (measured on B200: no gain for this launch sequence).
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-bool pdl_enabled();
-template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
-}
-
 // engine entry points (one per translation unit)
 int gemm_mma_sync(const srk_gemm_args* g, cudaStream_t st);
 int gemm_tcgen05(const srk_gemm_args* g, cudaStream_t st);

@@ -111,7 +111,6 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const GemmP& g = p.g;
     const int total_tiles = p.m_tiles * p.n_tiles;
-    pdl_launch_dependents();                                          // the next kernel may queue up behind us
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < Cfg::MAX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -130,8 +129,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
-    // resident weight tile, loaded once: weights do not depend on the previous grid, so the load is
-    // issued before the programmatic-dependent-launch wait and overlaps the previous kernel's drain
+    // resident weight tile, loaded once
     if (warp == 0 && lane == 0 && p.bstat && (int)blockIdx.x < total_tiles) {
         const int ntb = blockIdx.x % p.n_tiles;
         mbar_expect_tx(bfull_bar, (uint32_t)p.bres_bytes);
@@ -147,7 +145,6 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             }
         }
     }
-    pdl_wait();                                                       // prologue done; now the previous grid's data
 
     if (warp == 0) {
         // ================================ TMA producer ================================
@@ -782,7 +779,7 @@ static int launch_tc5(const CUtensorMap& ma, const CUtensorMap& mb, const TcPara
         if (p.stages > Cfg::MAX_STAGES) p.stages = Cfg::MAX_STAGES;
     }
     const size_t smem = (size_t)p.bres_bytes + (size_t)p.stages * p.stage_bytes + Cfg::STAGING_BYTES + 1024 + Cfg::AUX_BYTES;
-    SRK_CUDA(launch_pdl(gemm_tc5_kernel<BN, EPI, ACT, DT>, dim3(grid), dim3(Cfg::THREADS), smem, st, ma, mb, p));
+    gemm_tc5_kernel<BN, EPI, ACT, DT><<<grid, Cfg::THREADS, smem, st>>>(ma, mb, p);
     SRK_LAUNCH_CHECK("gemm_tc5_kernel");
     return 0;
 }
