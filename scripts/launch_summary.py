@@ -36,6 +36,11 @@ if len(sys.argv) > 2:
     for k, (n, t, b) in agg.items():
         if k.startswith("gemm_") or k.startswith("mlp_"):
             fam["gemm"][0] += n; fam["gemm"][1] += t; fam["gemm"][2] += b
-    json.dump({"gemm_family": {"launches": fam["gemm"][0], "us": fam["gemm"][1], "dram_bytes": fam["gemm"][2]},
+    famof = lambda k: "attn_block" if k.startswith("attn_block") else "mlp" if k.startswith("mlp_") else "gemm_res_ln" if k.startswith("gemm_tc5_kernel<192, 2") else "gemm" if k.startswith("gemm_") else "other"
+    byf = collections.defaultdict(lambda: {"launches": 0, "us": 0.0, "dram_bytes": 0.0})
+    for k, (n, t, b) in agg.items():
+        f = byf[famof(k)]; f["launches"] += n; f["us"] += t; f["dram_bytes"] += b
+    json.dump({"step": {"launches": len(per), "us": tot, "dram_bytes": totb}, "by_family": byf,
+               "gemm_family": {"launches": fam["gemm"][0], "us": fam["gemm"][1], "dram_bytes": fam["gemm"][2]},
                "by_kernel": {k: {"launches": n, "us": t, "dram_bytes": b} for k, (n, t, b) in agg.items()},
                "total_us": tot, "total_dram_bytes": totb}, open(sys.argv[2], "w"), indent=1)

@@ -9,6 +9,8 @@ kind, kw, B, h, w, desc = CF.WORKLOADS[wl]
 B = int(os.environ.get("SRK_B", B))
 torch.manual_seed(0)
 net = CF.build(kind, kw).cuda().eval()
+from sr_caco_2_b200 import _lib as L
+net.options = L.OPT_NO_GRAPH          # plain launches: one profiler record per kernel
 scale = kw.get("upscale", kw.get("scale"))
 x = torch.rand(B, 1, h, w, device="cuda")
 hr = (torch.rand(B, 1, h * scale, w * scale, device="cuda") * 255).round() / 255
