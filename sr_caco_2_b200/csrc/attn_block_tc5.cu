@@ -212,14 +212,24 @@ attn_block_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         unsigned char* ao = sm + AB_AO_OFF;
 
         // ---- head unit: head h of tile iteration it (job index 6 it + h) ----
-        auto unit = [&](int it, int tile, int h) {
-            const int j = it * AB_NH + h, s = j % 3;
-            // shift-mask region labels of the tile's two windows (threads 0..127 of the group)
+        // per tile, once per group: the shift-mask region labels of the tile's two windows (threads 0..127 of the group;
+        // the group barrier inside the tile's first unit publishes them) and this warp's window flags
+        bool w_valid = false, w_masked = false;
+        auto tile_setup = [&](int tile) {
             const int tg = gw * 32 + lane;
-            const int wg = tile * 2 + (tg >> 6);
-            const int win = wg % nW, wi = win / wpr, wj = win - wi * wpr;
-            const bool m_any = p.shift > 0 && (wi == nWy - 1 || wj == wpr - 1);
-            if (tg < 128) lab[tg] = (unsigned char)(m_any ? win_pos_label(win, tg & 63, p.H, p.W, p.shift) : 0);
+            if (tg < 128) {
+                const int wg = tile * 2 + (tg >> 6);
+                const int win = wg % nW, wi = win / wpr, wj = win - wi * wpr;
+                const bool m_any = p.shift > 0 && (wi == nWy - 1 || wj == wpr - 1);
+                lab[tg] = (unsigned char)(m_any ? win_pos_label(win, tg & 63, p.H, p.W, p.shift) : 0);
+            }
+            const int wg2 = tile * 2 + window;
+            const int win2 = wg2 % nW, wi2 = win2 / wpr, wj2 = win2 - wi2 * wpr;
+            w_valid = (long long)wg2 * 64 < p.M;
+            w_masked = p.shift > 0 && (wi2 == nWy - 1 || wj2 == wpr - 1);
+        };
+        auto unit = [&](int it, int h) {
+            const int j = it * AB_NH + h, s = j % 3;
             mbar_wait(q_full(s), (j / 3) & 1);
             tc_fence_after();
             {   // drain: thread = row, 48 columns -> 96 B of the staged row [q 32 | k 32 | v 32]
@@ -248,16 +258,10 @@ attn_block_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             if (lane == 0) mbar_arrive(q_empty(s));                       // accumulator stage drained
             asm volatile("bar.sync %0, 256;" ::"r"(bar_g) : "memory");   // the head is staged (+ labels)
             if (it > 0) mbar_wait(ao_empty, (it - 1) & 1);                // the previous tile's proj MMAs have read AO
-            {
-                const int wg2 = tile * 2 + window;
-                if ((long long)wg2 * 64 < p.M) {
-                    const int win2 = wg2 % nW, wi2 = win2 / wpr, wj2 = win2 - wi2 * wpr;
-                    const bool masked = p.shift > 0 && (wi2 == nWy - 1 || wj2 == wpr - 1);
-                    attn_unit<32, true, unsigned char>(stg_s + window * 64 * AB_SROW16, stg + (size_t)window * 64 * AB_SROW16, AB_SROW16,
-                                                       strip, 0, 32, 64, stab + h * 225, lab + window * 64, masked, p.scale, lane,
-                                                       ao, window * 64, h);
-                }
-            }
+            if (w_valid)
+                attn_unit<32, true, unsigned char>(stg_s + window * 64 * AB_SROW16, stg + (size_t)window * 64 * AB_SROW16, AB_SROW16,
+                                                   strip, 0, 32, 64, stab + h * 225, lab + window * 64, w_masked, p.scale, lane,
+                                                   ao, window * 64, h);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes of AO -> visible to UMMA
             __syncwarp();
             if (lane == 0) mbar_arrive(ao_full);
@@ -319,24 +323,31 @@ attn_block_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                     bt[k] = __ldg(reinterpret_cast<const float4*>(p.ln_b + 64 * k + 4 * hl));
                 }
             }
-            asm volatile("bar.sync 3, 512;" ::: "memory");           // both groups left their staging tiles
-            mbar_wait(pd_full, tp & 1);
-            tc_fence_after();
-#pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
-                // residual rows of the half (two row pairs per warp): L2 hits thanks to prefetch_res, they arrive under the TMEM drain
-                float4 resv[2][AB_KB];
-                int row[2];
+            // residual rows (two row pairs per warp and half; L2 hits thanks to prefetch_res): the first half's rows are
+            // requested before the waits below, the second half's under the first half's phase R
+            float4 resa[2][2][AB_KB];
+            int rows_[2][2];
+            auto request_res = [&](int half) {
                 const WinGeo geo = win_geo(tile, half);
 #pragma unroll
                 for (int rr = 0; rr < 2; ++rr) {
-                    row[rr] = token_row(geo, rr);
-                    const float* rp = p.res + (size_t)(row[rr] >= 0 ? row[rr] : 0) * p.ld32 + 4 * hl;
+                    rows_[half][rr] = token_row(geo, rr);
+                    const float* rp = p.res + (size_t)(rows_[half][rr] >= 0 ? rows_[half][rr] : 0) * p.ld32 + 4 * hl;
 #pragma unroll
                     for (int k = 0; k < AB_KB; ++k)
                         asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                     : "=f"(resv[rr][k].x), "=f"(resv[rr][k].y), "=f"(resv[rr][k].z), "=f"(resv[rr][k].w) : "l"(rp + 64 * k));
+                                     : "=f"(resa[half][rr][k].x), "=f"(resa[half][rr][k].y), "=f"(resa[half][rr][k].z), "=f"(resa[half][rr][k].w)
+                                     : "l"(rp + 64 * k));
                 }
+            };
+            request_res(0);
+            asm volatile("bar.sync 3, 512;" ::: "memory");           // both groups left their staging tiles
+            mbar_wait(pd_full, tp & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float4 (&resv)[2][AB_KB] = resa[half];
+                int (&row)[2] = rows_[half];
                 // phase T: the half's two lane groups (4 warps each, 48 columns per warp) drain PD into the staging tile
                 if ((lg >> 1) == half) {
                     const int qc = (uw >> 2) & 3;                     // 0..3: which 48 of the 192 columns
@@ -360,6 +371,7 @@ attn_block_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                     if (lane == 0) mbar_arrive(pd_empty);
                 }
                 asm volatile("bar.sync 3, 512;" ::: "memory");       // staging complete
+                if (half == 0) request_res(1);
                 // phase R: two row pairs per warp (one row per half-warp), lane hl owns columns 64 k + 4 hl
                 float4 v[2][AB_KB];
                 float sm_[2], mean[2], qq[2];
@@ -419,12 +431,12 @@ attn_block_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         int tile = blockIdx.x, prev_tile = 0;
 #pragma unroll 1
         for (int it = 0; it <= n_my; ++it, tile += gridDim.x) {
-            if (it < n_my) unit(it, tile, grp);
+            if (it < n_my) { tile_setup(tile); unit(it, grp); }
             if (it > 0) final_stage(it - 1, prev_tile);
             if (it < n_my) {
                 prefetch_res(tile);
-                unit(it, tile, grp + 2);
-                unit(it, tile, grp + 4);
+                unit(it, grp + 2);
+                unit(it, grp + 4);
             }
             prev_tile = tile;
         }
