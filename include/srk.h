@@ -225,11 +225,12 @@ int srk_conv_in(const float* x, int B, int h, int w, int H, int W, float in_scal
 /* conv_in fused with patch_embed.norm and norm1 of the first Swin block: f0 = conv(x) (fp32),
  * xa = LN(f0; g1,b1) (fp32), a16 = LN(xa; g2,b2) (16-bit) stored at the token's window-major row
  * for cyclic shift win_shift (-1: token order).  ld32 == ld16 = channels padded to 64.
+ * ln_pad_one: also write 1.0 into pad columns C, C + 1 of a16 (consumer: a qkv weight with the folded bias).
  * Replaces network_swinir.py:939 + :610-614 + :293-306 in one pass. */
 int srk_conv_in_ln(const float* x, int B, int h, int w, int H, int W, float in_scale,
                    const float* wgt, const float* bias, int C, float* f0, float* xa, int ld32,
                    const float* g1, const float* b1, const float* g2, const float* b2,
-                   void* a16, int ld16, int out16_dtype, int win_shift, void* stream);
+                   void* a16, int ld16, int out16_dtype, int win_shift, int ln_pad_one, void* stream);
 
 /* 1-channel 3x3 output conv (conv_last / EDSR tail.1): a: (B,H,W,lda) fp16, w: (9, Cin) fp16
  * tap major, y: (B,1,Hc,Wc) fp32 cropped to Hc x Wc, y = (conv + bias) * out_scale.

@@ -118,7 +118,7 @@ PROTOTYPES = {
     "srk_conv_in": (C.c_int, [fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, fp, fp,
                               C.c_int, fp, C.c_int, vp, C.c_int, C.c_int, vp]),
     "srk_conv_in_ln": (C.c_int, [fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, fp, fp,
-                                 C.c_int, fp, fp, C.c_int, fp, fp, fp, fp, vp, C.c_int, C.c_int, C.c_int, vp]),
+                                 C.c_int, fp, fp, C.c_int, fp, fp, fp, fp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "srk_conv_out": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_float,
                                C.c_float, fp, C.c_int, C.c_int, vp]),
     "srk_swinir_workspace_bytes": (C.c_size_t, [C.POINTER(SwinIRPlan), C.c_int, C.c_int, C.c_int]),

@@ -144,7 +144,7 @@ conv_in_ln_kernel(const float* __restrict__ x, int B, int h, int w, int H, int W
                   float* __restrict__ f0, float* __restrict__ xa, int ld32,
                   const float* __restrict__ g1, const float* __restrict__ b1,
                   const float* __restrict__ g2, const float* __restrict__ b2,
-                  uint16_t* __restrict__ a16, int ld16, int dt16, int win_shift) {
+                  uint16_t* __restrict__ a16, int ld16, int dt16, int win_shift, int pad_one) {
     extern __shared__ float cws[];                // [9][ld32] weights (tap major, zero padded), then bias[ld32]
     for (int i = threadIdx.x; i < 9 * ld32; i += blockDim.x) {
         const int t = i / ld32, c = i - t * ld32;
@@ -224,8 +224,9 @@ conv_in_ln_kernel(const float* __restrict__ x, int B, int h, int w, int H, int W
 #pragma unroll
         for (int k = 0; k < NP; ++k) {
             const bool inb = 64 * k + 2 * lane < C;
-            const float y0 = inb ? (v[k].x - mean) * rstd * G2[k].x + B2[k].x : 0.f;
-            const float y1 = inb ? (v[k].y - mean) * rstd * G2[k].y + B2[k].y : 0.f;
+            const float padv = (pad_one && 64 * k + 2 * lane == C) ? 1.f : 0.f;      // pad columns C, C + 1 carry the folded qkv bias
+            const float y0 = inb ? (v[k].x - mean) * rstd * G2[k].x + B2[k].x : padv;
+            const float y1 = inb ? (v[k].y - mean) * rstd * G2[k].y + B2[k].y : padv;
             *reinterpret_cast<uint32_t*>(a16 + row16 * ld16 + 64 * k + 2 * lane) = pack2(y0, y1, dt16);
         }
     }
@@ -541,8 +542,9 @@ extern "C" int srk_conv_in(const float* x, int B, int h, int w, int H, int W, fl
 extern "C" int srk_conv_in_ln(const float* x, int B, int h, int w, int H, int W, float in_scale,
                               const float* wgt, const float* bias, int C, float* f0, float* xa, int ld32,
                               const float* g1, const float* b1, const float* g2, const float* b2,
-                              void* a16, int ld16, int out16_dtype, int win_shift, void* stream) {
+                              void* a16, int ld16, int out16_dtype, int win_shift, int ln_pad_one, void* stream) {
     SRK_REQUIRE(x && wgt && bias && f0 && xa && g1 && b1 && g2 && b2 && a16, "conv_in_ln: null pointer");
+    SRK_REQUIRE(!ln_pad_one || C + 2 <= ld16, "conv_in_ln: ln_pad_one needs two pad columns");
     SRK_REQUIRE(B > 0 && h > 0 && w > 0 && H >= h && W >= w && H - h < h && W - w < w, "conv_in_ln: bad shape");
     SRK_REQUIRE(H % 8 == 0 && W % 8 == 0 && (win_shift == -1 || win_shift == 0 || win_shift == 4), "conv_in_ln: bad window geometry");
     SRK_REQUIRE(ld32 % 64 == 0 && ld32 == ld16 && ld32 >= C && ld32 <= 256 && C % 2 == 0, "conv_in_ln: channels must be padded to a multiple of 64 (<= 256)");
@@ -553,7 +555,7 @@ extern "C" int srk_conv_in_ln(const float* x, int B, int h, int w, int H, int W,
     const size_t smem = (size_t)10 * ld32 * sizeof(float);
     ProfScope ps(SRK_PROF_CONV_IN, stream);
     cudaStream_t st = (cudaStream_t)stream;
-#define L(NP) conv_in_ln_kernel<NP><<<grid, 256, smem, st>>>(x, B, h, w, H, W, in_scale, wgt, bias, C, f0, xa, ld32, g1, b1, g2, b2, (uint16_t*)a16, ld16, out16_dtype, win_shift)
+#define L(NP) conv_in_ln_kernel<NP><<<grid, 256, smem, st>>>(x, B, h, w, H, W, in_scale, wgt, bias, C, f0, xa, ld32, g1, b1, g2, b2, (uint16_t*)a16, ld16, out16_dtype, win_shift, ln_pad_one)
     switch (ld32 / 64) { case 1: L(1); break; case 2: L(2); break; case 3: L(3); break; default: L(4); break; }
 #undef L
     SRK_LAUNCH_CHECK("conv_in_ln_kernel");

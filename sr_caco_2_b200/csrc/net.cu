@@ -155,10 +155,13 @@ extern "C" int srk_swinir_forward(const srk_swinir_plan* p, const float* x, floa
     int nblk_total = 0;
     for (int l = 0; l < p->n_layers; ++l) nblk_total += p->depths[l];
     const bool first_fused = nblk_total > 0 && p->depths[0] > 0 && Cp <= 256;
+    bool a16_ones_init = false;
     if (first_fused) {
         const srk_stb_params& s0 = p->stbs[0];
+        const int ones0 = !(p->options & SRK_OPT_NO_FOLD_QKV_BIAS) && Cp - C >= 2 && C % 2 == 0 && s0.w_qkv_fb != nullptr;
         TRY(srk_conv_in_ln(x, B, h, w, H, W, p->img_range, p->conv_first_w, p->conv_first_b, C, b.F0, b.XA, Cp,
-                           p->pe_norm_g, p->pe_norm_b, s0.ln1_g, s0.ln1_b, b.A16, Cp, ldt, s0.shift, stream));
+                           p->pe_norm_g, p->pe_norm_b, s0.ln1_g, s0.ln1_b, b.A16, Cp, ldt, s0.shift, ones0, stream));
+        a16_ones_init = ones0 != 0;
     } else {
         TRY(srk_conv_in(x, B, h, w, H, W, p->img_range, p->conv_first_w, p->conv_first_b, C, b.F0, Cp,
                         nullptr, 0, 0, stream));
@@ -172,7 +175,7 @@ extern "C" int srk_swinir_forward(const srk_swinir_plan* p, const float* x, floa
     // qkv bias folded into the GEMM: the LayerNorm epilogue that produces a block's A rows writes 1.0 into the pad
     // columns C, C + 1 and the block's folded weight (w_qkv_fb) carries the bias there -> no bias add in the epilogue
     const bool fold_ok = !(p->options & SRK_OPT_NO_FOLD_QKV_BIAS) && Cp - C >= 2 && C % 2 == 0;
-    bool a16_ones = false;
+    bool a16_ones = a16_ones_init;
     bool final_norm_done = false;
     for (int l = 0; l < p->n_layers; ++l) {
         const float* cur = b.XA;
