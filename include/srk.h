@@ -102,6 +102,9 @@ enum { SRK_MET_PSNR = 0, SRK_MET_MSE = 1, SRK_MET_NRMSE = 2, SRK_MET_SSIM = 3,
        SRK_MET_PSNR_Y = 4, SRK_MET_N = 5 };
 #define SRK_MAX_ROI_THS 8
 size_t srk_metrics_scratch_bytes(int B, int n_ths);
+/* on != 0: the quantised hot path runs the round-1 tile kernel instead of the row-streaming kernel (tests: the two
+ * kernels are cross-checked against each other and against the reference known-answer values) */
+int srk_metrics_use_tile_kernel(int on);
 int srk_metrics(const float* E, const float* H, int B, int Hpx, int Wpx, int border,
                 int quantize, const int* roi_ths, int n_ths, double* out, int32_t* flags,
                 void* scratch, void* stream);

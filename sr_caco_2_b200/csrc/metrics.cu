@@ -526,6 +526,262 @@ metrics_fast_kernel(const FastParams p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Row-streaming version of the hot path (round 2).  A CTA of 128 threads owns a strip of 128 input columns
+// (118 SSIM-map columns) of one image and streams a segment of its rows top to bottom:
+//   vertical pass : thread = column.  The last 12 rows of the four maps (x, y), (x^2 + y^2, x y) live in registers as
+//                   packed fp32x2 pairs (slot = row % 12, static through a 12-row unrolled body); every new row yields
+//                   the column's vertically filtered values with 22 FFMA2, written as one 16 B chunk per column
+//   horizontal    : every 4 rows, thread = (row of the batch, 4 adjacent outputs): 14 chunks stream through a register
+//                   sliding window (88 FFMA2), then the SSIM formula and the ROI-bucket sums
+// sigma_x^2 + sigma_y^2 only ever appears as a sum, so x^2 + y^2 is filtered as ONE map (4 maps instead of 5).
+// Bookkeeping is kept off the FMA-bound path: quantisation rounds with the 1.5 * 2^23 add (same ties-to-even as
+// rintf, and the level is then the low byte of the float's bits: no F2I / I2F / FRND, which run at a quarter of the
+// rate), the ROI bucket of a level comes from a 256-byte table, and the per-bucket sums live in shared memory, one
+// private word per (bucket, thread): squared errors as exact integers packed with their count (sse << 8 | cnt: a
+// thread owns <= 254 rows), SSIM sums as (fp32 sum, count).  The finalize kernel and the scratch layout of the tile
+// version are unchanged.  NRMSE only needs the extrema of the whole cropped target (the ROIs are upper level sets, see
+// the finalize kernel), so every CTA writes the extrema of all pixels it read into the buckets it owns pixels of.
+// ------------------------------------------------------------------------------------------
+constexpr int ST_THREADS = 128;          // input columns per strip
+constexpr int ST_OW = 118;               // SSIM-map columns per strip (128 - 10)
+constexpr int ST_VSTRIDE = 170;          // 16 B chunks per staged row: column c at chunk c + c / 4 (<= 131 + 32 read); the
+                                         // stride (2 mod 8) keeps the (2 groups x 4 rows) of a quarter warp on 8 banks
+constexpr int ST_KROWS = 16, ST_KSTRIDE = 136;   // ring of ROI-bucket rows: column c at byte c + 3 (4-byte aligned reads)
+constexpr float ST_MAGIC = 12582912.f;   // 1.5 * 2^23: t + MAGIC rounds t in [0, 2^22) to an integer, ties to even
+constexpr int ST_MAGIC_BITS = 0x4B400000;
+
+struct StreamParams {
+    FastParams f;
+    int seg_rows;                        // SSIM-map rows per row segment (<= 244)
+};
+
+template <bool H8IN>
+__global__ void __launch_bounds__(ST_THREADS, 4)
+metrics_stream_kernel(const StreamParams sp) {
+    const FastParams& p = sp.f;
+    __shared__ __align__(16) float4 vbuf[2][4][ST_VSTRIDE];         // [buffer][row of the batch][padded column]
+    __shared__ __align__(16) unsigned char kring[ST_KROWS][ST_KSTRIDE];
+    __shared__ __align__(16) unsigned char lut[256];                // level -> ROI bucket (# thresholds <= level)
+    __shared__ unsigned int sacc[MAXV][ST_THREADS];                 // per (bucket, thread): sse << 8 | count of owned pixels
+    __shared__ float2 ssacc[MAXV][ST_THREADS];                      // per (bucket, thread): SSIM sum, count (as bits)
+    __shared__ unsigned long long r_sse[MAXV], r_cnt[MAXV], r_scnt[MAXV];
+    __shared__ double r_ssim[MAXV];
+    __shared__ int r_mn, r_mx;
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int b = blockIdx.x, seg = blockIdx.y, strip = blockIdx.z;   // strips slowest: a ragged (cheap) last strip is scheduled last
+    const int Hc = p.Hpx - 2 * p.border, Wc = p.Wpx - 2 * p.border;
+    const int mapH = Hc - 10, mapW = Wc - 10;
+    const int c0 = strip * ST_OW;                                     // first input / output column of the strip (cropped frame)
+    const int r0 = seg * sp.seg_rows;                                 // first input / output row of the segment
+    const bool last_strip = strip == (int)gridDim.z - 1, last_seg = seg == (int)gridDim.y - 1;
+    const int out_rows = min(sp.seg_rows, mapH - r0);                 // SSIM rows of this segment
+    const int in_rows = out_rows + 10;
+    const int NB = p.n_ths + 1;
+    const float* Eb = p.E + (size_t)b * p.Hpx * p.Wpx;
+    const float* Hb = H8IN ? nullptr : p.H + (size_t)b * p.Hpx * p.Wpx;
+    const unsigned char* H8b = H8IN ? p.H8 + (size_t)b * p.Hpx * p.Wpx : nullptr;
+
+    if (tid < MAXV) { r_sse[tid] = 0ull; r_cnt[tid] = 0ull; r_scnt[tid] = 0ull; r_ssim[tid] = 0.0; }
+    if (tid == 0) { r_mn = 255; r_mx = -1; }
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) { sacc[k][tid] = 0u; ssacc[k][tid] = make_float2(0.f, 0.f); }
+    for (int l = tid; l < 256; l += ST_THREADS) {
+        int kb = 0;
+#pragma unroll
+        for (int t = 0; t < SRK_MAX_ROI_THS; ++t) kb += (t < p.n_ths && (float)l >= p.ths[t]) ? 1 : 0;
+        lut[l] = (unsigned char)kb;
+    }
+
+    // ---- vertical-pass state: this thread's column ----
+    const int col = c0 + tid;                                         // cropped-frame column
+    const bool col_in = col < Wc;
+    // squared errors are owned by exactly one strip / segment (the halo columns / rows belong to the neighbours)
+    const bool col_owned = col_in && (tid < ST_OW || last_strip);
+    const int own_rows = col_owned ? (last_seg ? in_rows : sp.seg_rows) : 0;
+    // rows past the segment / columns past the image re-read the last valid pixel: they only feed masked outputs, and
+    // a real pixel keeps the extrema and the non-finite test right without a predicate on the load
+    const size_t col_off = (size_t)(p.border + r0) * p.Wpx + (size_t)(col_in ? col : Wc - 1) + p.border;
+    const float* Ec = Eb + col_off;                                   // row i of the segment: + i * Wpx (32-bit: Hpx * Wpx < 2^31 is checked at launch)
+    const float* Hcp = H8IN ? nullptr : Hb + col_off;
+    const unsigned char* H8c = H8IN ? H8b + col_off : nullptr;
+    const bool v_active = c0 + (tid & ~31) < Wc;                      // warp-uniform: any column of this warp inside the image
+    uint64_t ring[12][2];                                             // [row % 12][(x, y) | (x^2 + y^2, x y)]
+#pragma unroll
+    for (int j = 0; j < 12; ++j) { ring[j][0] = 0ull; ring[j][1] = 0ull; }
+    int hmin = ST_MAGIC_BITS + 255, hmax = ST_MAGIC_BITS - 1;         // extrema of the target's float bits (monotonic in the level)
+    float nf = 0.f;                                                   // sum of 0 * pixel: NaN iff any pixel read was NaN / Inf
+    uint64_t g2[11];
+#pragma unroll
+    for (int k = 0; k < 11; ++k) g2[k] = dup2(c_gauss[k]);
+    unsigned int* my_sacc = &sacc[0][tid];
+    float2* my_ssacc = &ssacc[0][tid];
+
+    // ---- horizontal-pass state: (row of the batch, 4 adjacent outputs); a warp = 8 groups x 4 rows ----
+    const int hrow = tid & 3, hgrp = tid >> 2;
+    const bool h_active = c0 + 4 * (hgrp & ~7) < mapW && 4 * (hgrp & ~7) < ST_OW;     // warp-uniform
+    unsigned int omask = 0;                                           // which of this thread's 4 outputs exist
+#pragma unroll
+    for (int o = 0; o < 4; ++o) omask |= (4 * hgrp + o < ST_OW && c0 + 4 * hgrp + o < mapW) ? (1u << o) : 0u;
+
+    // raw pixels of the next batch of 4 rows (requested one batch ahead)
+    float e_nx[4];
+    float h_nx[4];
+    unsigned int h8_nx[4];
+    auto request = [&](int i0) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int off = min(i0 + u, in_rows - 1) * p.Wpx;
+            e_nx[u] = __ldg(Ec + off);
+            if (H8IN) h8_nx[u] = __ldg(H8c + off); else h_nx[u] = __ldg(Hcp + off);
+        }
+    };
+    if (v_active) request(0);
+    __syncthreads();
+
+    for (int base = 0; base < in_rows; base += 12) {
+#pragma unroll
+        for (int bq = 0; bq < 3; ++bq) {                              // three batches of 4 rows = one turn of the 12-row ring
+            const int i0 = base + 4 * bq;
+            if (i0 >= in_rows) break;
+            const int buf = (i0 >> 2) & 1;
+            // ---------------- vertical pass: 4 rows ----------------
+            if (v_active) {
+                float e_cur[4], h_cur[4];
+                unsigned int h8_cur[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { e_cur[u] = e_nx[u]; if (H8IN) h8_cur[u] = h8_nx[u]; else h_cur[u] = h_nx[u]; }
+                request(i0 + 4);
+                unsigned char* krow = &kring[i0 & (ST_KROWS - 1)][tid + 3];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = 4 * bq + u;                         // ring slot (static)
+                    // tensor2uint82float (utils_image.py:369-372): (x.clamp(0,1) * 255).round()
+                    nf = fmaf(e_cur[u], 0.f, nf);
+                    const float em = __fadd_rn(__fmul_rn(__saturatef(e_cur[u]), 255.f), ST_MAGIC);
+                    const int be = __float_as_int(em);
+                    int bh;
+                    float hm;
+                    if (H8IN) {
+                        bh = ST_MAGIC_BITS | (int)h8_cur[u];
+                        hm = __int_as_float(bh);
+                    } else {
+                        nf = fmaf(h_cur[u], 0.f, nf);
+                        hm = __fadd_rn(__fmul_rn(__saturatef(h_cur[u]), 255.f), ST_MAGIC);
+                        bh = __float_as_int(hm);
+                    }
+                    const int kb = lut[bh & 0xff];
+                    krow[u * ST_KSTRIDE] = (unsigned char)kb;
+                    const int d = be - bh;
+                    const unsigned int w = (i0 + u < own_rows) ? (unsigned int)(d * d) * 256u + 1u : 0u;
+                    atomicAdd(my_sacc + kb * ST_THREADS, w);          // private word: no contention, no read-back dependency
+                    hmin = min(hmin, bh); hmax = max(hmax, bh);
+                    const float x = div255(__fadd_rn(em, -ST_MAGIC)), y = div255(__fadd_rn(hm, -ST_MAGIC));
+                    ring[j][0] = pack64(__float_as_uint(x), __float_as_uint(y));
+                    ring[j][1] = pack64(__float_as_uint(fmaf(x, x, y * y)), __float_as_uint(x * y));
+                    // vertically filtered values of output row i - 10 (rows i-10 .. i = slots j+2 .. j+12 mod 12)
+                    uint64_t v0 = 0ull, v1 = 0ull;
+#pragma unroll
+                    for (int k = 0; k < 11; ++k) {
+                        const int sl = (j + 2 + k) % 12;
+                        v0 = fma2(g2[k], ring[sl][0], v0);
+                        v1 = fma2(g2[k], ring[sl][1], v1);
+                    }
+                    uint32_t a0, a1, a2, a3;
+                    unpack64(v0, a0, a1); unpack64(v1, a2, a3);
+                    vbuf[buf][u][tid + (tid >> 2)] = make_float4(__uint_as_float(a0), __uint_as_float(a1), __uint_as_float(a2), __uint_as_float(a3));
+                }
+            }
+            __syncthreads();
+            // ---------------- horizontal pass + SSIM: output row (i0 + hrow - 10), columns 4 hgrp .. 4 hgrp + 3 ----------------
+            const int orow = i0 + hrow - 10;
+            if (h_active && orow >= 0 && orow < out_rows && omask) {
+                uint64_t acc[4][2];
+#pragma unroll
+                for (int o = 0; o < 4; ++o) { acc[o][0] = 0ull; acc[o][1] = 0ull; }
+                const float4* vrow = &vbuf[buf][hrow][5 * hgrp];      // column 4 hgrp + k sits at chunk 5 hgrp + k + k / 4
+#pragma unroll
+                for (int k = 0; k < 14; ++k) {
+                    const float4 ch = vrow[k + (k >> 2)];
+                    const uint64_t w0 = pack64(__float_as_uint(ch.x), __float_as_uint(ch.y));
+                    const uint64_t w1 = pack64(__float_as_uint(ch.z), __float_as_uint(ch.w));
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) {
+                        const int tap = k - o;
+                        if (tap >= 0 && tap < 11) {
+                            acc[o][0] = fma2(g2[tap], w0, acc[o][0]);
+                            acc[o][1] = fma2(g2[tap], w1, acc[o][1]);
+                        }
+                    }
+                }
+                // ROI buckets of the 4 window centres: input row orow + 5, columns 4 hgrp + 5 .. + 8 (bytes 4 hgrp + 8 .. of the row)
+                const unsigned int kb4 = *reinterpret_cast<const unsigned int*>(&kring[(i0 + hrow - 5) & (ST_KROWS - 1)][4 * hgrp + 8]);
+                float ss[4];
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                    uint32_t u0, u1, u2, u3;
+                    unpack64(acc[o][0], u0, u1); unpack64(acc[o][1], u2, u3);
+                    const float mxm = __uint_as_float(u0), mym = __uint_as_float(u1);
+                    const float ess = __uint_as_float(u2), exy = __uint_as_float(u3);
+                    const float c1 = 1e-4f, c2 = 9e-4f;
+                    const float mxx = mxm * mxm, myy = mym * mym, mxy = mxm * mym;
+                    const float svar = (ess - mxx) - myy, sxy = exy - mxy;
+                    float rden;                                       // denominator >= c1 * c2 = 9e-8: no denormal fix-up needed
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rden) : "f"((mxx + myy + c1) * (svar + c2)));
+                    const float v = (2.f * mxy + c1) * (2.f * sxy + c2) * rden;
+                    ss[o] = (omask >> o & 1u) ? v : 0.f;
+                }
+                if (kb4 == (kb4 & 0xffu) * 0x01010101u) {             // one bucket (the common case inside / outside a ROI)
+                    float2* a = my_ssacc + (kb4 & 0xffu) * ST_THREADS;
+                    float2 t = *a;
+                    t.x += (ss[0] + ss[1]) + (ss[2] + ss[3]);
+                    t.y = __uint_as_float(__float_as_uint(t.y) + __popc(omask));
+                    *a = t;
+                } else {
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) {
+                        float2* a = my_ssacc + ((kb4 >> (8 * o)) & 0xffu) * ST_THREADS;
+                        float2 t = *a;
+                        t.x += ss[o];
+                        t.y = __uint_as_float(__float_as_uint(t.y) + (omask >> o & 1u));
+                        *a = t;
+                    }
+                }
+            }
+            // (the other buffer is written by the next batch; this one is rewritten two batches later, after the next barrier)
+        }
+    }
+    if (__any_sync(0xffffffffu, !(nf == 0.f)) && lane == 0) atomicOr(&p.flags[b], 1);
+    __syncthreads();                                                  // sacc atomics of the last batch
+
+    // ---- reduction: warp -> shared atomics -> one global atomic per quantity ----
+    if (!v_active) { hmin = ST_MAGIC_BITS + 255; hmax = ST_MAGIC_BITS - 1; }
+    const int wmn = __reduce_min_sync(0xffffffffu, hmin) - ST_MAGIC_BITS, wmx = __reduce_max_sync(0xffffffffu, hmax) - ST_MAGIC_BITS;
+    if (lane == 0) { atomicMin(&r_mn, wmn); atomicMax(&r_mx, wmx); }
+    for (int k = 0; k < NB; ++k) {
+        const unsigned int w = sacc[k][tid];
+        const float2 sv = ssacc[k][tid];
+        const unsigned int c_ = __reduce_add_sync(0xffffffffu, w & 0xffu);
+        const unsigned int s_ = __reduce_add_sync(0xffffffffu, w >> 8);      // <= 32 * 254 * 65025 fits 32 bits
+        const unsigned int sc_ = __reduce_add_sync(0xffffffffu, __float_as_uint(sv.y));
+        float f_ = sv.x;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) f_ += __shfl_xor_sync(0xffffffffu, f_, o);
+        if (lane == 0) {
+            if (c_) { atomicAdd(&r_cnt[k], (unsigned long long)c_); atomicAdd(&r_sse[k], (unsigned long long)s_); }
+            if (sc_) { atomicAdd(&r_scnt[k], (unsigned long long)sc_); atomicAdd(&r_ssim[k], (double)f_); }
+        }
+    }
+    __syncthreads();
+    if (tid < NB) {
+        BucketAcc* a = p.acc + (size_t)b * MAXV + tid;
+        if (r_cnt[tid]) { atomicAdd(&a->cnt, r_cnt[tid]); atomicAdd(&a->sse, r_sse[tid]);
+                          atomicMin(&a->mn, r_mn); atomicMax(&a->mx, r_mx); }
+        if (r_scnt[tid]) { atomicAdd(&a->scnt, r_scnt[tid]); atomicAdd(&a->ssim, r_ssim[tid]); }
+    }
+}
+
 __global__ void metrics_fast_finalize_kernel(const BucketAcc* acc, int B, int n_ths, int Hc, int Wc,
                                              double* out, int32_t* flags) {
     const int NV = n_ths + 1;
@@ -577,6 +833,15 @@ __global__ void metrics_fast_finalize_kernel(const BucketAcc* acc, int B, int n_
     if (f) atomicOr(&flags[b], f);
 }
 
+bool g_metrics_tile_path = false;            // srk_metrics_use_tile_kernel(): tests compare the two hot-path kernels
+int g_metrics_ctas_per_sm = 6;               // row segments are sized for this many streaming CTAs per SM (bits 8.. of the same call)
+static int num_sms_metrics() {
+    int dev = 0, v = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v;
+}
+
 static int upload_gauss() {
     static bool done[64] = {false};
     int dev = 0;
@@ -617,6 +882,7 @@ static int run_metrics(const float* E, const float* H, const float* roi, int B, 
     SRK_REQUIRE(Hc >= 11 && Wc >= 11,
                 "metrics: kernel size can't be greater than actual input size (%dx%d after border %d)",
                 Hc, Wc, border);
+    SRK_REQUIRE((long long)Hpx * Wpx < (1ll << 31), "metrics: image too large (%dx%d)", Hpx, Wpx);
     if (int rc = upload_gauss()) return rc;
     bool sorted = true;
     for (int i = 1; i < n_ths; ++i) sorted = sorted && roi_ths[i] > roi_ths[i - 1];
@@ -631,15 +897,33 @@ static int run_metrics(const float* E, const float* H, const float* roi, int B, 
         SRK_CUDA(cudaMemsetAsync(flags, 0, sizeof(int32_t) * B, st));
         metrics_fast_init_kernel<<<ceil_div((long long)B * MAXV, 128), 128, 0, st>>>(fp.acc, B * MAXV);
         SRK_LAUNCH_CHECK("metrics_fast_init_kernel");
-        const size_t smem = sizeof(float) * (2 * MH * (MH + 2) + 5 * MH * (MT + 1)) + MH * MH;
-        static bool attr[64] = {};
-        if (first_use_on_device(attr)) {
-            SRK_CUDA(cudaFuncSetAttribute(metrics_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            SRK_CUDA(cudaFuncSetAttribute(metrics_fast_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        if (g_metrics_tile_path) {                     // round-1 tile kernel: kept as the in-library cross-check of the streaming kernel
+            const size_t smem = sizeof(float) * (2 * MH * (MH + 2) + 5 * MH * (MT + 1)) + MH * MH;
+            static bool attr[64] = {};
+            if (first_use_on_device(attr)) {
+                SRK_CUDA(cudaFuncSetAttribute(metrics_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                SRK_CUDA(cudaFuncSetAttribute(metrics_fast_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            }
+            dim3 grid(ceil_div(Wc, MT), ceil_div(Hc, MT), B);
+            metrics_fast_kernel<<<grid, NTHREADS, smem, st>>>(fp);
+            SRK_LAUNCH_CHECK("metrics_fast_kernel");
+        } else {
+            // streaming kernel: strips of 118 SSIM columns x row segments; segments sized for ~6 CTAs per SM (4 resident: the
+            // rest balances the SMs; measured 82 / 77 / 76 / 78 us at 4 / 5 / 6 / 8 for 32 x 512 x 512), <= 244 rows each
+            const int mapH = Hc - 10, mapW = Wc - 10;
+            const int strips = ceil_div(mapW, ST_OW);
+            int nseg = ceil_div(g_metrics_ctas_per_sm * num_sms_metrics(), (long long)strips * B);
+            if (nseg < ceil_div(mapH, 244)) nseg = ceil_div(mapH, 244);
+            if (nseg > ceil_div(mapH, 32)) nseg = ceil_div(mapH, 32);
+            if (nseg < 1) nseg = 1;
+            StreamParams sp{};
+            sp.f = fp;
+            sp.seg_rows = ceil_div(mapH, nseg);
+            dim3 grid(B, ceil_div(mapH, sp.seg_rows), strips);
+            if (H8) metrics_stream_kernel<true><<<grid, ST_THREADS, 0, st>>>(sp);
+            else metrics_stream_kernel<false><<<grid, ST_THREADS, 0, st>>>(sp);
+            SRK_LAUNCH_CHECK("metrics_stream_kernel");
         }
-        dim3 grid(ceil_div(Wc, MT), ceil_div(Hc, MT), B);
-        metrics_fast_kernel<<<grid, NTHREADS, smem, st>>>(fp);
-        SRK_LAUNCH_CHECK("metrics_fast_kernel");
         metrics_fast_finalize_kernel<<<ceil_div((long long)B * (n_ths + 1), 128), 128, 0, st>>>(fp.acc, B, n_ths, Hc, Wc, out, flags);
         SRK_LAUNCH_CHECK("metrics_fast_finalize_kernel");
         return 0;
@@ -667,6 +951,12 @@ static int run_metrics(const float* E, const float* H, const float* roi, int B, 
 }
 
 }  // namespace srk
+
+extern "C" int srk_metrics_use_tile_kernel(int on) {
+    srk::g_metrics_tile_path = (on & 1) != 0;
+    srk::g_metrics_ctas_per_sm = (on >> 8) > 0 ? (on >> 8) : 6;
+    return 0;
+}
 
 extern "C" size_t srk_metrics_scratch_bytes(int B, int n_ths) {
     const int NV = 1 + (n_ths < 0 ? 0 : n_ths);

@@ -156,6 +156,41 @@ def test_metrics_full_size_properties(L):
     np.testing.assert_allclose(m1["ssim"][:2].cpu(), sub["ssim"].double(), atol=2e-6)
 
 
+@pytest.mark.parametrize("shape", [(1, 11, 11, 0), (2, 12, 139, 0), (3, 140, 128, 0), (2, 129, 131, 1), (1, 300, 250, 3),
+                                   (2, 534, 260, 8), (5, 64, 64, 8), (1, 1040, 47, 2)])
+def test_metrics_streaming_kernel_geometries(L, shape):
+    """The row-streaming hot-path kernel against (a) the round-1 tile kernel: integer sums (PSNR / MSE / NRMSE of
+    every ROI variant) bit-identical, SSIM within fp32 summation noise; (b) the oracle.  Geometries: a single 11 x 11
+    window, widths that leave a ragged / one-column last strip, heights that need several row segments (> 244 map
+    rows), 8 ROI thresholds (9 buckets: the packed counters of the kernel)."""
+    from sr_caco_2_b200 import utils_image as UI
+    B, Hh, Ww, border = shape
+    E, H = T.synthetic_pair(B, Hh, Ww, 900 + Hh)
+    ths = (1, 3, 5, 8, 13, 40, 90, 200)
+    lib = L.load()
+    try:
+        lib.srk_metrics_use_tile_kernel(1)
+        tile = UI.compute_metrics(E.to(DEV), H.to(DEV), border, ths, check=False)["raw"].cpu()
+    finally:
+        lib.srk_metrics_use_tile_kernel(0)
+    got = UI.compute_metrics(E.to(DEV), H.to(DEV), border, ths, check=False)["raw"].cpu()
+    h8 = UI.compute_metrics(E.to(DEV), (H * 255).round().clamp(0, 255).to(torch.uint8).to(DEV), border, ths, check=False)["raw"].cpu()
+    for i in (0, 1, 2, 4):                                  # psnr, mse, nrmse, psnr_y: exact integer sums underneath
+        assert torch.equal(got[..., i], tile[..., i]), i
+        assert torch.equal(h8[..., i], tile[..., i]), i
+    assert float((got[..., 3] - tile[..., 3]).abs().max()) < 1e-5          # a single-window map has no averaging
+    assert float((h8[..., 3] - got[..., 3]).abs().max()) == 0.0
+    om = O.all_metrics(E, H, border)
+    np.testing.assert_allclose(got[:, 0, 0], om["psnr"], rtol=1e-10)
+    np.testing.assert_allclose(got[:, 0, 2], om["nrmse"], rtol=1e-10)
+    np.testing.assert_allclose(got[:, 0, 3], om["ssim"].double(), atol=2e-5)
+    for v, th in ((2, 3), (6, 40)):
+        orm = O.all_metrics(E, H, border, th)
+        np.testing.assert_allclose(got[:, v, 0], orm["psnr"], rtol=1e-10)
+        np.testing.assert_allclose(got[:, v, 2], orm["nrmse"], rtol=1e-10)
+        np.testing.assert_allclose(got[:, v, 3], orm["ssim"].double(), atol=2e-5)
+
+
 # ------------------------------------------------------------------------------------------
 # building blocks
 # ------------------------------------------------------------------------------------------
