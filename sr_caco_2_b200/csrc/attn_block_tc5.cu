@@ -46,7 +46,7 @@ constexpr int AB_AO_OFF = AB_W_OFF + AB_NW * AB_WSLOT;
 constexpr int AB_STG_OFF = AB_AO_OFF + AB_KB * 16384;
 constexpr int AB_BAR_OFF = AB_STG_OFF + 2 * AB_STG;
 constexpr int AB_TAB = (AB_NH * 225 * 4 + 15) / 16 * 16;         // rel-pos tables, padded to 16 B
-constexpr int AB_AUX = 256 + AB_TAB + 256 + AB_CP * 4;   // barriers, rel-pos tables, shift-mask labels, proj bias
+constexpr int AB_AUX = 256 + AB_TAB + 256 + AB_CP * 4 + 128;   // barriers, rel-pos tables, shift-mask labels, proj bias, window geometry
 constexpr size_t AB_SMEM = (size_t)AB_BAR_OFF + AB_AUX;         // the dynamic shared memory window itself is 1024 B aligned
 static_assert(64 * AB_SROW32 * 4 <= 2 * AB_STG, "the fp32 staging of the final stage aliases the two bf16 staging tiles");
 static_assert(AB_SMEM <= 232448, "shared memory plan exceeds the 227 KB per-CTA limit");
@@ -80,6 +80,7 @@ attn_block_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     float* stab = reinterpret_cast<float*>(sm + AB_BAR_OFF + 256);                    // [heads][225]
     unsigned char* slab = sm + AB_BAR_OFF + 256 + AB_TAB;                   // [group][window][64] region labels
     float* sbp = reinterpret_cast<float*>(slab + 256);                               // [192] proj bias
+    int4* sgeo_all = reinterpret_cast<int4*>(slab + 256 + AB_CP * 4);                 // [group][tile parity][window]: see WinGeo
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_my = (int)blockIdx.x < p.m_tiles ? (p.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -214,19 +215,33 @@ attn_block_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         // ---- head unit: head h of tile iteration it (job index 6 it + h) ----
         // per tile, once per group: the shift-mask region labels of the tile's two windows (threads 0..127 of the group;
         // the group barrier inside the tile's first unit publishes them) and this warp's window flags
+        // Window geometry (two integer divisions per window) is worked out ONCE per tile and group, by two threads, an
+        // iteration ahead (compute_geo(it + 1) runs after the final stage of tile it - 1, whose slot it reuses, and is
+        // published by the group barriers of the units that follow); everybody else reads the 16 B record.
+        //   x: first token row of the window's image, or -1 beyond the problem   y, z: window origin (rows, columns)
+        //   w: 1 if the shift mask applies (last window row / column of a shifted block)
+        int4* sgeo = sgeo_all + grp * 4;
+        auto compute_geo = [&](int it, int tile) {
+            const int tg = gw * 32 + lane;
+            if (tg < 2) {
+                const int wg = tile * 2 + tg;
+                const int bi = wg / nW, win = wg - bi * nW;
+                const int wi = win / wpr, wj = win - wi * wpr;
+                sgeo[(it & 1) * 2 + tg] = make_int4((long long)wg * 64 < p.M ? bi * p.T : -1, wi << 3, wj << 3,
+                                                    (p.shift > 0 && (wi == nWy - 1 || wj == wpr - 1)) ? 1 : 0);
+            }
+        };
         bool w_valid = false, w_masked = false;
-        auto tile_setup = [&](int tile) {
+        auto tile_setup = [&](int it) {
             const int tg = gw * 32 + lane;
             if (tg < 128) {
-                const int wg = tile * 2 + (tg >> 6);
-                const int win = wg % nW, wi = win / wpr, wj = win - wi * wpr;
-                const bool m_any = p.shift > 0 && (wi == nWy - 1 || wj == wpr - 1);
-                lab[tg] = (unsigned char)(m_any ? win_pos_label(win, tg & 63, p.H, p.W, p.shift) : 0);
+                const int4 g = sgeo[(it & 1) * 2 + (tg >> 6)];
+                const int pos = tg & 63;
+                lab[tg] = (unsigned char)(g.w ? region_label(g.y + (pos >> 3), p.H, p.shift) * 3 + region_label(g.z + (pos & 7), p.W, p.shift) : 0);
             }
-            const int wg2 = tile * 2 + window;
-            const int win2 = wg2 % nW, wi2 = win2 / wpr, wj2 = win2 - wi2 * wpr;
-            w_valid = (long long)wg2 * 64 < p.M;
-            w_masked = p.shift > 0 && (wi2 == nWy - 1 || wj2 == wpr - 1);
+            const int4 g2 = sgeo[(it & 1) * 2 + window];
+            w_valid = g2.x >= 0;
+            w_masked = g2.w != 0;
         };
         auto unit = [&](int it, int h) {
             const int j = it * AB_NH + h, s = j % 3;
@@ -282,13 +297,10 @@ attn_block_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         auto pack = [&](float a, float b) { return o_bf16 ? packf<SRK_BF16>(a, b) : packf<SRK_FP16>(a, b); };
         // per-window geometry of a tile (uniform over the CTA): image base row, window origin in the shifted frame
         struct WinGeo { int base, y0, x0; };                          // base < 0: the window lies beyond the problem
-        auto win_geo = [&](int tile, int half) {
+        auto win_geo = [&](int it, int half) {
+            const int4 r = sgeo[(it & 1) * 2 + half];
             WinGeo g;
-            const int wg = tile * 2 + half;
-            const int bi = wg / nW, win = wg - bi * nW;
-            const int wi = win / wpr, wj = win - wi * wpr;
-            g.base = (long long)wg * 64 < p.M ? bi * p.T : -1;
-            g.y0 = (wi << 3) + p.shift; g.x0 = (wj << 3) + p.shift;
+            g.base = r.x; g.y0 = r.y + p.shift; g.x0 = r.z + p.shift;
             return g;
         };
         // token row (fp32 stream / LN2 output) of this lane's row rr (0, 1) of a window, or -1
@@ -300,10 +312,10 @@ attn_block_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             return g.base < 0 ? -1 : g.base + y * p.W + x;
         };
         // L2 prefetch of the residual rows a tile's final stage will read (issued a whole unit ahead: no registers held)
-        auto prefetch_res = [&](int tile) {
+        auto prefetch_res = [&](int it) {
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-                const WinGeo g = win_geo(tile, half);
+                const WinGeo g = win_geo(it, half);
 #pragma unroll
                 for (int rr = 0; rr < 2; ++rr) {
                     const int row = token_row(g, rr);
@@ -312,7 +324,7 @@ attn_block_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 }
             }
         };
-        auto final_stage = [&](int tp, int tile) {
+        auto final_stage = [&](int tp) {
             // LayerNorm parameters of this lane's columns (requested before the waits below)
             float4 gg[AB_KB], bt[AB_KB];
 #pragma unroll
@@ -328,7 +340,7 @@ attn_block_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             float4 resa[2][2][AB_KB];
             int rows_[2][2];
             auto request_res = [&](int half) {
-                const WinGeo geo = win_geo(tile, half);
+                const WinGeo geo = win_geo(tp, half);
 #pragma unroll
                 for (int rr = 0; rr < 2; ++rr) {
                     rows_[half][rr] = token_row(geo, rr);
@@ -428,17 +440,19 @@ attn_block_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         };
 
         // per tile: first head unit, then (both groups together) the final stage of the PREVIOUS tile, then the other two units
-        int tile = blockIdx.x, prev_tile = 0;
+        int tile = blockIdx.x;
+        compute_geo(0, tile);
+        asm volatile("bar.sync %0, 256;" ::"r"(bar_g) : "memory");
 #pragma unroll 1
         for (int it = 0; it <= n_my; ++it, tile += gridDim.x) {
-            if (it < n_my) { tile_setup(tile); unit(it, grp); }
-            if (it > 0) final_stage(it - 1, prev_tile);
+            if (it < n_my) { tile_setup(it); unit(it, grp); }
+            if (it > 0) final_stage(it - 1);
             if (it < n_my) {
-                prefetch_res(tile);
+                compute_geo(it + 1, tile + gridDim.x);
+                prefetch_res(it);
                 unit(it, grp + 2);
                 unit(it, grp + 4);
             }
-            prev_tile = tile;
         }
     }
     tc_fence_before();
