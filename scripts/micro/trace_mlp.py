@@ -32,9 +32,9 @@ lib.srk_debug_mlp_trace.restype = C.c_int
 assert lib.srk_debug_mlp_trace(buf) == 0
 v = list(buf)
 t0 = min(x for x in v if x > 0)
-names = {0: "MMA  q  [loop top, fc1(q+2) issued, before w_full, fc2 issue]", 1: "GELU q  [wait d1, d1 ready, loads done, h_full]", 2: "FIN  t  [wait d2, d2 ready, half0 done, half1 done]"}
+names = {0: "MMA  q  [loop top, fc1(q+2) issued, before w_full, fc2 issue | fc1: d1_empty ok, w_full ok]", 1: "GELU q  [wait d1, d1 ready, loads done, h_full | h_empty ok, piece0 done, piece1 load ok, piece1 done]", 2: "FIN  t  [wait d2, d2 ready, half0 done, half1 done]"}
 for role in (0, 1, 2):
     print(names[role])
     for i in range(44):
-        e = v[(role * 64 + i) * 8:(role * 64 + i) * 8 + 4]
+        e = v[(role * 64 + i) * 8:(role * 64 + i) * 8 + 8]
         if any(e): print(f"  {i:3d} " + " ".join(f"{(x - t0) if x else -1:8d}" for x in e))

@@ -182,25 +182,30 @@ mlp_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
     } else if (warp == 1) {
         // ===================================== MMA issuer =====================================
-        if (lane == 0) {
+        {   // the whole warp runs the loop (uniform control flow); one elected lane issues the MMAs and commits
             const uint32_t idesc1 = umma_idesc(1, 128, ML_CH), idesc2 = umma_idesc(1, 128, CP);
             int ws = 0, wph = 0, tc = 0;
             int d1s = 0, d1ph = 0, hs = 0, hph = 0;
             auto w_next = [&]() { if (++ws == ML_NW) { ws = 0; wph ^= 1; } };
+            int trq = 0;
             auto fc1 = [&]() {
                 mbar_wait(d1_empty(d1s), d1ph ^ 1);
+                ML_TR(0, trq, 4);
                 mbar_wait(w_full(ws), wph);
+                ML_TR(0, trq, 5);
                 tc_fence_after();
 #pragma unroll
                 for (int kb = 0; kb < KB1; ++kb) {
                     const uint64_t da = umma_desc_sw128(sA + kb * 16384), db = umma_desc_sw128(sW + ws * Cfg::WSLOT + kb * 8192);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        tc_mma_f16(tD1 + d1s * ML_CH, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc1, (kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < 4; ++k)
+                            tc_mma_f16(tD1 + d1s * ML_CH, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc1, (kb | k) != 0 ? 1u : 0u);
+                    }
                 }
-                tc_commit(w_empty(ws));
+                if (elect_one()) { tc_commit(w_empty(ws)); tc_commit(d1_full(d1s)); }
+                __syncwarp();
                 w_next();
-                tc_commit(d1_full(d1s));
                 if (++d1s == 2) { d1s = 0; d1ph ^= 1; }
             };
             const int n_my = (int)blockIdx.x < p.m_tiles ? (p.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -211,12 +216,14 @@ mlp_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const int c = q % NC, ti = q / NC;
                 if (c == 0) { mbar_wait(a_full, ti & 1); tc_fence_after(); }
                 fc1();
-                if (c == NC - 1) tc_commit(a_empty);
+                if (c == NC - 1 && elect_one()) tc_commit(a_empty);
+                __syncwarp();
             };
             if (Q > 0) fc1_q(0);
             if (Q > 1) fc1_q(1);
             for (int q = 0; q < Q; ++q) {
                 ML_TR(0, q, 0);
+                trq = q;
                 if (q + 2 < Q) fc1_q(q + 2);                      // two chunks ahead, also across the tile boundary
                 ML_TR(0, q, 1);
                 const int c = q % NC, ti = q / NC;
@@ -229,14 +236,17 @@ mlp_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 tc_fence_after();
                 ML_TR(0, q, 3);
                 const uint64_t da = umma_desc_sw128(sH + hs * 16384), db = umma_desc_sw128(sW + ws * Cfg::WSLOT);
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    tc_mma_f16(d2, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2, (c | k) != 0 ? 1u : 0u);
-                tc_commit(w_empty(ws));
+                    for (int k = 0; k < 4; ++k)
+                        tc_mma_f16(d2, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2, (c | k) != 0 ? 1u : 0u);
+                    tc_commit(w_empty(ws));
+                    tc_commit(h_empty(hs));
+                    if (c == NC - 1) tc_commit(d2_full(ti & 1));
+                }
+                __syncwarp();
                 w_next();
-                tc_commit(h_empty(hs));
                 if (++hs == ML_NH) { hs = 0; hph ^= 1; }
-                if (c == NC - 1) tc_commit(d2_full(ti & 1));
             }
             (void)tc;
         }
@@ -284,12 +294,16 @@ mlp_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tc_wait_ld16(va);
             tc_ld16_nowait(t_row + 16, vb);
             mbar_wait(h_empty(hs), (hu & 1) ^ 1);                    // fc2 of the previous user of this H stage retired
+            if (lg == 0) ML_TR(1, q, 4);
             const float* bias = sb1 + c * ML_CH;
             unsigned char* hrow = ml_smem_raw + (sH - raw) + hs * 16384 + r * 128;
             convert(va, bias, hrow, 0);
+            if (lg == 0) ML_TR(1, q, 5);
             tc_wait_ld16(vb);
             tc_ld16_nowait(t_row + 32, va);
+            if (lg == 0) ML_TR(1, q, 6);
             convert(vb, bias + 16, hrow, 1);
+            if (lg == 0) ML_TR(1, q, 7);
             tc_wait_ld16(va);
             tc_ld16_nowait(t_row + 48, vb);
             convert(va, bias + 32, hrow, 2);
