@@ -31,6 +31,14 @@
 
 namespace srk {
 
+#ifdef SRK_AB_TRACE
+// experiment builds only (scripts/micro/trace_ab.py): per-role clock64 stamps of CTA 0
+__device__ long long g_ab_trace[4 * 64 * 8];
+#define AB_TR(role, idx, ev) do { if (blockIdx.x == 0 && lane == 0 && (idx) < 64) g_ab_trace[((role) * 64 + (idx)) * 8 + (ev)] = clock64(); } while (0)
+#else
+#define AB_TR(role, idx, ev) do { } while (0)
+#endif
+
 constexpr int AB_CP = 192;                  // padded embedding = heads * 32 (the only instantiation: 6 heads)
 constexpr int AB_KB = AB_CP / 64;
 constexpr int AB_NH = 6;
@@ -46,7 +54,7 @@ constexpr int AB_AO_OFF = AB_W_OFF + AB_NW * AB_WSLOT;
 constexpr int AB_STG_OFF = AB_AO_OFF + AB_KB * 16384;
 constexpr int AB_BAR_OFF = AB_STG_OFF + 2 * AB_STG;
 constexpr int AB_TAB = (AB_NH * 225 * 4 + 15) / 16 * 16;         // rel-pos tables, padded to 16 B
-constexpr int AB_AUX = 256 + AB_TAB + 256 + AB_CP * 4 + 128;   // barriers, rel-pos tables, shift-mask labels, proj bias, window geometry
+constexpr int AB_AUX = 256 + AB_TAB + 256 + AB_CP * 4 + 192;   // barriers, rel-pos tables, shift-mask labels, proj bias, window geometry
 constexpr size_t AB_SMEM = (size_t)AB_BAR_OFF + AB_AUX;         // the dynamic shared memory window itself is 1024 B aligned
 static_assert(64 * AB_SROW32 * 4 <= 2 * AB_STG, "the fp32 staging of the final stage aliases the two bf16 staging tiles");
 static_assert(AB_SMEM <= 232448, "shared memory plan exceeds the 227 KB per-CTA limit");
@@ -80,7 +88,7 @@ attn_block_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     float* stab = reinterpret_cast<float*>(sm + AB_BAR_OFF + 256);                    // [heads][225]
     unsigned char* slab = sm + AB_BAR_OFF + 256 + AB_TAB;                   // [group][window][64] region labels
     float* sbp = reinterpret_cast<float*>(slab + 256);                               // [192] proj bias
-    int4* sgeo_all = reinterpret_cast<int4*>(slab + 256 + AB_CP * 4);                 // [group][tile parity][window]: see WinGeo
+    int4* sgeo_all = reinterpret_cast<int4*>(slab + 256 + AB_CP * 4);                 // [group][tile iteration % 3][window]: see compute_geo
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_my = (int)blockIdx.x < p.m_tiles ? (p.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -90,7 +98,7 @@ attn_block_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         for (int s = 0; s < AB_NW; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
         for (int s = 0; s < 3; ++s) { mbar_init(q_full(s), 1); mbar_init(q_empty(s), 8); }
         mbar_init(ao_full, 8 * AB_NH); mbar_init(ao_empty, 1);
-        mbar_init(pd_full, 1); mbar_init(pd_empty, 16);
+        mbar_init(pd_full, 1); mbar_init(pd_empty, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wq) : "memory");
@@ -216,18 +224,18 @@ attn_block_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         // per tile, once per group: the shift-mask region labels of the tile's two windows (threads 0..127 of the group;
         // the group barrier inside the tile's first unit publishes them) and this warp's window flags
         // Window geometry (two integer divisions per window) is worked out ONCE per tile and group, by two threads, an
-        // iteration ahead (compute_geo(it + 1) runs after the final stage of tile it - 1, whose slot it reuses, and is
-        // published by the group barriers of the units that follow); everybody else reads the 16 B record.
+        // iteration ahead (three slots: tile it + 1 is written while tiles it and it - 1 are still read; the group
+        // barriers of the unit that follows publish it); everybody else reads the 16 B record.
         //   x: first token row of the window's image, or -1 beyond the problem   y, z: window origin (rows, columns)
         //   w: 1 if the shift mask applies (last window row / column of a shifted block)
-        int4* sgeo = sgeo_all + grp * 4;
+        int4* sgeo = sgeo_all + grp * 6;
         auto compute_geo = [&](int it, int tile) {
             const int tg = gw * 32 + lane;
             if (tg < 2) {
                 const int wg = tile * 2 + tg;
                 const int bi = wg / nW, win = wg - bi * nW;
                 const int wi = win / wpr, wj = win - wi * wpr;
-                sgeo[(it & 1) * 2 + tg] = make_int4((long long)wg * 64 < p.M ? bi * p.T : -1, wi << 3, wj << 3,
+                sgeo[(it % 3) * 2 + tg] = make_int4((long long)wg * 64 < p.M ? bi * p.T : -1, wi << 3, wj << 3,
                                                     (p.shift > 0 && (wi == nWy - 1 || wj == wpr - 1)) ? 1 : 0);
             }
         };
@@ -235,18 +243,21 @@ attn_block_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         auto tile_setup = [&](int it) {
             const int tg = gw * 32 + lane;
             if (tg < 128) {
-                const int4 g = sgeo[(it & 1) * 2 + (tg >> 6)];
+                const int4 g = sgeo[(it % 3) * 2 + (tg >> 6)];
                 const int pos = tg & 63;
                 lab[tg] = (unsigned char)(g.w ? region_label(g.y + (pos >> 3), p.H, p.shift) * 3 + region_label(g.z + (pos & 7), p.W, p.shift) : 0);
             }
-            const int4 g2 = sgeo[(it & 1) * 2 + window];
+            const int4 g2 = sgeo[(it % 3) * 2 + window];
             w_valid = g2.x >= 0;
             w_masked = g2.w != 0;
         };
         auto unit = [&](int it, int h) {
             const int j = it * AB_NH + h, s = j % 3;
+            const int tri = it * 3 + (h >> 1);
+            if (gw == 0) AB_TR(grp, tri, 0);
             mbar_wait(q_full(s), (j / 3) & 1);
             tc_fence_after();
+            if (gw == 0) AB_TR(grp, tri, 1);
             {   // drain: thread = row, 48 columns -> 96 B of the staged row [q 32 | k 32 | v 32]
                 const uint32_t t_row = tQ + ((uint32_t)(lg * 32) << 16) + (uint32_t)(s * 96 + hq * 48);
                 unsigned char* srow = stg + (size_t)(lg * 32 + lane) * AB_SROW16 + hq * 96;
@@ -271,8 +282,11 @@ attn_block_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(q_empty(s));                       // accumulator stage drained
+            if (gw == 0) AB_TR(grp, tri, 2);
             asm volatile("bar.sync %0, 256;" ::"r"(bar_g) : "memory");   // the head is staged (+ labels)
+            if (gw == 0) AB_TR(grp, tri, 3);
             if (it > 0) mbar_wait(ao_empty, (it - 1) & 1);                // the previous tile's proj MMAs have read AO
+            if (gw == 0) AB_TR(grp, tri, 4);
             if (w_valid)
                 attn_unit<32, true, unsigned char>(stg_s + window * 64 * AB_SROW16, stg + (size_t)window * 64 * AB_SROW16, AB_SROW16,
                                                    strip, 0, 32, 64, stab + h * 225, lab + window * 64, w_masked, p.scale, lane,
@@ -280,52 +294,84 @@ attn_block_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes of AO -> visible to UMMA
             __syncwarp();
             if (lane == 0) mbar_arrive(ao_full);
+            if (gw == 0) AB_TR(grp, tri, 5);
             asm volatile("bar.sync %0, 256;" ::"r"(bar_g) : "memory");   // staging (k, v) free for the group's next unit
+            if (gw == 0) AB_TR(grp, tri, 6);
         };
 
-        // ---- final stage of tile iteration tp: PD -> x', LN2 (both groups together, 16 warps) ----
-        // A warp finishes rows fw*4 .. fw*4+3 of each 64-row half (= window), two rows at a time: half-warp hh
-        // owns one row, lane hl the columns 64 k + 4 hl.
-        const int fw = uw;
+        // ---- final stage, one QUARTER of a tile at a time: PD rows of one TMEM lane group -> x', LN2 ----
+        // Group g finishes window g of the previous tile (rows 64 g .. 64 g + 63 = lane groups 2 g, 2 g + 1) in two
+        // quarters of 32 rows, each between two of its head units, with its own staging tile and its own barrier: no
+        // barrier spans the two groups, so one group's (latency bound) final stage runs under the other group's
+        // attention arithmetic.  Phase T: the two warps of the quarter's lane group drain 96 accumulator columns each
+        // into the fp32 staging tile (aliases the group's bf16 staging tile); phase R: all 8 warps, 4 rows each, two
+        // rows at a time: half-warp hh owns a row, lane hl the columns 64 k + 4 hl.
         const int hl = lane & 15, hh = lane >> 4;
-        float* stg32 = reinterpret_cast<float*>(sm + AB_STG_OFF);     // [64][AB_SROW32] fp32, aliases both bf16 staging tiles
+        float* stg32 = reinterpret_cast<float*>(stg);                 // [32][AB_SROW32] fp32
         const float inv_c = 1.f / (float)p.ln_C;
         bool colin[AB_KB];
 #pragma unroll
         for (int k = 0; k < AB_KB; ++k) colin[k] = 64 * k + 4 * hl < p.ln_C;
         const bool o_bf16 = p.out16_dtype == SRK_BF16;
         auto pack = [&](float a, float b) { return o_bf16 ? packf<SRK_BF16>(a, b) : packf<SRK_FP16>(a, b); };
-        // per-window geometry of a tile (uniform over the CTA): image base row, window origin in the shifted frame
-        struct WinGeo { int base, y0, x0; };                          // base < 0: the window lies beyond the problem
-        auto win_geo = [&](int it, int half) {
-            const int4 r = sgeo[(it & 1) * 2 + half];
-            WinGeo g;
-            g.base = r.x; g.y0 = r.y + p.shift; g.x0 = r.z + p.shift;
-            return g;
-        };
-        // token row (fp32 stream / LN2 output) of this lane's row rr (0, 1) of a window, or -1
-        auto token_row = [&](const WinGeo& g, int rr) {
-            const int pos = fw * 4 + 2 * rr + hh;
-            int y = g.y0 + (pos >> 3), x = g.x0 + (pos & 7);
+        // token row (fp32 stream / LN2 output) of window position pos of window `grp` of tile iteration it, or -1
+        auto token_row = [&](int it, int pos) {
+            const int4 g = sgeo[(it % 3) * 2 + grp];
+            int y = g.y + p.shift + (pos >> 3), x = g.z + p.shift + (pos & 7);
             if (y >= p.H) y -= p.H;
             if (x >= p.W) x -= p.W;
-            return g.base < 0 ? -1 : g.base + y * p.W + x;
+            return g.x < 0 ? -1 : g.x + y * p.W + x;
         };
-        // L2 prefetch of the residual rows a tile's final stage will read (issued a whole unit ahead: no registers held)
+        // L2 prefetch of the residual rows of this group's window (issued a tile ahead: no registers held)
         auto prefetch_res = [&](int it) {
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const WinGeo g = win_geo(it, half);
-#pragma unroll
-                for (int rr = 0; rr < 2; ++rr) {
-                    const int row = token_row(g, rr);
-                    if (row >= 0 && hl < 6)
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res + (size_t)row * p.ld32 + 32 * hl));
-                }
+            const int tg = gw * 32 + lane;
+            const int row = token_row(it, tg >> 2);
+            if (row >= 0) {
+                const float* rp = p.res + (size_t)row * p.ld32 + 32 * (tg & 3);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(rp));
+                if ((tg & 3) < 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + 128));
             }
         };
-        auto final_stage = [&](int tp) {
-            // LayerNorm parameters of this lane's columns (requested before the waits below)
+        auto quarter = [&](int tp, int qi) {
+            // residual rows of this warp (L2 hits thanks to prefetch_res), requested before anything else
+            float4 resv[2][AB_KB];
+            int row[2];
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                row[rr] = token_row(tp, 32 * qi + gw * 4 + 2 * rr + hh);
+                const float* rp = p.res + (size_t)(row[rr] >= 0 ? row[rr] : 0) * p.ld32 + 4 * hl;
+#pragma unroll
+                for (int k = 0; k < AB_KB; ++k)
+                    asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(resv[rr][k].x), "=f"(resv[rr][k].y), "=f"(resv[rr][k].z), "=f"(resv[rr][k].w)
+                                 : "l"(rp + 64 * k));
+            }
+            if (gw == 0) AB_TR(2 + grp, 2 * tp + qi, 0);
+            // phase T: lane group 2 grp + qi = warps gw = 2 grp + qi (columns 0..95) and gw + 4 (columns 96..191)
+            if ((gw & 3) == 2 * grp + qi) {
+                mbar_wait(pd_full, tp & 1);
+                tc_fence_after();
+                const int hq2 = gw >> 2;
+                float* srow = stg32 + (size_t)lane * AB_SROW32 + hq2 * 96;
+                const uint32_t t_row = tPD + ((uint32_t)(lg * 32) << 16) + (uint32_t)(hq2 * 96);
+                uint32_t va[16], vb[16];
+                tc_ld16_nowait(t_row, va);
+#pragma unroll
+                for (int c = 0; c < 6; c += 2) {
+                    tc_wait_ld16(va);
+                    tc_ld16_nowait(t_row + 16 * (c + 1), vb);
+#pragma unroll
+                    for (int e = 0; e < 16; e += 4) *reinterpret_cast<uint4*>(srow + 16 * c + e) = make_uint4(va[e], va[e + 1], va[e + 2], va[e + 3]);
+                    tc_wait_ld16(vb);
+                    if (c + 2 < 6) tc_ld16_nowait(t_row + 16 * (c + 2), va);
+#pragma unroll
+                    for (int e = 0; e < 16; e += 4) *reinterpret_cast<uint4*>(srow + 16 * (c + 1) + e) = make_uint4(vb[e], vb[e + 1], vb[e + 2], vb[e + 3]);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(pd_empty);
+            }
+            // LayerNorm parameters of this lane's columns
             float4 gg[AB_KB], bt[AB_KB];
 #pragma unroll
             for (int k = 0; k < AB_KB; ++k) {
@@ -335,123 +381,83 @@ attn_block_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                     bt[k] = __ldg(reinterpret_cast<const float4*>(p.ln_b + 64 * k + 4 * hl));
                 }
             }
-            // residual rows (two row pairs per warp and half; L2 hits thanks to prefetch_res): the first half's rows are
-            // requested before the waits below, the second half's under the first half's phase R
-            float4 resa[2][2][AB_KB];
-            int rows_[2][2];
-            auto request_res = [&](int half) {
-                const WinGeo geo = win_geo(tp, half);
+            asm volatile("bar.sync %0, 256;" ::"r"(bar_g) : "memory");   // staging complete
+            if (gw == 0) AB_TR(2 + grp, 2 * tp + qi, 1);
+            // phase R
+            float4 v[2][AB_KB];
+            float sm_[2], mean[2], qq[2];
 #pragma unroll
-                for (int rr = 0; rr < 2; ++rr) {
-                    rows_[half][rr] = token_row(geo, rr);
-                    const float* rp = p.res + (size_t)(rows_[half][rr] >= 0 ? rows_[half][rr] : 0) * p.ld32 + 4 * hl;
+            for (int rr = 0; rr < 2; ++rr) {
+                const float* srow = stg32 + (size_t)(gw * 4 + 2 * rr + hh) * AB_SROW32 + 4 * hl;
+                sm_[rr] = 0.f;
+#pragma unroll
+                for (int k = 0; k < AB_KB; ++k) {
+                    v[rr][k] = *reinterpret_cast<const float4*>(srow + 64 * k);
+                    const float4 bb = *reinterpret_cast<const float4*>(sbp + 64 * k + 4 * hl);
+                    v[rr][k].x = (v[rr][k].x + bb.x) + resv[rr][k].x; v[rr][k].y = (v[rr][k].y + bb.y) + resv[rr][k].y;
+                    v[rr][k].z = (v[rr][k].z + bb.z) + resv[rr][k].z; v[rr][k].w = (v[rr][k].w + bb.w) + resv[rr][k].w;
+                    sm_[rr] += (v[rr][k].x + v[rr][k].y) + (v[rr][k].z + v[rr][k].w);      // pad columns are exactly 0
+                }
+                if (row[rr] >= 0) {
+                    float* oo = p.out32 + (size_t)row[rr] * p.ld32 + 4 * hl;
+#pragma unroll
+                    for (int k = 0; k < AB_KB; ++k) *reinterpret_cast<float4*>(oo + 64 * k) = v[rr][k];
+                }
+            }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) sm_[rr] += __shfl_xor_sync(0xffffffffu, sm_[rr], o);
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                mean[rr] = sm_[rr] * inv_c; qq[rr] = 0.f;
+#pragma unroll
+                for (int k = 0; k < AB_KB; ++k) {
+                    v[rr][k].x -= mean[rr]; v[rr][k].y -= mean[rr]; v[rr][k].z -= mean[rr]; v[rr][k].w -= mean[rr];
+                    const float q4 = (v[rr][k].x * v[rr][k].x + v[rr][k].y * v[rr][k].y) + (v[rr][k].z * v[rr][k].z + v[rr][k].w * v[rr][k].w);
+                    qq[rr] += colin[k] ? q4 : 0.f;
+                }
+            }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) qq[rr] += __shfl_xor_sync(0xffffffffu, qq[rr], o);
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const float rstd = rsqrtf(qq[rr] * inv_c + 1e-5f);
+                if (row[rr] >= 0) {
+                    uint16_t* o16 = p.out16 + (size_t)row[rr] * p.ld16 + 4 * hl;
 #pragma unroll
                     for (int k = 0; k < AB_KB; ++k)
-                        asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                     : "=f"(resa[half][rr][k].x), "=f"(resa[half][rr][k].y), "=f"(resa[half][rr][k].z), "=f"(resa[half][rr][k].w)
-                                     : "l"(rp + 64 * k));
+                        *reinterpret_cast<uint2*>(o16 + 64 * k) =
+                            make_uint2(pack(v[rr][k].x * rstd * gg[k].x + bt[k].x, v[rr][k].y * rstd * gg[k].y + bt[k].y),
+                                       pack(v[rr][k].z * rstd * gg[k].z + bt[k].z, v[rr][k].w * rstd * gg[k].w + bt[k].w));
                 }
-            };
-            request_res(0);
-            asm volatile("bar.sync 3, 512;" ::: "memory");           // both groups left their staging tiles
-            mbar_wait(pd_full, tp & 1);
-            tc_fence_after();
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                float4 (&resv)[2][AB_KB] = resa[half];
-                int (&row)[2] = rows_[half];
-                // phase T: the half's two lane groups (4 warps each, 48 columns per warp) drain PD into the staging tile
-                if ((lg >> 1) == half) {
-                    const int qc = (uw >> 2) & 3;                     // 0..3: which 48 of the 192 columns
-                    float* srow = stg32 + (size_t)((lg & 1) * 32 + lane) * AB_SROW32 + qc * 48;
-                    const uint32_t t_row = tPD + ((uint32_t)(lg * 32) << 16) + (uint32_t)(qc * 48);
-                    uint32_t va[16], vb[16];
-                    tc_ld16_nowait(t_row, va);
-                    tc_wait_ld16(va);
-                    tc_ld16_nowait(t_row + 16, vb);
-#pragma unroll
-                    for (int e = 0; e < 16; e += 4) *reinterpret_cast<uint4*>(srow + e) = make_uint4(va[e], va[e + 1], va[e + 2], va[e + 3]);
-                    tc_wait_ld16(vb);
-                    tc_ld16_nowait(t_row + 32, va);
-#pragma unroll
-                    for (int e = 0; e < 16; e += 4) *reinterpret_cast<uint4*>(srow + 16 + e) = make_uint4(vb[e], vb[e + 1], vb[e + 2], vb[e + 3]);
-                    tc_wait_ld16(va);
-#pragma unroll
-                    for (int e = 0; e < 16; e += 4) *reinterpret_cast<uint4*>(srow + 32 + e) = make_uint4(va[e], va[e + 1], va[e + 2], va[e + 3]);
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(pd_empty);
-                }
-                asm volatile("bar.sync 3, 512;" ::: "memory");       // staging complete
-                if (half == 0) request_res(1);
-                // phase R: two row pairs per warp (one row per half-warp), lane hl owns columns 64 k + 4 hl
-                float4 v[2][AB_KB];
-                float sm_[2], mean[2], qq[2];
-#pragma unroll
-                for (int rr = 0; rr < 2; ++rr) {
-                    const float* srow = stg32 + (size_t)(fw * 4 + 2 * rr + hh) * AB_SROW32 + 4 * hl;
-                    sm_[rr] = 0.f;
-#pragma unroll
-                    for (int k = 0; k < AB_KB; ++k) {
-                        v[rr][k] = *reinterpret_cast<const float4*>(srow + 64 * k);
-                        const float4 bb = *reinterpret_cast<const float4*>(sbp + 64 * k + 4 * hl);
-                        v[rr][k].x = (v[rr][k].x + bb.x) + resv[rr][k].x; v[rr][k].y = (v[rr][k].y + bb.y) + resv[rr][k].y;
-                        v[rr][k].z = (v[rr][k].z + bb.z) + resv[rr][k].z; v[rr][k].w = (v[rr][k].w + bb.w) + resv[rr][k].w;
-                        sm_[rr] += (v[rr][k].x + v[rr][k].y) + (v[rr][k].z + v[rr][k].w);      // pad columns are exactly 0
-                    }
-                    if (row[rr] >= 0) {
-                        float* oo = p.out32 + (size_t)row[rr] * p.ld32 + 4 * hl;
-#pragma unroll
-                        for (int k = 0; k < AB_KB; ++k) *reinterpret_cast<float4*>(oo + 64 * k) = v[rr][k];
-                    }
-                }
-#pragma unroll
-                for (int o = 8; o > 0; o >>= 1)
-#pragma unroll
-                    for (int rr = 0; rr < 2; ++rr) sm_[rr] += __shfl_xor_sync(0xffffffffu, sm_[rr], o);
-#pragma unroll
-                for (int rr = 0; rr < 2; ++rr) {
-                    mean[rr] = sm_[rr] * inv_c; qq[rr] = 0.f;
-#pragma unroll
-                    for (int k = 0; k < AB_KB; ++k) {
-                        v[rr][k].x -= mean[rr]; v[rr][k].y -= mean[rr]; v[rr][k].z -= mean[rr]; v[rr][k].w -= mean[rr];
-                        const float q4 = (v[rr][k].x * v[rr][k].x + v[rr][k].y * v[rr][k].y) + (v[rr][k].z * v[rr][k].z + v[rr][k].w * v[rr][k].w);
-                        qq[rr] += colin[k] ? q4 : 0.f;
-                    }
-                }
-#pragma unroll
-                for (int o = 8; o > 0; o >>= 1)
-#pragma unroll
-                    for (int rr = 0; rr < 2; ++rr) qq[rr] += __shfl_xor_sync(0xffffffffu, qq[rr], o);
-#pragma unroll
-                for (int rr = 0; rr < 2; ++rr) {
-                    const float rstd = rsqrtf(qq[rr] * inv_c + 1e-5f);
-                    if (row[rr] >= 0) {
-                        uint16_t* o16 = p.out16 + (size_t)row[rr] * p.ld16 + 4 * hl;
-#pragma unroll
-                        for (int k = 0; k < AB_KB; ++k)
-                            *reinterpret_cast<uint2*>(o16 + 64 * k) =
-                                make_uint2(pack(v[rr][k].x * rstd * gg[k].x + bt[k].x, v[rr][k].y * rstd * gg[k].y + bt[k].y),
-                                           pack(v[rr][k].z * rstd * gg[k].z + bt[k].z, v[rr][k].w * rstd * gg[k].w + bt[k].w));
-                    }
-                }
-                asm volatile("bar.sync 3, 512;" ::: "memory");       // staging free
             }
+            asm volatile("bar.sync %0, 256;" ::"r"(bar_g) : "memory");   // staging free for the next unit's drain
+            if (gw == 0) AB_TR(2 + grp, 2 * tp + qi, 2);
         };
 
-        // per tile: first head unit, then (both groups together) the final stage of the PREVIOUS tile, then the other two units
+        // Per tile and group: three head units with the two final-stage quarters of the PREVIOUS tile between them; the
+        // groups use different slots (0: u q u q u, 1: u u q u q) so that their final stages do not coincide.
         int tile = blockIdx.x;
         compute_geo(0, tile);
         asm volatile("bar.sync %0, 256;" ::"r"(bar_g) : "memory");
 #pragma unroll 1
         for (int it = 0; it <= n_my; ++it, tile += gridDim.x) {
-            if (it < n_my) { tile_setup(it); unit(it, grp); }
-            if (it > 0) final_stage(it - 1);
-            if (it < n_my) {
+            const bool live = it < n_my, fin = it > 0;
+            if (live) {
+                tile_setup(it);
                 compute_geo(it + 1, tile + gridDim.x);
+                unit(it, grp);
+                if (grp == 1) unit(it, grp + 2);
+            }
+            if (fin) quarter(it - 1, 0);
+            if (live) unit(it, grp == 0 ? grp + 2 : grp + 4);
+            if (fin) quarter(it - 1, 1);
+            if (live) {
                 prefetch_res(it);
-                unit(it, grp + 2);
-                unit(it, grp + 4);
+                if (grp == 0) unit(it, grp + 4);
             }
         }
     }
@@ -466,6 +472,12 @@ attn_block_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 }  // namespace srk
 
 using namespace srk;
+
+#ifdef SRK_AB_TRACE
+extern "C" int srk_debug_ab_trace(long long* out) {
+    return cudaMemcpyFromSymbol(out, g_ab_trace, sizeof(long long) * 4 * 64 * 8) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 extern "C" int srk_attn_block(const srk_attn_block_args* a, void* stream) {
     SRK_REQUIRE(a && a->A && a->Wqkv && a->Wproj && a->b_proj && a->rel_table && a->res && a->out32 && a->out16 && a->ln_g && a->ln_b,
