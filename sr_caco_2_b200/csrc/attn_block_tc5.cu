@@ -450,15 +450,13 @@ attn_block_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 tile_setup(it);
                 compute_geo(it + 1, tile + gridDim.x);
                 unit(it, grp);
-                if (grp == 1) unit(it, grp + 2);
+                unit(it, grp + 2);
+                if (grp == 1) unit(it, grp + 4);
             }
             if (fin) quarter(it - 1, 0);
-            if (live) unit(it, grp == 0 ? grp + 2 : grp + 4);
+            if (live && grp == 0) unit(it, grp + 4);
             if (fin) quarter(it - 1, 1);
-            if (live) {
-                prefetch_res(it);
-                if (grp == 0) unit(it, grp + 4);
-            }
+            if (live) prefetch_res(it);
         }
     }
     tc_fence_before();
