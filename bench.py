@@ -431,23 +431,40 @@ def main():
     # The plugin call a user makes: evaluator.make_cuda_step on HOST tensors.  The loader's images are uint8
     # (SURVEY 8f-1): LR and HR travel as the stored uint8 levels, `uint2tensor` (/255) runs on the device and the
     # metrics kernel reads the target bytes directly.  The fp32 shipping of round 1 is timed beside it.
-    res_host = torch.empty(B, 10, dtype=torch.float64).pin_memory()
+    res_host = [torch.empty(B, 10, dtype=torch.float64).pin_memory() for _ in range(2)]
+    res_evt = [torch.cuda.Event() for _ in range(2)]
     step_fn = EV.make_cuda_step(net, scale, swin_pad, roi_ths=ROI_THS, check=False)
     lr8_host = [(t * 255).round().to(torch.uint8).pin_memory() for t in lr_host]
     hr8_host = [(t * 255).round().to(torch.uint8).pin_memory() for t in hr_host]
 
-    def time_e2e(lrs, hrs):
-        def e2e_step(i):
-            vals = step_fn(lrs[i % NB], hrs[i % NB])
-            res_host.copy_(vals, non_blocking=True)
-            torch.cuda.current_stream().synchronize()      # the caller reads the scores every step
-            return res_host[:, 0].sum().item()
-        for i in range(2):
-            e2e_step(i)
+    def time_e2e(lrs, hrs, pipelined=True):
+        """Every step: H2D of that step's inputs from pinned host memory, the plugin call, D2H of its (B, 10) score
+        block and a host-side read of it.  pipelined: the host reads the scores of step i after it has enqueued step
+        i + 1 (two pinned result buffers, one event each) -- what `evaluator.evaluate_patches` does for a whole sweep;
+        otherwise the host waits for every step before it enqueues the next one."""
+        acc = [0.0]
+        def consume(slot):
+            res_evt[slot].synchronize()
+            acc[0] += res_host[slot][:, 0].sum().item()
+        def run(n):
+            pending = None
+            for i in range(n):
+                vals = step_fn(lrs[i % NB], hrs[i % NB])
+                slot = i & 1
+                res_host[slot].copy_(vals, non_blocking=True)
+                res_evt[slot].record()
+                if not pipelined:
+                    consume(slot)
+                    continue
+                if pending is not None:
+                    consume(pending)
+                pending = slot
+            if pending is not None:
+                consume(pending)
+        run(2)
         barrier()
         ev0.record()
-        for i in range(K):
-            e2e_step(i)
+        run(K)
         ev1.record()
         barrier()
         tt = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
@@ -456,9 +473,10 @@ def main():
         return world * B * K / (float(tt.item()) * 1e-3)
 
     e2e_value = time_e2e(lr8_host, hr8_host)
+    e2e_sync = time_e2e(lr8_host, hr8_host, pipelined=False)
     e2e_fp32 = time_e2e(lr_host, hr_host)
     h2d = lr8_host[0].numel() + hr8_host[0].numel()
-    d2h = res_host.numel() * 8
+    d2h = res_host[0].numel() * 8
 
     if rank != 0:
         if world > 1:
@@ -538,6 +556,9 @@ def main():
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "shipping": "uint8 LR + uint8 HR (the loader's stored levels), /255 on the device",
+                    "host_loop": "every step: H2D of its inputs from pinned memory, plugin call, D2H + host read of its (B, 10) scores; "
+                                 "the host reads step i's scores after enqueueing step i + 1 (as evaluator.evaluate_patches does)",
+                    "host_waits_every_step": {"value": e2e_sync},
                     "fp32_shipping": {"value": e2e_fp32, "h2d_bytes_per_step": 4 * h2d}},
             "roofline": roofline}
     if world == 1 and not args.no_eager_baseline:
