@@ -111,4 +111,16 @@ for k, (hh, ww) in enumerate([(64, 64), (128, 128), (256, 256)]):
     us = run("up", A=Ui, a_mode=1, lda=64, nB=B, H=hh, W=ww, Wt=Wu, M=Mi, N=256, K=576, dtype=1, bias=bias, out16=Uo, ld16=64, out16_dtype=1, out16_mode=1)
     report(f"up{k} 64->256 ps @{hh}", us, 2*Mi*256*576, Mi*(128+512))
     del Ui, Uo
+# EDSR body conv: 64 -> 64 on 64 x (64 x 64), 16-bit in / out, resident weights; 5x5 folded tail conv 64 -> 64 at 64x64
+Be = 64
+Me = Be * 64 * 64
+Ae = t16(Me, 64, dt=torch.float16); We = t16(64, 9*64, dt=torch.float16); Oe = torch.empty(Me, 64, device=dev, dtype=torch.float16)
+if eng == "tcgen05":
+    for halo in (1, 0):
+        L.load().srk_gemm_conv_halo(halo)
+        us = run("edsr", A=Ae, a_mode=1, lda=64, nB=Be, H=64, W=64, Wt=We, M=Me, N=64, K=576, dtype=1, bias=bias, act=3, out16=Oe, ld16=64, out16_dtype=1)
+        report(f"conv 64->64 relu B=64 halo={halo}", us, 2*Me*64*576, Me*(128+128))
+        us = run("before_up", A=Ah, a_mode=1, lda=Cp, nB=B, H=H, W=W, Wt=Wb, M=M, N=64, K=9*192, dtype=1, bias=bias, act=2, out16=U0, ld16=64, out16_dtype=1)
+        report(f"conv 192->64 lrelu halo={halo}", us, 2*M*64*1728, M*(384+128))
+    L.load().srk_gemm_conv_halo(1)
 json.dump(rows, open(f"gpurun_out/gemm_bench_{eng}.json", "w"), indent=1)

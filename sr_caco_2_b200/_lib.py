@@ -100,6 +100,7 @@ PROTOTYPES = {
     "srk_index_map": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
     "srk_metrics_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "srk_metrics_use_tile_kernel": (C.c_int, [C.c_int]),
+    "srk_gemm_conv_halo": (C.c_int, [C.c_int]),
     "srk_metrics": (C.c_int, [fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                               C.POINTER(C.c_int), C.c_int, vp, vp, vp, vp]),
     "srk_metrics_roi": (C.c_int, [fp, fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp,

@@ -34,6 +34,11 @@ struct TcParams {
     // shared-memory plan (host computed): B-stationary keeps the CTA's whole weight tile
     // (nkb x BN x 64) resident and streams only A through `stages` 16 KB slots
     int bstat, stages, stage_bytes, bres_bytes;
+    // conv halo mode (64-output-channel convs): ONE TMA box (64 ch, 8 + 2r, 16 + 2r) per (tile, channel block) feeds
+    // all kt * kt taps as shifted-window A descriptors into the swizzled halo tile; `stages` / `stage_bytes` then
+    // describe the ring of weight k-blocks (none when the weights are resident).  These convs are bound by the TMA
+    // request rate of the per-tap boxes (~5 cycles per 128 B pixel row, 9 or 25 boxes per channel block), not by bytes.
+    int halo, halo_r, halo_box_bytes, halo_stride, a_stages;
 };
 
 #ifndef SRK_LN_ROW_BATCH
@@ -93,7 +98,8 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const uint32_t raw = smem_u32(tc_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                     // SW128 tiles need 1024 B alignment
     // [resident B (B-stationary only)] [operand stages] [epilogue staging] [barriers]
-    const uint32_t stages_base = base + p.bres_bytes;
+    const uint32_t halo_base = base + p.bres_bytes;                   // halo ring (conv halo mode only)
+    const uint32_t stages_base = halo_base + p.a_stages * p.halo_stride;
     const uint32_t stg_base = stages_base + p.stages * p.stage_bytes;
     const uint32_t bars = stg_base + Cfg::STAGING_BYTES;    // full[8] empty[8] tfull[2] tempty[2] bfull tmem_ptr
     auto full_bar = [&](int s) { return bars + 8u * s; };
@@ -102,6 +108,8 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     auto tempty_bar = [&](int s) { return bars + 8u * (2 * Cfg::MAX_STAGES + 2 + s); };
     const uint32_t bfull_bar = bars + 8u * (2 * Cfg::MAX_STAGES + 4);
     const uint32_t tmem_slot = bars + 8u * (2 * Cfg::MAX_STAGES + 5);
+    auto afull_bar = [&](int s) { return bars + 8u * (2 * Cfg::MAX_STAGES + 6 + s); };      // halo ring (<= 4 stages)
+    auto aempty_bar = [&](int s) { return bars + 8u * (2 * Cfg::MAX_STAGES + 10 + s); };
     const int NS = p.stages;
     // B-stationary: CTA c owns n-tile c % n_tiles and M tiles c / n_tiles, + gridDim / n_tiles, ...
     // (the host makes gridDim a multiple of n_tiles), so "tile += gridDim.x" keeps nt fixed.
@@ -115,6 +123,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     if (threadIdx.x == 0) {
         for (int s = 0; s < Cfg::MAX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         mbar_init(bfull_bar, 1);
+        for (int s = 0; s < 4; ++s) { mbar_init(afull_bar(s), 1); mbar_init(aempty_bar(s), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), Cfg::EPI_WARPS / Cfg::kGroups); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -149,7 +158,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     if (warp == 0) {
         // ================================ TMA producer ================================
         if (lane == 0) {
-            int stage = 0, phase = 0;
+            int stage = 0, phase = 0, hstage = 0, hphase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
                 int cb_, cx = 0, cy = 0;
@@ -162,14 +171,40 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 } else {
                     cb_ = 0;
                 }
+                if (p.halo) {
+                    // channel-block major: one halo box, then (unless resident) the kt * kt weight k-blocks that use it
+                    const int taps = g.kt * g.kt;
+                    for (int cblk = 0; cblk < g.cpb; ++cblk) {
+                        mbar_wait(aempty_bar(hstage), hphase ^ 1);
+                        mbar_expect_tx(afull_bar(hstage), (uint32_t)p.halo_box_bytes);
+                        tma_load_4d(halo_base + hstage * p.halo_stride, &map_a, afull_bar(hstage), cblk * 64,
+                                    cx - p.halo_r, cy - p.halo_r, cb_);
+                        if (++hstage == p.a_stages) { hstage = 0; hphase ^= 1; }
+                        if (!p.bstat) {
+                            for (int tap = 0; tap < taps; ++tap) {
+                                mbar_wait(empty_bar(stage), phase ^ 1);
+                                mbar_expect_tx(full_bar(stage), (uint32_t)Cfg::B_BYTES);
+                                tma_load_2d(stages_base + stage * p.stage_bytes, &map_b, full_bar(stage),
+                                            (tap * g.cpb + cblk) * TBK, nt * BN);
+                                if (++stage == NS) { stage = 0; phase ^= 1; }
+                            }
+                        }
+                    }
+                    continue;
+                }
+                // (tap, channel block) of k-block kb = tap * cpb + cblk are carried as counters: this single thread is the
+                // kernel's critical path for the convs (two integer divisions per k-block were ~2/3 of its instructions)
+                int cblk = 0, dx = -(g.kt >> 1), dy = -(g.kt >> 1);
                 for (int kb = 0; kb < p.nkb; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t sa = stages_base + stage * p.stage_bytes, sb = sa + Cfg::A_BYTES;
                     mbar_expect_tx(full_bar(stage), (uint32_t)p.stage_bytes);
                     if (g.a_mode == SRK_A_CONV3X3) {
-                        const int tap = kb / g.cpb, cblk = kb - tap * g.cpb;
-                        const int dy = tap / g.kt - (g.kt >> 1), dx = tap - (tap / g.kt) * g.kt - (g.kt >> 1);
                         tma_load_4d(sa, &map_a, full_bar(stage), cblk * 64, cx + dx, cy + dy, cb_);
+                        if (++cblk == g.cpb) {
+                            cblk = 0;
+                            if (++dx > (g.kt >> 1)) { dx = -(g.kt >> 1); ++dy; }
+                        }
                     } else {
                         tma_load_2d(sa, &map_a, full_bar(stage), kb * TBK, mt * TBM);
                     }
@@ -182,13 +217,48 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         // ================================ MMA issuer ================================
         if (lane == 0) {
             const uint32_t idesc = umma_idesc(g.dtype == SRK_BF16 ? 1 : 0, TBM, BN);
-            int stage = 0, phase = 0, it = 0;
+            int stage = 0, phase = 0, it = 0, hstage = 0, hphase = 0;
             if (p.bstat && (int)blockIdx.x < total_tiles) { mbar_wait(bfull_bar, 0); tc_fence_after(); }
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
                 const int as = it & 1, aphase = (it >> 1) & 1;
                 mbar_wait(tempty_bar(as), aphase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+                if (p.halo) {
+                    const int taps = g.kt * g.kt, hw = 8 + 2 * p.halo_r;          // halo width in pixels (= 128 B rows)
+                    for (int cblk = 0; cblk < g.cpb; ++cblk) {
+                        mbar_wait(afull_bar(hstage), hphase);
+                        tc_fence_after();
+                        const uint32_t ha = halo_base + hstage * p.halo_stride;
+                        int ty = 0, tx = 0;
+                        for (int tap = 0; tap < taps; ++tap) {
+                            const int kb = tap * g.cpb + cblk;
+                            uint32_t sb = base + kb * Cfg::B_BYTES;
+                            if (!p.bstat) {
+                                mbar_wait(full_bar(stage), phase);
+                                tc_fence_after();
+                                sb = stages_base + stage * p.stage_bytes;
+                            }
+                            // A = the 8 x 16 pixel window of the halo tile shifted by the tap: 16 core groups (image
+                            // rows) hw * 128 B apart, starting at halo pixel (tap / kt, tap % kt).  Legal because the
+                            // 128 B swizzle is a function of the absolute shared-memory address (1024 B aligned tile).
+                            const uint64_t da = umma_desc_sw128_sbo(ha + (uint32_t)(ty * hw + tx) * 128u, (uint32_t)hw * 128u);
+                            if (++tx == g.kt) { tx = 0; ++ty; }
+                            const uint64_t db = umma_desc_sw128(sb);
+#pragma unroll
+                            for (int k = 0; k < TBK / 16; ++k)
+                                tc_mma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (cblk | tap | k) != 0 ? 1u : 0u);
+                            if (!p.bstat) {
+                                tc_commit(empty_bar(stage));
+                                if (++stage == NS) { stage = 0; phase ^= 1; }
+                            }
+                        }
+                        tc_commit(aempty_bar(hstage));
+                        if (++hstage == p.a_stages) { hstage = 0; hphase ^= 1; }
+                    }
+                    tc_commit(tfull_bar(as));
+                    continue;
+                }
                 for (int kb = 0; kb < p.nkb; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
@@ -762,7 +832,28 @@ static int launch_tc5(const CUtensorMap& ma, const CUtensorMap& mb, const TcPara
     int grid = total < num_sms() ? total : num_sms();
     // shared-memory plan: keep the weight tile resident when it fits and every CTA sees >= 2 M tiles
     const int bres = p.nkb * Cfg::B_BYTES;
-    {
+    size_t halo_bytes = 0;
+    if (p.halo) {
+        // conv halo mode: [resident B | -] [halo ring] [ring of weight k-blocks]
+        p.bstat = (bres + 3 * p.halo_stride <= Cfg::AVAIL) && (num_sms() >= p.n_tiles) && (p.m_tiles * p.n_tiles >= 2 * num_sms());
+        if (p.bstat) {
+            grid = (num_sms() / p.n_tiles) * p.n_tiles;
+            if (grid > total) grid = total;
+            p.bres_bytes = bres;
+            p.stages = 0; p.stage_bytes = Cfg::B_BYTES;
+            p.a_stages = (Cfg::AVAIL - bres) / p.halo_stride;
+            if (p.a_stages > 4) p.a_stages = 4;
+        } else {
+            p.bres_bytes = 0;
+            p.stage_bytes = Cfg::B_BYTES;
+            p.a_stages = p.g.cpb >= 2 ? 3 : 2;                      // halo ring first, the rest goes to the weight ring
+            p.stages = (Cfg::AVAIL - p.a_stages * p.halo_stride) / p.stage_bytes;
+            if (p.stages > Cfg::MAX_STAGES) p.stages = Cfg::MAX_STAGES;
+            if (p.stages < 2) return fail(SRK_ERR_UNSUPPORTED, "gemm(tcgen05): conv halo mode does not fit shared memory");
+        }
+        halo_bytes = (size_t)p.a_stages * p.halo_stride;
+    } else {
+        p.a_stages = 0; p.halo_stride = 0;
         p.bstat = (bres + 3 * Cfg::A_BYTES <= Cfg::AVAIL) && (num_sms() >= p.n_tiles) &&
                   (EPI == E_ATTN || p.m_tiles * p.n_tiles >= 2 * num_sms());
         if (EPI == E_ATTN && !p.bstat) return fail(SRK_ERR_UNSUPPORTED, "gemm(tcgen05): fused attention needs the resident-weight mode");
@@ -778,7 +869,7 @@ static int launch_tc5(const CUtensorMap& ma, const CUtensorMap& mb, const TcPara
         p.stages = (Cfg::AVAIL - p.bres_bytes) / p.stage_bytes;
         if (p.stages > Cfg::MAX_STAGES) p.stages = Cfg::MAX_STAGES;
     }
-    const size_t smem = (size_t)p.bres_bytes + (size_t)p.stages * p.stage_bytes + Cfg::STAGING_BYTES + 1024 + Cfg::AUX_BYTES;
+    const size_t smem = (size_t)p.bres_bytes + halo_bytes + (size_t)p.stages * p.stage_bytes + Cfg::STAGING_BYTES + 1024 + Cfg::AUX_BYTES;
     gemm_tc5_kernel<BN, EPI, ACT, DT><<<grid, Cfg::THREADS, smem, st>>>(ma, mb, p);
     SRK_LAUNCH_CHECK("gemm_tc5_kernel");
     return 0;
@@ -813,6 +904,8 @@ static int dispatch_tc5(const srk_gemm_args* a, const CUtensorMap& ma, const CUt
     return launch_tc5<BN, E_GENERIC, 0, 0>(ma, mb, p, st);
 }
 
+bool g_conv_halo = true;     // srk_gemm_conv_halo(): tests compare the halo-tile convs with the per-tap-box convs
+
 int gemm_tcgen05(const srk_gemm_args* a, cudaStream_t st) {
     SRK_REQUIRE(a->N % 64 == 0, "gemm(tcgen05): N=%d must be a multiple of 64", a->N);
     SRK_REQUIRE(((uintptr_t)a->A & 15) == 0 && ((uintptr_t)a->Wt & 15) == 0, "gemm(tcgen05): operands must be 16 B aligned");
@@ -835,7 +928,21 @@ int gemm_tcgen05(const srk_gemm_args* a, cudaStream_t st) {
     const bool attn = a->attn_table != nullptr;
     if (attn) SRK_REQUIRE(BN == 192 && a->N == p.n_tiles * 192, "gemm(tcgen05): fused attention needs N == pairs * 192");
     CUtensorMap ma, mb;
-    if (a->a_mode == SRK_A_CONV3X3) {
+    if (a->a_mode == SRK_A_CONV3X3 && BN == 64 && g_conv_halo) {
+        // halo mode (64 output channels): 8 x 16 pixel tiles; ONE box (64 ch, 8 + 2r, 16 + 2r) per channel block serves every tap
+        const int r = a->conv_k == 5 ? 2 : 1;
+        p.halo = 1; p.halo_r = r;
+        p.conv_bw = 8; p.conv_bh = 16;
+        p.halo_box_bytes = (8 + 2 * r) * (16 + 2 * r) * 128;
+        p.halo_stride = (int)align_up((size_t)p.halo_box_bytes, 1024);
+        p.conv_tx = (a->W + 7) / 8;
+        p.conv_ty = (a->H + 15) / 16;
+        p.m_tiles = a->nB * p.conv_tx * p.conv_ty;
+        cuuint64_t dims[4] = {(cuuint64_t)a->lda, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->nB};
+        cuuint64_t strides[3] = {(cuuint64_t)a->lda * 2, (cuuint64_t)a->W * a->lda * 2, (cuuint64_t)a->H * a->W * a->lda * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)(8 + 2 * r), (cuuint32_t)(16 + 2 * r), 1};
+        if (int rc = encode_map(&ma, a->dtype, 4, a->A, dims, strides, box)) return rc;
+    } else if (a->a_mode == SRK_A_CONV3X3) {
         // pick the 128-pixel box (BW x BH) that wastes the fewest out-of-image pixels
         long best = -1;
         for (int bw = 8; bw <= 128; bw *= 2) {
@@ -874,3 +981,5 @@ int gemm_tcgen05(const srk_gemm_args* a, cudaStream_t st) {
 }
 
 }  // namespace srk
+
+extern "C" int srk_gemm_conv_halo(int on) { srk::g_conv_halo = on != 0; return 0; }

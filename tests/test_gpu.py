@@ -363,6 +363,62 @@ def test_gemm_conv3x3_pixelshuffle_and_image_epilogues(L, engine):
     assert float((img.cpu() - exp).abs().max()) < 3e-3 * max(1.0, float(exp.abs().max()))
 
 
+@pytest.mark.parametrize("geom", [(3, 40, 24, 64, 3), (2, 33, 17, 192, 3), (2, 64, 64, 64, 3), (2, 21, 30, 64, 5), (1, 16, 8, 128, 3)])
+def test_conv_halo_tiles_equal_per_tap_boxes(L, geom):
+    """64-output-channel convs of the tcgen05 engine: ONE halo TMA box per channel block with the taps read as
+    shifted-window UMMA descriptors (default) against one TMA box per tap (srk_gemm_conv_halo(0)) and against the
+    fp32 convolution.  The two operand paths add the same products in a different order (channel-block major vs
+    tap major): equal to fp32 accumulation noise.  Geometries: ragged tiles in both directions, several channel
+    blocks (streamed weights), a 5x5 window (halo radius 2), exact tiles."""
+    if "tcgen05" not in ENGINES:
+        pytest.skip("tcgen05 engine not under test")
+    L.set_engine("tcgen05")
+    B, H, W, Cin, kk = geom
+    g = torch.Generator().manual_seed(77 + H)
+    x = torch.randn(B, Cin, H, W, generator=g).half()
+    wt = (torch.randn(64, Cin, kk, kk, generator=g) * 0.05).half()
+    bias = torch.randn(64, generator=g)
+    ref = F.leaky_relu(F.conv2d(x.float(), wt.float(), bias, padding=kk // 2), 0.01).permute(0, 2, 3, 1).reshape(-1, 64)
+    wk = wt.float().permute(0, 2, 3, 1).reshape(64, kk * kk * Cin).half().contiguous().to(DEV)          # k = tap * Cin + c
+    a = x.permute(0, 2, 3, 1).contiguous().to(DEV)
+    M = B * H * W
+    res = torch.randn(M, 64, generator=g)
+    outs = []
+    lib = L.load()
+    try:
+        for halo in (1, 0):
+            lib.srk_gemm_conv_halo(halo)
+            o32 = torch.zeros(M, 64, device=DEV)
+            o16 = torch.zeros(M, 64, dtype=torch.float16, device=DEV)
+            _gemm(L, A=a, a_mode=L.A_CONV3X3, conv_k=kk, lda=Cin, nB=B, H=H, W=W, Wt=wk, M=M, N=64, K=kk * kk * Cin,
+                  dtype=L.SRK_FP16, bias=bias.to(DEV), act=L.ACT_LRELU, res=res.to(DEV), out32=o32, ld32=64,
+                  out16=o16, ld16=64, out16_dtype=L.SRK_FP16, out16_mode=L.O16_ROWS)
+            torch.cuda.synchronize()
+            outs.append((o32.cpu(), o16.float().cpu()))
+    finally:
+        lib.srk_gemm_conv_halo(1)
+    exp = ref + res
+    scale = max(1.0, float(exp.abs().max()))
+    assert float((outs[0][0] - exp).abs().max()) < 3e-3 * scale
+    assert float((outs[0][0] - outs[1][0]).abs().max()) < 2e-5 * scale
+    assert float((outs[0][1] - outs[1][1]).abs().max()) < 0.01 * scale
+    # 16-bit-only output (the E_O16 epilogue the EDSR body uses)
+    try:
+        for halo in (1, 0):
+            lib.srk_gemm_conv_halo(halo)
+            o16 = torch.zeros(M, 64, dtype=torch.float16, device=DEV)
+            _gemm(L, A=a, a_mode=L.A_CONV3X3, conv_k=kk, lda=Cin, nB=B, H=H, W=W, Wt=wk, M=M, N=64, K=kk * kk * Cin,
+                  dtype=L.SRK_FP16, bias=bias.to(DEV), act=L.ACT_RELU, out16=o16, ld16=64, out16_dtype=L.SRK_FP16,
+                  out16_mode=L.O16_ROWS)
+            torch.cuda.synchronize()
+            outs.append(o16.float().cpu())
+    finally:
+        lib.srk_gemm_conv_halo(1)
+    exp16 = F.relu(F.conv2d(x.float(), wt.float(), bias, padding=kk // 2)).permute(0, 2, 3, 1).reshape(-1, 64)
+    assert float((outs[2] - exp16).abs().max()) < 0.02 * max(1.0, float(exp16.abs().max()))
+    assert float((outs[2] - outs[3]).abs().max()) < 0.01 * max(1.0, float(exp16.abs().max()))
+
+
 @pytest.mark.parametrize("engine", ENGINES)
 def test_gemm_conv5x5_image_epilogue(L, engine):
     """conv_k = 5 (implicit GEMM over a 5x5 window, zero padding 2) with the image epilogue, s = 8."""
