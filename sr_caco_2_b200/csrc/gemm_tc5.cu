@@ -157,7 +157,8 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
     if (warp == 0) {
         // ================================ TMA producer ================================
-        if (lane == 0) {
+        {   // the whole warp runs the loop (uniform control flow, address arithmetic on the uniform datapath); one elected
+            // lane arms the barriers and issues the TMA loads
             int stage = 0, phase = 0, hstage = 0, hphase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
@@ -176,16 +177,22 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     const int taps = g.kt * g.kt;
                     for (int cblk = 0; cblk < g.cpb; ++cblk) {
                         mbar_wait(aempty_bar(hstage), hphase ^ 1);
-                        mbar_expect_tx(afull_bar(hstage), (uint32_t)p.halo_box_bytes);
-                        tma_load_4d(halo_base + hstage * p.halo_stride, &map_a, afull_bar(hstage), cblk * 64,
-                                    cx - p.halo_r, cy - p.halo_r, cb_);
+                        if (elect_one()) {
+                            mbar_expect_tx(afull_bar(hstage), (uint32_t)p.halo_box_bytes);
+                            tma_load_4d(halo_base + hstage * p.halo_stride, &map_a, afull_bar(hstage), cblk * 64,
+                                        cx - p.halo_r, cy - p.halo_r, cb_);
+                        }
+                        __syncwarp();
                         if (++hstage == p.a_stages) { hstage = 0; hphase ^= 1; }
                         if (!p.bstat) {
                             for (int tap = 0; tap < taps; ++tap) {
                                 mbar_wait(empty_bar(stage), phase ^ 1);
-                                mbar_expect_tx(full_bar(stage), (uint32_t)Cfg::B_BYTES);
-                                tma_load_2d(stages_base + stage * p.stage_bytes, &map_b, full_bar(stage),
-                                            (tap * g.cpb + cblk) * TBK, nt * BN);
+                                if (elect_one()) {
+                                    mbar_expect_tx(full_bar(stage), (uint32_t)Cfg::B_BYTES);
+                                    tma_load_2d(stages_base + stage * p.stage_bytes, &map_b, full_bar(stage),
+                                                (tap * g.cpb + cblk) * TBK, nt * BN);
+                                }
+                                __syncwarp();
                                 if (++stage == NS) { stage = 0; phase ^= 1; }
                             }
                         }
@@ -198,24 +205,24 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 for (int kb = 0; kb < p.nkb; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t sa = stages_base + stage * p.stage_bytes, sb = sa + Cfg::A_BYTES;
-                    mbar_expect_tx(full_bar(stage), (uint32_t)p.stage_bytes);
-                    if (g.a_mode == SRK_A_CONV3X3) {
-                        tma_load_4d(sa, &map_a, full_bar(stage), cblk * 64, cx + dx, cy + dy, cb_);
-                        if (++cblk == g.cpb) {
-                            cblk = 0;
-                            if (++dx > (g.kt >> 1)) { dx = -(g.kt >> 1); ++dy; }
-                        }
-                    } else {
-                        tma_load_2d(sa, &map_a, full_bar(stage), kb * TBK, mt * TBM);
+                    if (elect_one()) {
+                        mbar_expect_tx(full_bar(stage), (uint32_t)p.stage_bytes);
+                        if (g.a_mode == SRK_A_CONV3X3) tma_load_4d(sa, &map_a, full_bar(stage), cblk * 64, cx + dx, cy + dy, cb_);
+                        else tma_load_2d(sa, &map_a, full_bar(stage), kb * TBK, mt * TBM);
+                        if (!p.bstat) tma_load_2d(sb, &map_b, full_bar(stage), kb * TBK, nt * BN);
                     }
-                    if (!p.bstat) tma_load_2d(sb, &map_b, full_bar(stage), kb * TBK, nt * BN);
+                    __syncwarp();
+                    if (g.a_mode == SRK_A_CONV3X3 && ++cblk == g.cpb) {
+                        cblk = 0;
+                        if (++dx > (g.kt >> 1)) { dx = -(g.kt >> 1); ++dy; }
+                    }
                     if (++stage == NS) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ================================
-        if (lane == 0) {
+        {   // warp-uniform like the producer: descriptors stay in uniform registers, one elected lane issues MMAs and commits
             const uint32_t idesc = umma_idesc(g.dtype == SRK_BF16 ? 1 : 0, TBM, BN);
             int stage = 0, phase = 0, it = 0, hstage = 0, hphase = 0;
             if (p.bstat && (int)blockIdx.x < total_tiles) { mbar_wait(bfull_bar, 0); tc_fence_after(); }
@@ -245,18 +252,21 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                             const uint64_t da = umma_desc_sw128_sbo(ha + (uint32_t)(ty * hw + tx) * 128u, (uint32_t)hw * 128u);
                             if (++tx == g.kt) { tx = 0; ++ty; }
                             const uint64_t db = umma_desc_sw128(sb);
+                            if (elect_one()) {
 #pragma unroll
-                            for (int k = 0; k < TBK / 16; ++k)
-                                tc_mma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (cblk | tap | k) != 0 ? 1u : 0u);
-                            if (!p.bstat) {
-                                tc_commit(empty_bar(stage));
-                                if (++stage == NS) { stage = 0; phase ^= 1; }
+                                for (int k = 0; k < TBK / 16; ++k)
+                                    tc_mma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (cblk | tap | k) != 0 ? 1u : 0u);
+                                if (!p.bstat) tc_commit(empty_bar(stage));
+                                if (tap == taps - 1) {
+                                    tc_commit(aempty_bar(hstage));
+                                    if (cblk == g.cpb - 1) tc_commit(tfull_bar(as));
+                                }
                             }
+                            __syncwarp();
+                            if (!p.bstat && ++stage == NS) { stage = 0; phase ^= 1; }
                         }
-                        tc_commit(aempty_bar(hstage));
                         if (++hstage == p.a_stages) { hstage = 0; hphase ^= 1; }
                     }
-                    tc_commit(tfull_bar(as));
                     continue;
                 }
                 for (int kb = 0; kb < p.nkb; ++kb) {
@@ -265,14 +275,17 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     const uint32_t sa = stages_base + stage * p.stage_bytes;
                     const uint32_t sb = p.bstat ? base + kb * Cfg::B_BYTES : sa + Cfg::A_BYTES;
                     const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sb);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < TBK / 16; ++k)        // +32 B per UMMA_K inside the swizzle atom
-                        tc_mma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                                   (kb | k) != 0 ? 1u : 0u);
-                    tc_commit(empty_bar(stage));               // frees the smem slot when the MMAs retire
+                        for (int k = 0; k < TBK / 16; ++k)    // +32 B per UMMA_K inside the swizzle atom
+                            tc_mma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                                       (kb | k) != 0 ? 1u : 0u);
+                        tc_commit(empty_bar(stage));           // frees the smem slot when the MMAs retire
+                        if (kb == p.nkb - 1) tc_commit(tfull_bar(as));   // accumulator complete
+                    }
+                    __syncwarp();
                     if (++stage == NS) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(tfull_bar(as));                      // accumulator complete
             }
         }
     } else {
