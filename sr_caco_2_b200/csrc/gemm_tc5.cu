@@ -528,6 +528,19 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             }
         }
         // row bookkeeping of one tile: lane i (< RPW) describes row i of this warp's phase-R rows
+        // image epilogue (pixelshuffle-direct): lane i also carries the row's position in the cropped image -- y * s, x * s
+        // and the image base -- so that the per-element addressing is adds and compares (it was three integer divisions
+        // per element: the folded tail conv spent most of its time there)
+        const bool has_img = EPI == E_GENERIC && g.img != nullptr;
+        int my_iy = 0, my_ix = 0, my_ib = 0;
+        auto img_of = [&](int m_, int& iy_, int& ix_, int& ib_) {
+            iy_ = 0; ix_ = 0; ib_ = 0;
+            if (has_img && m_ >= 0) {
+                const int bi = m_ / g.T, rem = m_ - bi * g.T;
+                const int y = rem / g.W, x = rem - y * g.W;
+                iy_ = y * g.img_s; ix_ = x * g.img_s; ib_ = bi * g.img_hc * g.img_wc;
+            }
+        };
         auto rows_of = [&](int tile_, int& m_, int& r32_, int& r16_) {
             m_ = -1; r32_ = 0; r16_ = 0;
             if (tile_ >= total_tiles) return;
@@ -551,6 +564,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         float2 resv[kPrefetch ? RPW : 1][NP];
         int my_m, my_r32, my_r16;
         rows_of(blockIdx.x, my_m, my_r32, my_r16);
+        img_of(my_m, my_iy, my_ix, my_ib);
         if (kPrefetch) {
             const int n0f = (blockIdx.x % p.n_tiles) * BN;
 #pragma unroll
@@ -569,6 +583,18 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const int n0 = nt * BN;
             int nx_m, nx_r32, nx_r16;
             rows_of(tile + gridDim.x, nx_m, nx_r32, nx_r16);
+            // this lane's two columns of each 64-column group as sub-pixel (i, j) of the s x s block (-1: pad column)
+            int ci[NP][2], cj[NP][2];
+            if (has_img) {
+#pragma unroll
+                for (int k = 0; k < NP; ++k)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int n = n0 + 64 * k + 2 * lane + e;
+                        ci[k][e] = n < g.img_s * g.img_s ? n / g.img_s : -1;
+                        cj[k][e] = n - ci[k][e] * g.img_s;
+                    }
+            }
             const int n0x = ((tile + (int)gridDim.x) % p.n_tiles) * BN;
             float2 bia[NP];
 #pragma unroll
@@ -686,12 +712,19 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         *reinterpret_cast<uint32_t*>(oo + 64 * k) =
                             EPI == E_GENERIC ? pack2(v[k].x, v[k].y, g.out16_dtype) : packf<DT>(v[k].x, v[k].y);
                 }
-                if (EPI == E_GENERIC && g.img && valid) {
+                if (EPI == E_GENERIC && has_img) {
+                    const int iy = __shfl_sync(0xffffffffu, my_iy, i), ix = __shfl_sync(0xffffffffu, my_ix, i);
+                    const int ib = __shfl_sync(0xffffffffu, my_ib, i);
+                    if (valid) {
 #pragma unroll
-                    for (int k = 0; k < NP; ++k) {
-                        size_t off;
-                        if (offimg_of(g, m, n0 + 64 * k + 2 * lane, off)) g.img[off] = v[k].x * g.img_scale;
-                        if (offimg_of(g, m, n0 + 64 * k + 2 * lane + 1, off)) g.img[off] = v[k].y * g.img_scale;
+                        for (int k = 0; k < NP; ++k) {
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int oy = iy + ci[k][e], ox = ix + cj[k][e];
+                                if (ci[k][e] >= 0 && oy < g.img_hc && ox < g.img_wc)
+                                    g.img[(size_t)ib + (size_t)oy * g.img_wc + ox] = (e ? v[k].y : v[k].x) * g.img_scale;
+                            }
+                        }
                     }
                 }
             };
@@ -779,6 +812,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             }
             asm volatile("bar.sync %0, %1;" ::"r"(1 + lg), "n"(32 * WPL) : "memory");   // staging free for the next tile
             my_m = nx_m; my_r32 = nx_r32; my_r16 = nx_r16;
+            img_of(my_m, my_iy, my_ix, my_ib);
         }
         }  // !kStage16
     }
