@@ -354,18 +354,14 @@ attn_block_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 const int hq2 = gw >> 2;
                 float* srow = stg32 + (size_t)lane * AB_SROW32 + hq2 * 96;
                 const uint32_t t_row = tPD + ((uint32_t)(lg * 32) << 16) + (uint32_t)(hq2 * 96);
-                uint32_t va[16], vb[16];
-                tc_ld16_nowait(t_row, va);
+                // three 32-column loads (one round trip each) instead of six 16-column ones: under the other group's
+                // attention arithmetic a tcgen05.ld + wait costs ~250 cycles, and only two warps can drain a lane group
+#pragma unroll 1
+                for (int c = 0; c < 3; ++c) {
+                    uint32_t v[32];
+                    tc_ld32(t_row + 32 * c, v);
 #pragma unroll
-                for (int c = 0; c < 6; c += 2) {
-                    tc_wait_ld16(va);
-                    tc_ld16_nowait(t_row + 16 * (c + 1), vb);
-#pragma unroll
-                    for (int e = 0; e < 16; e += 4) *reinterpret_cast<uint4*>(srow + 16 * c + e) = make_uint4(va[e], va[e + 1], va[e + 2], va[e + 3]);
-                    tc_wait_ld16(vb);
-                    if (c + 2 < 6) tc_ld16_nowait(t_row + 16 * (c + 2), va);
-#pragma unroll
-                    for (int e = 0; e < 16; e += 4) *reinterpret_cast<uint4*>(srow + 16 * (c + 1) + e) = make_uint4(vb[e], vb[e + 1], vb[e + 2], vb[e + 3]);
+                    for (int e = 0; e < 32; e += 4) *reinterpret_cast<uint4*>(srow + 32 * c + e) = make_uint4(v[e], v[e + 1], v[e + 2], v[e + 3]);
                 }
                 tc_fence_before();
                 __syncwarp();
