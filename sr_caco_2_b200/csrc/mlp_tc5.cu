@@ -167,16 +167,18 @@ mlp_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     for (int kb = 0; kb < KB1; ++kb) tma_prefetch_2d(&map_a, kb * 64, (tile + (int)gridDim.x) * 128);
                 }
             };
-            auto load_fc1 = [&](int q) {
-                const int c = q % NC;
-                if (c == 0) load_a(q / NC);
-                load_w1(c);
+            int c1 = 0, t1 = 0;
+            auto load_fc1 = [&](int) {
+                if (c1 == 0) load_a(t1);
+                load_w1(c1);
+                if (++c1 == NC) { c1 = 0; ++t1; }
             };
             if (Q > 0) load_fc1(0);
             if (Q > 1) load_fc1(1);
-            for (int q = 0; q < Q; ++q) {
+            for (int q = 0, c2 = 0; q < Q; ++q) {
                 if (q + 2 < Q) load_fc1(q + 2);
-                load_w2(q % NC);
+                load_w2(c2);
+                if (++c2 == NC) c2 = 0;
             }
             (void)tc;
         }
@@ -212,21 +214,22 @@ mlp_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int Q = n_my * NC;
             // fc1 of chunk q (tile iteration q / NC): the first chunk of a tile waits for its A tile, the last one hands
             // the A buffer back to the producer
-            auto fc1_q = [&](int q) {
-                const int c = q % NC, ti = q / NC;
-                if (c == 0) { mbar_wait(a_full, ti & 1); tc_fence_after(); }
+            // (chunk, tile iteration) of the fc1 and fc2 sequences are carried as counters: no divisions in this loop
+            int c1 = 0, t1 = 0;
+            auto fc1_q = [&](int) {
+                if (c1 == 0) { mbar_wait(a_full, t1 & 1); tc_fence_after(); }
                 fc1();
-                if (c == NC - 1 && elect_one()) tc_commit(a_empty);
+                if (c1 == NC - 1 && elect_one()) tc_commit(a_empty);
                 __syncwarp();
+                if (++c1 == NC) { c1 = 0; ++t1; }
             };
             if (Q > 0) fc1_q(0);
             if (Q > 1) fc1_q(1);
-            for (int q = 0; q < Q; ++q) {
+            for (int q = 0, c = 0, ti = 0; q < Q; ++q) {
                 ML_TR(0, q, 0);
                 trq = q;
                 if (q + 2 < Q) fc1_q(q + 2);                      // two chunks ahead, also across the tile boundary
                 ML_TR(0, q, 1);
-                const int c = q % NC, ti = q / NC;
                 const uint32_t d2 = tD2 + (uint32_t)((ti & 1) * CP);
                 // fc2(q)
                 mbar_wait(h_full(hs), hph);
@@ -247,6 +250,7 @@ mlp_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 __syncwarp();
                 w_next();
                 if (++hs == ML_NH) { hs = 0; hph ^= 1; }
+                if (++c == NC) { c = 0; ++ti; }
             }
             (void)tc;
         }
@@ -283,8 +287,8 @@ mlp_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 *reinterpret_cast<uint4*>(hrow + ((chunk ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
         };
-        for (int q = set, k = 0; q < n_chunks; q += 2, ++k) {
-            const int c = q % NC, hs = q % ML_NH, hu = q / ML_NH;
+        for (int q = set, k = 0, c = set % NC; q < n_chunks; q += 2, ++k) {
+            const int hs = q % ML_NH, hu = q / ML_NH;
             if (lg == 0) ML_TR(1, q, 0);
             mbar_wait(d1_full(set), k & 1);
             tc_fence_after();
@@ -317,6 +321,8 @@ mlp_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             __syncwarp();
             if (lane == 0) mbar_arrive(h_full(hs));
             if (lg == 0) ML_TR(1, q, 3);
+            c += 2;                                                  // chunk index of this set's next chunk
+            while (c >= NC) c -= NC;
         }
     } else {
         // ===================================== final warps =====================================
