@@ -5,10 +5,14 @@
 // Gaussian filter, fp32) and the PSNR_Y of dlib/utils/utils_trainer.py:1005-1012, for the full
 // image and up to 8 ROI thresholds (roi = H8 >= th, utils_trainer.py:986) in the same pass.
 //
-// One CTA owns a 32x32 tile of the border-cropped image: it loads the 42x42 halo tile of E and
-// H once (coalesced rows), accumulates the squared-error / min / max terms for the pixels it
-// owns while loading, runs the separable Gaussian (horizontal then vertical) in shared memory
-// for the five SSIM moments, and reduces with warp shuffles to one fp64 atomic per quantity.
+// Three kernels share the finalize step:
+//   metrics_stream_kernel  the hot path (quantised, nested level-set ROIs): row streaming, a CTA walks a strip of 128
+//                          columns top to bottom with the vertical filter taps in registers (see its header)
+//   metrics_fast_kernel    round 1's version of the same contract, kept as the in-library cross-check: one CTA owns a
+//                          32x32 tile, loads the 42x42 halo tile of E and H once, accumulates the squared-error / min /
+//                          max terms while loading, runs the separable Gaussian in shared memory, reduces with warp
+//                          shuffles to one atomic per quantity
+//   metrics_tile_kernel    the general contract (explicit ROI masks, unquantised inputs, unsorted thresholds), fp64 sums
 #include "common.cuh"
 #include <math.h>
 
