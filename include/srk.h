@@ -105,8 +105,8 @@ size_t srk_metrics_scratch_bytes(int B, int n_ths);
 /* on != 0: the quantised hot path runs the round-1 tile kernel instead of the row-streaming kernel (tests: the two
  * kernels are cross-checked against each other and against the reference known-answer values) */
 int srk_metrics_use_tile_kernel(int on);
-/* on == 0: the 64-output-channel 3x3 / 5x5 convs of the tcgen05 engine fetch one TMA box per tap instead of one halo
- * box per channel block (default on; tests compare the two operand paths) */
+/* on == 0: the 64 -> 64 channel 3x3 / 5x5 convs of the tcgen05 engine fetch one TMA box per tap instead of one halo
+ * box per tile (default on; tests compare the two operand paths) */
 int srk_gemm_conv_halo(int on);
 int srk_metrics(const float* E, const float* H, int B, int Hpx, int Wpx, int border,
                 int quantize, const int* roi_ths, int n_ths, double* out, int32_t* flags,

@@ -125,6 +125,9 @@ if eng == "tcgen05":
     L.load().srk_gemm_conv_halo(1)
 # folded reconstruction tail of cfg3: 5x5 conv 64 -> 64 (= 8 x 8 sub-pixels) with the image epilogue, 32 x (64 x 64) -> 32 x 512 x 512
 At = t16(M, 64, dt=torch.float16); Wt5 = t16(64, 25*64, dt=torch.float16); img = torch.empty(B, 1, 8*H, 8*W, device=dev)
-us = run("tail5", A=At, a_mode=1, conv_k=5, lda=64, nB=B, H=H, W=W, Wt=Wt5, M=M, N=64, K=25*64, dtype=1, bias=bias, img=img, img_s=8, img_scale=1.0, img_hc=8*H, img_wc=8*W)
-report("folded tail 5x5 64->8x8 img", us, 2*M*64*1600, M*(128+256))
+for halo in ((1, 0) if eng == "tcgen05" else (1,)):
+    if eng == "tcgen05": L.load().srk_gemm_conv_halo(halo)
+    us = run("tail5", A=At, a_mode=1, conv_k=5, lda=64, nB=B, H=H, W=W, Wt=Wt5, M=M, N=64, K=25*64, dtype=1, bias=bias, img=img, img_s=8, img_scale=1.0, img_hc=8*H, img_wc=8*W)
+    report(f"folded tail 5x5 64->8x8 img halo={halo}", us, 2*M*64*1600, M*(128+256))
+if eng == "tcgen05": L.load().srk_gemm_conv_halo(1)
 json.dump(rows, open(f"gpurun_out/gemm_bench_{eng}.json", "w"), indent=1)

@@ -363,13 +363,15 @@ def test_gemm_conv3x3_pixelshuffle_and_image_epilogues(L, engine):
     assert float((img.cpu() - exp).abs().max()) < 3e-3 * max(1.0, float(exp.abs().max()))
 
 
-@pytest.mark.parametrize("geom", [(3, 40, 24, 64, 3), (2, 33, 17, 192, 3), (2, 64, 64, 64, 3), (2, 21, 30, 64, 5), (1, 16, 8, 128, 3)])
+@pytest.mark.parametrize("geom", [(3, 40, 24, 64, 3), (2, 33, 17, 64, 3), (40, 64, 64, 64, 3), (2, 21, 30, 64, 5), (1, 16, 8, 64, 3), (2, 24, 24, 192, 3)])
 def test_conv_halo_tiles_equal_per_tap_boxes(L, geom):
     """64-output-channel convs of the tcgen05 engine: ONE halo TMA box per channel block with the taps read as
     shifted-window UMMA descriptors (default) against one TMA box per tap (srk_gemm_conv_halo(0)) and against the
     fp32 convolution.  The two operand paths add the same products in a different order (channel-block major vs
-    tap major): equal to fp32 accumulation noise.  Geometries: ragged tiles in both directions, several channel
-    blocks (streamed weights), a 5x5 window (halo radius 2), exact tiles."""
+    tap major): equal to fp32 accumulation noise.  The halo path is taken by the 64 -> 64 channel convs (the EDSR body,
+    the folded 5x5 tail).  Geometries: ragged tiles in both directions (few tiles: streamed weights), enough tiles for
+    resident weights, a 5x5 window (halo radius 2), a single partial tile; 192 input channels stay on per-tap boxes
+    (both runs identical)."""
     if "tcgen05" not in ENGINES:
         pytest.skip("tcgen05 engine not under test")
     L.set_engine("tcgen05")
