@@ -191,6 +191,34 @@ def test_metrics_streaming_kernel_geometries(L, shape):
         np.testing.assert_allclose(got[:, v, 3], orm["ssim"].double(), atol=2e-5)
 
 
+@pytest.mark.parametrize("case", [(2, 97, 133, 2, ()), (1, 300, 41, 0, (7,)), (1, 23, 501, 5, (250,)), (2, 50, 50, 4, (0, 255))])
+def test_metrics_streaming_kernel_threshold_edge_cases(L, case):
+    """No ROI threshold at all, a single one, thresholds at the ends of the level range (a ROI that is everything /
+    almost nothing): streaming kernel == tile kernel on the integer sums, SSIM to fp32 noise, PSNR / SSIM == oracle."""
+    from sr_caco_2_b200 import utils_image as UI
+    B, Hh, Ww, border, ths = case
+    g = torch.Generator().manual_seed(3 + Hh)
+    H = (torch.rand(B, 1, Hh, Ww, generator=g) * 255).round() / 255
+    E = H + 0.03 * torch.randn(B, 1, Hh, Ww, generator=g)
+    lib = L.load()
+    try:
+        lib.srk_metrics_use_tile_kernel(1)
+        tile = UI.compute_metrics(E.to(DEV), H.to(DEV), border, ths, check=False)["raw"].cpu()
+    finally:
+        lib.srk_metrics_use_tile_kernel(0)
+    got = UI.compute_metrics(E.to(DEV), H.to(DEV), border, ths, check=False)["raw"].cpu()
+    for i in (0, 1, 2, 4):
+        assert torch.equal(got[..., i], tile[..., i]), i
+    assert float((got[..., 3] - tile[..., 3]).abs().max()) < 2e-6
+    om = O.all_metrics(E, H, border)
+    np.testing.assert_allclose(got[:, 0, 0], om["psnr"], rtol=1e-10)
+    np.testing.assert_allclose(got[:, 0, 3], om["ssim"].double(), atol=2e-6)
+    for v, th in enumerate(ths):
+        orm = O.all_metrics(E, H, border, th)
+        np.testing.assert_allclose(got[:, 1 + v, 0], orm["psnr"], rtol=1e-10)
+        np.testing.assert_allclose(got[:, 1 + v, 3], orm["ssim"].double(), atol=2e-6)
+
+
 # ------------------------------------------------------------------------------------------
 # building blocks
 # ------------------------------------------------------------------------------------------
